@@ -1,0 +1,68 @@
+"""Build the CUDA extension in-tree with nvcc for sm_100a (no JIT cache, no torch extension loader).
+
+The resulting ``dxtb_b200/_C.so`` is a plain C-ABI shared library (see ``include/xtb_b200.h``).
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+CSRC = ROOT / "csrc"
+INCLUDE = ROOT.parent / "include"
+SO_PATH = ROOT / "_C.so"
+SOURCES = ["xtb_geometry.cu", "xtb_integrals.cu", "xtb_scf.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "-diag-suppress", "177",
+]
+
+
+def nvcc_path() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and Path(cand).exists():
+            return cand
+    raise RuntimeError("nvcc not found: the dxtb_b200 CUDA extension cannot be built")
+
+
+def needs_build() -> bool:
+    if not SO_PATH.exists():
+        return True
+    t = SO_PATH.stat().st_mtime
+    deps = [CSRC / s for s in SOURCES] + list(CSRC.glob("*.cuh")) + list(INCLUDE.glob("*.h"))
+    return any(d.stat().st_mtime > t for d in deps)
+
+
+def build_extension(force: bool = False, verbose: bool = False) -> Path:
+    """Compile every .cu for sm_100a and link ``_C.so``. Returns the path of the library."""
+    if not force and not needs_build():
+        return SO_PATH
+    nvcc = nvcc_path()
+    objdir = ROOT / "build"
+    objdir.mkdir(exist_ok=True)
+    objs = []
+    procs = []
+    for s in SOURCES:
+        obj = objdir / (s + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, f"-I{INCLUDE}", f"-I{CSRC}", "-c", str(CSRC / s), "-o", str(obj)]
+        if verbose:
+            print(" ".join(cmd))
+        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(str(obj))
+    for s, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {s}:\n{out}")
+        if verbose and out:
+            print(out)
+    cmd = [nvcc, "-shared", "-o", str(SO_PATH), *objs]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}")
+    return SO_PATH
+
+
+if __name__ == "__main__":
+    print(build_extension(force=True, verbose=True))

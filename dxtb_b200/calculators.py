@@ -1,0 +1,349 @@
+"""Drop-in for ``dxtb.calculators.GFN1Calculator`` on the batched fp64 single-point hot path.
+
+Same constructor / ``get_energy`` / ``get_forces`` / ``get_charges`` / ``get_iterations`` / ``reset`` surface as the
+reference (``calculators/gfn1.py:46-70``, ``calculators/types/abc.py:88-170, 429-510``,
+``calculators/types/energy.py:78-441``, ``calculators/types/autograd.py:80-201``); underneath, one
+``torch.autograd.Function`` drives the sm_100a kernels through the C ABI of ``include/xtb_b200.h``.
+Everything outside that path (GFN2, libcint, implicit SCF modes, fields, solvation, float32, CPU) raises
+``NotImplementedError``: there is deliberately no fallback.
+"""
+from __future__ import annotations
+
+import math
+import os
+import warnings
+from typing import Any
+
+import torch
+
+from . import _abi
+from .batch import INT_CUTOFF, BatchDescriptor
+from .exceptions import (DeviceError, DtypeError, MissingD3ReferenceError, SCFConvergenceError,
+                         SCFConvergenceWarning)
+from .param import gfn1_param
+
+__all__ = ["GFN1Calculator", "Calculator"]
+
+# resolved defaults of dxtb (constants/defaults.py)
+DEFAULT_OPTS: dict[str, Any] = {
+    "verbosity": 0,
+    "batch_mode": 0,
+    "maxiter": 100,
+    "mixer": "broyden",  # silently replaced by Anderson in scf_mode "full" (scf/unrolling/base.py:81-99)
+    "damp": 0.5,
+    "damp_init": 0.1,
+    "damp_soft_start": True,
+    "damp_generations": 5,
+    "damp_diagonal_offset": 0.01,
+    "damp_dynamic": False,
+    "guess": "eeq",
+    "scf_mode": "full",
+    "scp_mode": "potential",
+    "x_atol": 1e-4,
+    "x_atol_max": 1e-5,
+    "f_atol": 1e-4,
+    "fermi_etemp": 300.0,
+    "fermi_maxiter": 200,
+    "fermi_thresh": None,
+    "fermi_partition": "equal",
+    "exclude": [],
+    "int_cutoff": INT_CUTOFF,
+    "int_driver": "pytorch",
+    "force_convergence": False,
+    "strict": False,
+}
+_IGNORED_OPTS = {"cache_enabled", "cache_charges", "cache_iterations", "cache_density", "cache_potential",
+                 "cache_coefficients", "cache_mo_energies", "cache_occupation", "cache_overlap", "cache_hcore",
+                 "cache_fock", "timer", "int_level", "int_uplo", "method", "max_element", "grad", "anomaly", "f_atol",
+                 "verbosity", "batch_mode", "damp_dynamic", "damp_dynamic_factor", "log_level", "json"}
+
+_SMEM_LIMIT = 227 * 1024  # per-CTA opt-in shared memory on sm_100
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class _Workspace:
+    """Per-call device buffers (all torch-owned; the C side never allocates)."""
+
+    def __init__(self, d: BatchDescriptor, want_density: bool, scf_opts: _abi.XtbScfOpts):
+        dev, f64 = d.device, torch.float64
+        z = lambda n, dt=f64: torch.zeros(int(n), dtype=dt, device=dev)  # noqa: E731
+        self.cn, self.e_rep, self.e_xb = z(d.nat_tot), z(d.nat_tot), z(d.nat_tot)
+        self.q0_at = z(d.nat_tot)
+        self.gamma = z(d.struct.gam_total)
+        self.S, self.H0 = torch.empty(d.struct.mat_total, dtype=f64, device=dev), torch.empty(d.struct.mat_total, dtype=f64, device=dev)
+        self.q_orb, self.v_orb, self.emo, self.occ = z(d.nao_tot), z(d.nao_tot), z(d.nao_tot), z(d.nao_tot)
+        self.q_sh, self.q_at, self.e_atom = z(d.nsh_tot), z(d.nat_tot), z(d.nat_tot)
+        self.fenergy = z(d.nb)
+        self.iterations, self.status = z(d.nb, torch.int32), z(d.nb, torch.int32)
+        nbytes = _abi.lib().xtb_scf_workspace_bytes(d.ptr, _abi.C.addressof(scf_opts))
+        self.work = torch.empty(int(nbytes) // 8 + 1, dtype=f64, device=dev)
+        if want_density:
+            self.P = torch.empty(d.struct.mat_total, dtype=f64, device=dev)
+            self.W = torch.empty(d.struct.mat_total, dtype=f64, device=dev)
+        else:
+            self.P = self.W = None
+
+
+class _SinglePoint(torch.autograd.Function):
+    """forward = total energies (nb,), backward = analytic dE/dR (converged-SCF gradient)."""
+
+    @staticmethod
+    def forward(ctx, positions: torch.Tensor, chrg: torch.Tensor, spin: torch.Tensor | None, calc: "GFN1Calculator"):
+        d = calc.desc
+        lib = _abi.lib()
+        st = _stream_ptr(d.device)
+        need_grad = bool(ctx.needs_input_grad[0])
+        pos = d.gather_atoms(positions.detach())
+        o = calc._scf_struct(want_density=need_grad)
+        ws = _Workspace(d, need_grad, o)
+        excl = calc._exclude
+
+        _abi.check(lib.xtb_geometry_fwd(d.ptr, pos.data_ptr(), ws.cn.data_ptr(), ws.e_rep.data_ptr(), ws.e_xb.data_ptr(), st), "xtb_geometry_fwd")
+        if calc.opts["guess"] == "eeq":
+            eeq_work = torch.empty(int(d.struct.eeq_total) + 2 * (d.nat_tot + d.nb), dtype=torch.float64, device=d.device)
+            _abi.check(lib.xtb_eeq_guess(d.ptr, pos.data_ptr(), chrg.data_ptr(), eeq_work.data_ptr(), ws.q0_at.data_ptr(), st), "xtb_eeq_guess")
+        if "es2" not in excl:
+            _abi.check(lib.xtb_gamma_fwd(d.ptr, pos.data_ptr(), ws.gamma.data_ptr(), st), "xtb_gamma_fwd")
+        _abi.check(lib.xtb_overlap_h0_fwd(d.ptr, pos.data_ptr(), ws.cn.data_ptr(), ws.S.data_ptr(), ws.H0.data_ptr(), st), "xtb_overlap_h0_fwd")
+
+        nel_ab = calc._electrons(chrg, spin)
+        _abi.check(
+            lib.xtb_scf_run(
+                d.ptr, _abi.C.addressof(o), ws.S.data_ptr(), ws.H0.data_ptr(), ws.gamma.data_ptr(), nel_ab.data_ptr(),
+                ws.q0_at.data_ptr(), ws.work.data_ptr(), ws.q_orb.data_ptr(), ws.q_sh.data_ptr(), ws.q_at.data_ptr(),
+                ws.v_orb.data_ptr(), ws.e_atom.data_ptr(), ws.fenergy.data_ptr(), ws.emo.data_ptr(), ws.occ.data_ptr(),
+                ws.iterations.data_ptr(), ws.status.data_ptr(), ws.P.data_ptr() if need_grad else None,
+                ws.W.data_ptr() if need_grad else None, st,
+            ),
+            "xtb_scf_run",
+        )
+        e_at = ws.e_atom.clone()
+        if "rep" not in excl:
+            e_at += ws.e_rep
+        if "hal" not in excl:
+            e_at += ws.e_xb
+        e_pad = d.scatter_atoms(e_at)
+        energy = e_pad.sum(-1)
+        calc._store(ws, e_pad, nel_ab)
+        if need_grad:
+            ctx.calc = calc
+            ctx.excl_rep = "rep" in excl
+            ctx.save_for_backward(pos, ws.cn, ws.S, ws.P, ws.W, ws.v_orb, ws.q_sh, ws.gamma)
+        return energy
+
+    @staticmethod
+    def backward(ctx, grad_e: torch.Tensor):
+        calc = ctx.calc
+        d = calc.desc
+        pos, cn, S, P, W, v_orb, q_sh, gamma = ctx.saved_tensors
+        ge = grad_e.detach().to(torch.float64).reshape(-1).contiguous()
+        if ge.numel() != d.nb:
+            ge = ge.expand(d.nb).contiguous()
+        grad = torch.empty((d.nat_tot, 3), dtype=torch.float64, device=d.device)
+        dedcn = torch.empty(d.nat_tot, dtype=torch.float64, device=d.device)
+        if ctx.excl_rep:
+            raise NotImplementedError("analytic gradient with exclude=['rep'] is not implemented")
+        _abi.check(
+            _abi.lib().xtb_grad_bwd(d.ptr, pos.data_ptr(), cn.data_ptr(), S.data_ptr(), P.data_ptr(), W.data_ptr(), v_orb.data_ptr(),
+                                    q_sh.data_ptr(), gamma.data_ptr(), ge.data_ptr(), dedcn.data_ptr(), grad.data_ptr(),
+                                    _stream_ptr(d.device)),
+            "xtb_grad_bwd",
+        )
+        return d.scatter_atoms(grad), None, None, None
+
+
+class GFN1Calculator:
+    """GFN1-xTB calculator on one B200 (one instance per GPU shard)."""
+
+    def __init__(self, numbers: torch.Tensor, par: Any = None, *, classical: Any = None, interaction: Any = None,
+                 opts: dict[str, Any] | None = None, device: torch.device | str | None = None,
+                 dtype: torch.dtype | None = None, **kwargs: Any) -> None:
+        if not isinstance(numbers, torch.Tensor):
+            raise TypeError("numbers must be a torch.Tensor")
+        if numbers.dtype not in (torch.int16, torch.int32, torch.int64):  # types/base.py:518-524
+            raise DtypeError(f"Dtype of atomic numbers must be one of int16/int32/int64, but is '{numbers.dtype}'.")
+        if classical is not None or interaction is not None:
+            raise NotImplementedError("additional classical / interaction components are outside the B200 hot path")
+        dtype = dtype or torch.float64
+        if dtype != torch.float64:
+            raise NotImplementedError("the B200 path computes in float64 only")
+        device = torch.device(device) if device is not None else numbers.device
+        if device.type != "cuda":
+            raise NotImplementedError("dxtb_b200 has no CPU path: pass device='cuda' (the CUDA extension is the product)")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device, self.dtype = device, dtype
+        self.numbers = numbers.to(device)
+
+        o = dict(DEFAULT_OPTS)
+        for k, v in (opts or {}).items():
+            if k in o:
+                o[k] = v
+            elif k in _IGNORED_OPTS:
+                continue
+            else:
+                raise KeyError(f"unknown option '{k}'")
+        if str(o["scf_mode"]).lower() not in ("full", "full_tracking", "2"):
+            raise NotImplementedError("only scf_mode='full' (the reference default) is implemented")
+        if str(o["scp_mode"]).lower() not in ("potential", "1"):
+            raise NotImplementedError("only scp_mode='potential' (the reference default) is implemented")
+        if str(o["guess"]).lower() not in ("eeq", "sad"):
+            raise ValueError(f"unknown guess '{o['guess']}'")
+        o["guess"] = str(o["guess"]).lower()
+        mixer = str(o["mixer"]).lower()
+        if mixer in ("broyden", "anderson"):
+            self._mixer = 0
+        elif mixer == "simple":
+            self._mixer = 1
+        else:
+            raise ValueError(f"unknown mixer '{o['mixer']}'")
+        if int(o["damp_generations"]) > 5 or int(o["damp_generations"]) < 1:
+            raise NotImplementedError("damp_generations must be in 1..5")
+        self.opts = o
+        self._exclude = set(o["exclude"] or [])
+        if "all" in self._exclude or "scf" in self._exclude:
+            raise NotImplementedError("exclude=['scf'/'all'] is outside the hot path")
+        if "disp" not in self._exclude and not os.environ.get("DXTB_B200_D3_REFERENCE"):
+            raise MissingD3ReferenceError(
+                "D3(BJ) dispersion needs the reference C6 table that ships with tad-dftd3 (third-party data, not "
+                "available offline). Pass opts={'exclude': ['disp']} (a reference option) for now."
+            )
+        if "disp" not in self._exclude:
+            raise MissingD3ReferenceError("loading an external D3 reference table is not implemented yet")
+
+        self.par = gfn1_param()
+        self.desc = BatchDescriptor(self.numbers, device, self.par, exclude=tuple(self._exclude), int_cutoff=float(o["int_cutoff"]))
+        self.ihelp = self.desc  # index maps live in the descriptor
+        self.cache: dict[str, Any] = {}
+        smem = _abi.lib().xtb_scf_smem_bytes(self.desc.ptr)
+        self._use_smem = 1 if smem <= _SMEM_LIMIT else 0
+
+    # ------------------------------------------------------------------------------------------
+    def _scf_struct(self, want_density: bool) -> _abi.XtbScfOpts:
+        o, s = self.opts, _abi.XtbScfOpts()
+        s.maxiter = int(o["maxiter"])
+        s.mixer = self._mixer
+        s.generations = int(o["damp_generations"])
+        s.soft_start = 1 if o["damp_soft_start"] else 0
+        s.fermi_maxiter = int(o["fermi_maxiter"])
+        s.want_density = 1 if want_density else 0
+        s.use_smem = self._use_smem
+        s.jacobi_max_sweeps = 30
+        s.damp, s.damp_init = float(o["damp"]), float(o["damp_init"])
+        s.diag_offset = float(o["damp_diagonal_offset"])
+        s.x_atol, s.x_atol_max = float(o["x_atol"]), float(o["x_atol_max"])
+        s.kt = float(o["fermi_etemp"]) * self.par.KELVIN2AU  # scf/base.py:291
+        s.fermi_thresh = math.sqrt(torch.finfo(torch.float64).eps) if o["fermi_thresh"] is None else float(o["fermi_thresh"])
+        s.jacobi_tol = 1e-13
+        return s
+
+    def _electrons(self, chrg: torch.Tensor, spin: torch.Tensor | None) -> torch.Tensor:
+        """alpha/beta electron numbers on device (scf/iterator.py:172-176, wavefunction/filling.py:41-120)."""
+        if not hasattr(self, "_nel0"):
+            self._nel0 = torch.from_numpy(self.desc.nel0).to(self.device)
+        nel = self._nel0 - chrg
+        par = torch.remainder(nel.round(), 2)
+        if spin is None:
+            nuhf = par
+        else:
+            uhf = spin.to(nel)
+            nuhf = torch.where(torch.remainder(uhf, 2) == par, uhf, par)
+        diff = torch.minimum(nuhf, nel)
+        nb_ = (nel - diff) / 2.0
+        return torch.stack([nb_ + diff, nb_], dim=-1).round().contiguous()  # scf/base.py:878
+
+    def _prep(self, positions: torch.Tensor, chrg: Any, spin: Any):
+        if not isinstance(positions, torch.Tensor):
+            raise TypeError("positions must be a torch.Tensor")
+        if positions.dtype != self.dtype:
+            raise DtypeError(f"Dtype of positions ({positions.dtype}) does not match the calculator ({self.dtype}).")
+        if positions.device != self.device:
+            raise DeviceError(f"Device of positions ({positions.device}) does not match the calculator ({self.device}).")
+        if positions.shape != (*self.numbers.shape, 3):
+            raise ValueError(f"Shape of positions {tuple(positions.shape)} is not consistent with numbers {tuple(self.numbers.shape)}.")
+        nb = self.desc.nb
+        chrg_t = torch.as_tensor(chrg, dtype=torch.float64, device=self.device).reshape(-1)
+        if chrg_t.numel() == 1:
+            chrg_t = chrg_t.expand(nb)
+        if chrg_t.numel() != nb:
+            raise ValueError("chrg must be a scalar or have one entry per molecule")
+        spin_t = None
+        if spin is not None:
+            spin_t = torch.as_tensor(spin, dtype=torch.float64, device=self.device).reshape(-1)
+            if spin_t.numel() == 1:
+                spin_t = spin_t.expand(nb)
+        return chrg_t.contiguous(), spin_t
+
+    def _store(self, ws: _Workspace, e_pad: torch.Tensor, nel_ab: torch.Tensor) -> None:
+        status = ws.status.cpu()  # the single D2H sync of a single point
+        self.cache = {"energy_atom": e_pad, "ws": ws, "status": status}
+        if (status & _abi.STATUS_FERMI_FAILED).any():
+            raise RuntimeError("Fermi energy failed to converge.")  # wavefunction/filling.py:366
+        if (status & _abi.STATUS_S_NOT_POSDEF).any():
+            raise RuntimeError("Overlap matrix is not positive definite.")
+        if (status & _abi.STATUS_JACOBI_NOT_CONVERGED).any():
+            raise RuntimeError("Jacobi eigensolver did not converge.")
+        bad = (status & _abi.STATUS_SCF_NOT_CONVERGED).nonzero().reshape(-1).tolist()
+        if bad:
+            msg = (f"SCF does not converge after {self.opts['maxiter']} cycles; {len(bad)} systems did not converge ({bad}).")
+            if self.opts["force_convergence"]:
+                raise SCFConvergenceError(msg)
+            warnings.warn(msg, SCFConvergenceWarning)
+
+    # ---- reference API ------------------------------------------------------------------------------
+    def energy(self, positions: torch.Tensor, chrg: Any = 0, spin: Any = None, **_: Any) -> torch.Tensor:
+        chrg_t, spin_t = self._prep(positions, chrg, spin)
+        e = _SinglePoint.apply(positions, chrg_t, spin_t, self)
+        return e[0] if self.desc.single else e
+
+    def get_energy(self, positions: torch.Tensor, chrg: Any = 0, spin: Any = None, **kw: Any) -> torch.Tensor:
+        return self.energy(positions, chrg, spin, **kw)
+
+    def forces(self, positions: torch.Tensor, chrg: Any = 0, spin: Any = None, grad_mode: str = "autograd", **_: Any) -> torch.Tensor:
+        if not positions.requires_grad:  # calculators/types/decorators.py:63-82
+            raise RuntimeError("Position tensor needs ``requires_grad=True``.")
+        e = self.energy(positions, chrg, spin)
+        (g,) = torch.autograd.grad(e.sum(), positions)
+        return -g
+
+    def get_forces(self, positions: torch.Tensor, chrg: Any = 0, spin: Any = None, grad_mode: str = "autograd", **kw: Any) -> torch.Tensor:
+        return self.forces(positions, chrg, spin, grad_mode=grad_mode, **kw)
+
+    def forces_analytical(self, positions: torch.Tensor, chrg: Any = 0, spin: Any = None, **kw: Any) -> torch.Tensor:
+        p = positions.detach().clone().requires_grad_(True)
+        return self.forces(p, chrg, spin, **kw)
+
+    def _ensure(self, positions, chrg, spin):
+        if positions is not None:
+            with torch.no_grad():
+                self.energy(positions, chrg, spin)
+        if "ws" not in self.cache:
+            raise RuntimeError("no single point has been calculated yet")
+        return self.cache["ws"]
+
+    def get_charges(self, positions: torch.Tensor | None = None, chrg: Any = 0, spin: Any = None, **_: Any) -> torch.Tensor:
+        """Orbital-resolved Mulliken partial charges (calculators/types/abc.py:429-486)."""
+        return self.desc.scatter_orbitals(self._ensure(positions, chrg, spin).q_orb)
+
+    def get_mulliken_charges(self, positions: torch.Tensor | None = None, chrg: Any = 0, spin: Any = None, **_: Any) -> torch.Tensor:
+        """Atom-resolved Mulliken charges (ihelp.reduce_orbital_to_atom of ``get_charges``)."""
+        return self.desc.scatter_atoms(self._ensure(positions, chrg, spin).q_at)
+
+    def get_iterations(self, positions: torch.Tensor | None = None, chrg: Any = 0, spin: Any = None, **_: Any) -> torch.Tensor:
+        """Per-molecule number of SCF map evaluations (the reference reports max over the batch, scf/base.py:665)."""
+        return self._ensure(positions, chrg, spin).iterations.clone()
+
+    def get_mo_energies(self, positions: torch.Tensor | None = None, chrg: Any = 0, spin: Any = None, **_: Any) -> torch.Tensor:
+        return self.desc.scatter_orbitals(self._ensure(positions, chrg, spin).emo)
+
+    def get_occupation(self, positions: torch.Tensor | None = None, chrg: Any = 0, spin: Any = None, **_: Any) -> torch.Tensor:
+        return self.desc.scatter_orbitals(self._ensure(positions, chrg, spin).occ)
+
+    def reset(self) -> None:
+        self.cache = {}
+
+
+Calculator = GFN1Calculator

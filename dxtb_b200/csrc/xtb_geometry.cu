@@ -1,0 +1,295 @@
+// Geometry-only stages of the GFN1-xTB single point: coordination number, repulsion, halogen bond,
+// shell-resolved Coulomb matrix and the EEQ guess.  One CTA per molecule; all O(nat^2) and
+// HBM/L2-trivial (positions of one molecule fit in L1), so the kernels are latency-bound by design.
+#include "xtb_common.cuh"
+
+using namespace xtb;
+
+// ---------------------------------------------------------------------------------------------
+// CN (tad-mctc cn_d3 + exp_count; xtb/gfn1.py:57-64), repulsion (classicals/repulsion/base.py:269-334),
+// halogen bond (classicals/halogen/hal.py:209-364)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_geometry(const xtb_batch b, const double* __restrict__ pos, double* __restrict__ cn,
+                           double* __restrict__ erep, double* __restrict__ exb) {
+  const int m = blockIdx.x;
+  const int a0 = b.at_off[m], na = b.at_off[m + 1] - a0;
+  const double* p = pos + 3 * (size_t)a0;
+  for (int a = threadIdx.x; a < na; a += blockDim.x) {
+    const double* pa = b.at_par + (size_t)(a0 + a) * XTB_ATPAR;
+    const double xa = p[3 * a], ya = p[3 * a + 1], za = p[3 * a + 2];
+    double cna = 0.0, er = 0.0;
+    for (int c = 0; c < na; ++c) {
+      if (c == a) continue;
+      const double* pc = b.at_par + (size_t)(a0 + c) * XTB_ATPAR;
+      const double d = safe_dist(xa - p[3 * c], ya - p[3 * c + 1], za - p[3 * c + 2]);
+      if (d <= b.cn_cutoff) {
+        const double r0 = pa[XTB_AT_RCOV] + pc[XTB_AT_RCOV];
+        cna += 1.0 / (1.0 + exp(-b.kcn_d3 * (r0 / d - 1.0)));
+      }
+      if (d <= b.rep_cutoff) {
+        const double al = sqrt(pa[XTB_AT_AREP] * pc[XTB_AT_AREP] + kTiny);
+        er += pa[XTB_AT_ZEFF] * pc[XTB_AT_ZEFF] * exp(-al * pow(d, b.rep_kexp)) / d;
+      }
+    }
+    cn[a0 + a] = cna;
+    erep[a0 + a] = 0.5 * er;
+
+    double ex = 0.0;
+    const int z = b.at_z[a0 + a];
+    if (z == 17 || z == 35 || z == 53 || z == 85) {
+      // nearest neighbour of the halogen (hal.py:253-266)
+      int kb = 0;
+      double dbest = 1.79769313486231570e308;
+      for (int k = 0; k < na; ++k) {
+        const double dx = xa - p[3 * k], dy = ya - p[3 * k + 1], dz = za - p[3 * k + 2];
+        const double r1 = sqrt(dx * dx + dy * dy + dz * dz);
+        if (r1 > 0.0 && r1 < dbest) { kb = k; dbest = r1; }
+      }
+      const double d2xk = dbest * dbest;
+      for (int j = 0; j < na; ++j) {
+        const int zj = b.at_z[a0 + j];
+        if (!(zj == 7 || zj == 8 || zj == 15 || zj == 16)) continue;
+        const double dx = p[3 * j] - xa, dy = p[3 * j + 1] - ya, dz = p[3 * j + 2] - za;
+        const double d2xj = dx * dx + dy * dy + dz * dz;
+        if (sqrt(d2xj) > b.xb_cutoff) continue;
+        const double kx = p[3 * kb] - p[3 * j], ky = p[3 * kb + 1] - p[3 * j + 1], kz = p[3 * kb + 2] - p[3 * j + 2];
+        const double d2kj = kx * kx + ky * ky + kz * kz;
+        const double r0 = (pa[XTB_AT_RAD] + b.at_par[(size_t)(a0 + j) * XTB_ATPAR + XTB_AT_RAD]) * b.xb_rscale;
+        const double lj6 = pow(r0 / sqrt(d2xj), 6.0);
+        const double lj12 = lj6 * lj6;
+        const double lj = (lj12 - b.xb_damp * lj6) / (1.0 + lj12);
+        const double cosa = (d2xk + d2xj - d2kj) / sqrt(d2xk * d2xj);
+        ex += lj * pow(0.5 - 0.25 * cosa, 6.0) * pa[XTB_AT_XBOND];
+      }
+    }
+    exb[a0 + a] = ex;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// shell-resolved Coulomb matrix, harmonic average, gexp = 2 (coulomb/secondorder.py:799-870)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_gamma(const xtb_batch b, const double* __restrict__ pos, double* __restrict__ gamma) {
+  const int m = blockIdx.y;
+  const int s0 = b.sh_off[m], ns = b.sh_off[m + 1] - s0;
+  const int a0 = b.at_off[m];
+  double* g = gamma + b.gam_off[m];
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ns * ns; t += gridDim.x * blockDim.x) {
+    const int k = t / ns, l = t - k * ns;
+    const int A = b.sh_atom[s0 + k], B = b.sh_atom[s0 + l];
+    double dg = kEps;
+    if (A != B) {
+      const double* pa = pos + 3 * (size_t)(a0 + A);
+      const double* pb = pos + 3 * (size_t)(a0 + B);
+      const double d = safe_dist(pa[0] - pb[0], pa[1] - pb[1], pa[2] - pb[2]) + kEps;
+      dg = d * d;
+    }
+    const double hk = 1.0 / (b.sh_par[(size_t)(s0 + k) * XTB_SHPAR + XTB_SH_ETA] + kEps);
+    const double hl = 1.0 / (b.sh_par[(size_t)(s0 + l) * XTB_SHPAR + XTB_SH_ETA] + kEps);
+    const double avg = 2.0 / (hk + hl);
+    g[t] = 1.0 / sqrt(dg + 1.0 / (avg * avg));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// EEQ guess charges (tad-multicharge get_eeq_charges; scf/guess.py:118-120).
+// (nat+1)^2 saddle-point system per molecule, LU with partial pivoting inside one CTA.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_eeq(const xtb_batch b, const double* __restrict__ pos, const double* __restrict__ chrg,
+                      double* __restrict__ work, double* __restrict__ qat) {
+  __shared__ double red[32];
+  __shared__ int redi[32];
+  __shared__ int s_piv;
+  const int m = blockIdx.x;
+  const int a0 = b.at_off[m], na = b.at_off[m + 1] - a0;
+  const int n = na + 1;
+  double* A = work + b.eeq_off[m];
+  double* rhs = work + b.eeq_total + 2 * (size_t)(a0 + m);
+  double* x = rhs + n;
+  const double* p = pos + 3 * (size_t)a0;
+  const double kcn = 7.5, cn_max = 8.0, cn_cut = 25.0;
+
+  // erf-counting CN, cut at cn_max (tad-mctc cn_eeq)
+  for (int a = threadIdx.x; a < na; a += blockDim.x) {
+    const double* pa = b.at_par + (size_t)(a0 + a) * XTB_ATPAR;
+    double c = 0.0;
+    for (int j = 0; j < na; ++j) {
+      if (j == a) continue;
+      const double d = safe_dist(p[3 * a] - p[3 * j], p[3 * a + 1] - p[3 * j + 1], p[3 * a + 2] - p[3 * j + 2]);
+      if (d <= cn_cut) {
+        const double r0 = pa[XTB_AT_RCOV] + b.at_par[(size_t)(a0 + j) * XTB_ATPAR + XTB_AT_RCOV];
+        c += 0.5 * (1.0 + erf(-kcn * (d / r0 - 1.0)));
+      }
+    }
+    c = log(1.0 + exp(cn_max)) - log(1.0 + exp(cn_max - c));
+    rhs[a] = -pa[XTB_AT_EEQ_CHI] + sqrt(fmax(c, kEps)) * pa[XTB_AT_EEQ_KCN];
+  }
+  if (threadIdx.x == 0) rhs[na] = chrg[m];
+  for (int t = threadIdx.x; t < n * n; t += blockDim.x) {
+    const int i = t / n, j = t - i * n;
+    double v;
+    if (i == na || j == na) {
+      v = (i == j) ? 0.0 : 1.0;
+    } else {
+      const double ri = b.at_par[(size_t)(a0 + i) * XTB_ATPAR + XTB_AT_EEQ_RAD];
+      if (i == j) {
+        v = b.at_par[(size_t)(a0 + i) * XTB_ATPAR + XTB_AT_EEQ_ETA] + sqrt(2.0 / kPi) / ri;
+      } else {
+        const double rj = b.at_par[(size_t)(a0 + j) * XTB_ATPAR + XTB_AT_EEQ_RAD];
+        const double d = safe_dist(p[3 * i] - p[3 * j], p[3 * i + 1] - p[3 * j + 1], p[3 * i + 2] - p[3 * j + 2]);
+        v = erf(d / sqrt(ri * ri + rj * rj)) / d;
+      }
+    }
+    A[t] = v;
+  }
+  __syncthreads();
+
+  // LU with partial pivoting (LAPACK dgesv order of operations), rhs carried along
+  for (int k = 0; k < n; ++k) {
+    double best = -1.0;
+    int bi = k;
+    for (int i = k + threadIdx.x; i < n; i += blockDim.x) {
+      const double v = fabs(A[(size_t)i * n + k]);
+      if (v > best) { best = v; bi = i; }
+    }
+    // block argmax (first index wins on ties, as idamax)
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = best; redi[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double bb = red[0];
+      int ii = redi[0];
+      for (int w = 1; w < (int)((blockDim.x + 31) >> 5); ++w)
+        if (red[w] > bb || (red[w] == bb && redi[w] < ii)) { bb = red[w]; ii = redi[w]; }
+      s_piv = ii;
+    }
+    __syncthreads();
+    const int piv = s_piv;
+    if (piv != k) {
+      for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        const double t1 = A[(size_t)k * n + j];
+        A[(size_t)k * n + j] = A[(size_t)piv * n + j];
+        A[(size_t)piv * n + j] = t1;
+      }
+      if (threadIdx.x == 0) { const double t1 = rhs[k]; rhs[k] = rhs[piv]; rhs[piv] = t1; }
+    }
+    __syncthreads();
+    const double dkk = A[(size_t)k * n + k];
+    const int rem = n - k - 1;
+    // eliminate rows i>k; column k itself is kept (multipliers are recomputed, never overwritten here)
+    for (int t = threadIdx.x; t < rem * (rem + 1); t += blockDim.x) {
+      const int i = k + 1 + t / (rem + 1), jj = t % (rem + 1);
+      const double f = A[(size_t)i * n + k] / dkk;
+      if (jj == rem) rhs[i] -= f * rhs[k];
+      else A[(size_t)i * n + k + 1 + jj] -= f * A[(size_t)k * n + k + 1 + jj];
+    }
+    __syncthreads();
+  }
+  // back substitution (column oriented)
+  for (int i = n - 1; i >= 0; --i) {
+    const double xi = rhs[i] / A[(size_t)i * n + i];
+    __syncthreads();
+    if (threadIdx.x == 0) x[i] = xi;
+    for (int j = threadIdx.x; j < i; j += blockDim.x) rhs[j] -= A[(size_t)j * n + i] * xi;
+    __syncthreads();
+  }
+  for (int a = threadIdx.x; a < na; a += blockDim.x) qat[a0 + a] = x[a];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Atom-pair part of the analytic gradient: repulsion (repulsion/base.py:337-406), second-order
+// electrostatics with fixed charges (secondorder.py:873-926) and the CN chain rule
+// (ncoord/utils.py:30-52 with the exp-count derivative).  One CTA per molecule.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_grad_atoms(const xtb_batch b, const double* __restrict__ pos, const double* __restrict__ q_sh,
+                             const double* __restrict__ gamma, const double* __restrict__ dedcn,
+                             const double* __restrict__ ge, double* __restrict__ grad) {
+  const int m = blockIdx.x;
+  const int a0 = b.at_off[m], na = b.at_off[m + 1] - a0;
+  const int s0 = b.sh_off[m], ns = b.sh_off[m + 1] - s0;
+  const double* p = pos + 3 * (size_t)a0;
+  const double* g = gamma + b.gam_off[m];
+  const double scale = ge[m];
+  for (int a = threadIdx.x; a < na; a += blockDim.x) {
+    const double* pa = b.at_par + (size_t)(a0 + a) * XTB_ATPAR;
+    const int sa0 = b.at_sh0[a0 + a], nsa = b.at_nsh[a0 + a];
+    double gx = 0.0, gy = 0.0, gz = 0.0;
+    for (int c = 0; c < na; ++c) {
+      if (c == a) continue;
+      const double* pc = b.at_par + (size_t)(a0 + c) * XTB_ATPAR;
+      const double dx = p[3 * a] - p[3 * c], dy = p[3 * a + 1] - p[3 * c + 1], dz = p[3 * a + 2] - p[3 * c + 2];
+      const double d = safe_dist(dx, dy, dz);
+      double f = 0.0;  // dE/dR_A = f * (R_A - R_C)
+      if (d <= b.rep_cutoff) {
+        const double al = sqrt(pa[XTB_AT_AREP] * pc[XTB_AT_AREP] + kTiny);
+        const double r1k = pow(d, b.rep_kexp);
+        const double e = pa[XTB_AT_ZEFF] * pc[XTB_AT_ZEFF] * exp(-al * r1k) / d;
+        f += -(al * r1k * b.rep_kexp + 1.0) * e / (d * d);
+      }
+      if (d <= b.cn_cutoff) {
+        const double r0 = pa[XTB_AT_RCOV] + pc[XTB_AT_RCOV];
+        const double ex = exp(-b.kcn_d3 * (r0 / d - 1.0));
+        const double dcf = -b.kcn_d3 * r0 / (d * d) * ex / ((1.0 + ex) * (1.0 + ex));
+        f += (dedcn[a0 + a] + dedcn[a0 + c]) * dcf / d;
+      }
+      // ES2: sum over shells of A and C of -gamma^3 q q
+      const int sc0 = b.at_sh0[a0 + c], nsc = b.at_nsh[a0 + c];
+      double es = 0.0;
+      for (int k = 0; k < nsa; ++k)
+        for (int l = 0; l < nsc; ++l) {
+          const double gm = g[(size_t)(sa0 + k) * ns + sc0 + l];
+          es -= gm * gm * gm * q_sh[s0 + sa0 + k] * q_sh[s0 + sc0 + l];
+        }
+      f += es;
+      gx += f * dx; gy += f * dy; gz += f * dz;
+    }
+    atomicAdd(&grad[3 * (size_t)(a0 + a)], scale * gx);
+    atomicAdd(&grad[3 * (size_t)(a0 + a) + 1], scale * gy);
+    atomicAdd(&grad[3 * (size_t)(a0 + a) + 2], scale * gz);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" int xtb_version(void) { return 100; }
+extern "C" int xtb_sizeof_batch(void) { return (int)sizeof(xtb_batch); }
+extern "C" int xtb_sizeof_scf_opts(void) { return (int)sizeof(xtb_scf_opts); }
+
+extern "C" int xtb_geometry_fwd(const xtb_batch* b, const double* pos, double* cn, double* e_rep, double* e_xb,
+                                void* stream) {
+  if (!b || !pos || !cn || !e_rep || !e_xb) return -1;
+  if (b->nb == 0) return 0;
+  k_geometry<<<b->nb, 128, 0, (cudaStream_t)stream>>>(*b, pos, cn, e_rep, e_xb);
+  return launch_status();
+}
+
+extern "C" int xtb_eeq_guess(const xtb_batch* b, const double* pos, const double* chrg, double* work, double* q_at,
+                             void* stream) {
+  if (!b || !pos || !chrg || !work || !q_at) return -1;
+  if (b->nb == 0) return 0;
+  k_eeq<<<b->nb, 256, 0, (cudaStream_t)stream>>>(*b, pos, chrg, work, q_at);
+  return launch_status();
+}
+
+extern "C" int xtb_gamma_fwd(const xtb_batch* b, const double* pos, double* gamma, void* stream) {
+  if (!b || !pos || !gamma) return -1;
+  if (b->nb == 0) return 0;
+  if (b->gexp != 2.0) return -2;
+  const int nt = 256;
+  int gx = (b->nsh_max * b->nsh_max + nt - 1) / nt;
+  if (gx > 64) gx = 64;
+  k_gamma<<<dim3(gx, b->nb), nt, 0, (cudaStream_t)stream>>>(*b, pos, gamma);
+  return launch_status();
+}
+
+// used by xtb_grad_bwd (xtb_integrals.cu)
+int xtb_launch_grad_atoms(const xtb_batch* b, const double* pos, const double* q_sh, const double* gamma,
+                          const double* dedcn, const double* ge, double* grad, cudaStream_t st) {
+  k_grad_atoms<<<b->nb, 128, 0, st>>>(*b, pos, q_sh, gamma, dedcn, ge, grad);
+  return launch_status();
+}

@@ -1,0 +1,653 @@
+// On-device self-consistent field loop of the GFN1-xTB single point: ONE CTA PER MOLECULE runs the whole
+// SCF (Fock build, eigensolve, Fermi filling, density, Mulliken populations, ES2/ES3 potential, Anderson
+// mixing, per-molecule convergence, final energies) with no host round trip.
+//
+// Eigensolver: the generalised problem F C = S C eps is solved in the S-orthonormal basis of the previous
+// iteration's eigenvectors (C^T S C = I), i.e. A = C^T F C is nearly diagonal after the first iterations
+// and a cyclic parallel-order Jacobi (round-robin pairing, all n/2 rotations of a round applied in one
+// conflict-free pass over 2x2 blocks) converges in 2-3 sweeps instead of 6-8.  The rotations are applied
+// to C directly, so no separate back-transformation is needed.  The first basis is S^{-1/2}-like
+// (eigenvectors of S scaled by 1/sqrt(eigenvalue)), obtained with the same Jacobi routine.
+//
+// Matrices (C, A/F, X/P) live in shared memory when 3*ne*ld*8 B fit (nao <= ~96), otherwise in a global
+// workspace (L2-resident for the active CTAs).  Leading dimension ld is odd so that both row and column
+// accesses of fp64 data are bank-conflict free.
+#include "xtb_common.cuh"
+
+using namespace xtb;
+
+namespace {
+
+constexpr int NT = 512;  // threads per CTA
+
+struct Ctx {
+  int n, ne, ld, ns, na, np;
+  int o0, s0, a0;
+  double *C, *A, *X;             // ne x ld matrices (shared or global)
+  const double *S, *H0, *gam;    // global, n x n / ns x ns
+  double *eps, *srt, *focc, *v, *vnew, *q, *n0, *eorb, *qsh, *vsh, *qat, *red, *cs;
+  int *pp, *qq, *occl;
+  const int *ao_sh, *sh_atom, *at_sh0, *at_nsh, *sh_ao, *sh_l;
+  const double* gam3;            // at_par base (stride XTB_ATPAR)
+  double *xh, *fh;               // Anderson history [gen+1][n] (global)
+  int status;
+};
+
+// Out[i][j] = sum_{k<K} L[k*ld+i] * R[k*ld+j], i,j < ne; 4x4 register tiles.
+__device__ void gemm_tn(int ne, int K, const double* __restrict__ L, const double* __restrict__ R, int ld, double* __restrict__ Out,
+                        int ldo, int nout) {
+  const int nt4 = (ne + 3) >> 2;
+  for (int t = threadIdx.x; t < nt4 * nt4; t += NT) {
+    const int ti = t / nt4, tj = t - ti * nt4;
+    const int i0 = ti << 2, j0 = tj << 2;
+    double acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
+    // ne is even and ld = ne + 1, so i0+3 <= ne+1 may touch the pad column: it is kept zero / ignored
+    for (int k = 0; k < K; ++k) {
+      const double* lr = L + (size_t)k * ld + i0;
+      const double* rr = R + (size_t)k * ld + j0;
+      double a[4], bv[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) a[r] = (i0 + r < ne) ? lr[r] : 0.0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) bv[c] = (j0 + c < ne) ? rr[c] : 0.0;
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = fma(a[r], bv[c], acc[r][c]);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (i0 + r < nout && j0 + c < nout) Out[(size_t)(i0 + r) * ldo + j0 + c] = acc[r][c];
+  }
+  __syncthreads();
+}
+
+// Cyclic Jacobi with round-robin parallel ordering on the symmetric ne x ne matrix A (full storage),
+// accumulating the rotations into the columns of V (nrow rows).  Returns the number of sweeps, or
+// -sweeps if the off-diagonal did not drop below tol.
+__device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, int nrow, double tol, int maxsweeps) {
+  const int ne = c.ne, ld = c.ld, np = c.np;
+  int sweep = 0;
+  // already diagonal?  (converged SCF: the warm-started matrix needs no rotation at all)
+  for (;;) {
+    double off = 0.0;
+    for (int t = threadIdx.x; t < ne * ne; t += NT) {
+      const int i = t / ne, j = t - i * ne;
+      if (i != j) off = fmax(off, fabs(A[(size_t)i * ld + j]));
+    }
+    off = block_max(off, c.red);
+    if (off <= tol) return sweep;
+    if (sweep >= maxsweeps) return -sweep;
+    ++sweep;
+    for (int r = 0; r < ne - 1; ++r) {
+      for (int k = threadIdx.x; k < np; k += NT) {
+        int p, q;
+        if (k == 0) { p = r; q = ne - 1; }
+        else { p = (r + k) % (ne - 1); q = (r - k + ne - 1) % (ne - 1); }
+        if (p > q) { const int t = p; p = q; q = t; }
+        const double app = A[(size_t)p * ld + p], aqq = A[(size_t)q * ld + q], apq = A[(size_t)p * ld + q];
+        double cc = 1.0, ss = 0.0;
+        if (apq != 0.0) {
+          const double tau = (aqq - app) / (2.0 * apq);
+          const double t = copysign(1.0, tau) / (fabs(tau) + sqrt(1.0 + tau * tau));
+          cc = 1.0 / sqrt(1.0 + t * t);
+          ss = t * cc;
+        }
+        c.pp[k] = p; c.qq[k] = q; c.cs[2 * k] = cc; c.cs[2 * k + 1] = ss;
+      }
+      __syncthreads();
+      // A <- J^T A J on disjoint 2x2 blocks (pair kp) x (pair kq)
+      for (int t = threadIdx.x; t < np * np; t += NT) {
+        const int kp = t / np, kq = t - kp * np;
+        const int p1 = c.pp[kp], q1 = c.qq[kp], p2 = c.pp[kq], q2 = c.qq[kq];
+        const double c1 = c.cs[2 * kp], s1 = c.cs[2 * kp + 1], c2 = c.cs[2 * kq], s2 = c.cs[2 * kq + 1];
+        double* r0 = A + (size_t)p1 * ld;
+        double* r1 = A + (size_t)q1 * ld;
+        const double a00 = r0[p2], a01 = r0[q2], a10 = r1[p2], a11 = r1[q2];
+        const double x00 = c1 * a00 - s1 * a10, x01 = c1 * a01 - s1 * a11;
+        const double x10 = s1 * a00 + c1 * a10, x11 = s1 * a01 + c1 * a11;
+        double y00 = c2 * x00 - s2 * x01, y01 = s2 * x00 + c2 * x01;
+        double y10 = c2 * x10 - s2 * x11, y11 = s2 * x10 + c2 * x11;
+        if (kp == kq) { y01 = 0.0; y10 = 0.0; }
+        r0[p2] = y00; r0[q2] = y01; r1[p2] = y10; r1[q2] = y11;
+      }
+      // V <- V J
+      for (int t = threadIdx.x; t < nrow * np; t += NT) {
+        const int i = t / np, k = t - i * np;
+        const int p = c.pp[k], q = c.qq[k];
+        const double cc = c.cs[2 * k], ss = c.cs[2 * k + 1];
+        double* row = V + (size_t)i * ld;
+        const double vp = row[p], vq = row[q];
+        row[p] = cc * vp - ss * vq;
+        row[q] = ss * vp + cc * vq;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// Fermi smearing, both spin channels in lockstep (wavefunction/filling.py:201-366).
+// focc[k] = f_alpha + f_beta; returns G = kT sum ln(f^f (1-f)^(1-f)) (scf/base.py:586-594).
+__device__ double fermi_fill(Ctx& c, double nel_a, double nel_b, const xtb_scf_opts& o) {
+  const int n = c.n;
+  // rank sort of the eigenvalues (ascending; ties broken by index)
+  for (int k = threadIdx.x; k < n; k += NT) {
+    const double e = c.eps[k];
+    int rk = 0;
+    for (int j = 0; j < n; ++j) {
+      const double ej = c.eps[j];
+      rk += (ej < e) || (ej == e && j < k);
+    }
+    c.srt[rk] = e;
+  }
+  __syncthreads();
+  double nel[2] = {nel_a, nel_b}, ef[2], ef_used[2], hom[2];
+  bool ne_[2];
+  if (fabs(nel_a + nel_b) < kEps) {
+    for (int k = threadIdx.x; k < n; k += NT) c.focc[k] = 0.0;
+    __syncthreads();
+    return 0.0;
+  }
+  if (o.kt < 3e-7) {  // aufbau (scf/base.py:889)
+    for (int k = threadIdx.x; k < n; k += NT) {
+      const double e = c.eps[k];
+      int rk = 0;
+      for (int j = 0; j < n; ++j) rk += (c.eps[j] < e) || (c.eps[j] == e && j < k);
+      c.focc[k] = (rk < nel_a ? 1.0 : 0.0) + (rk < nel_b ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    return 0.0;
+  }
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    int h = (int)ceil(nel[s] - 5.0e-15) - 1;
+    if (h < 0) h = 0;
+    if (h > n - 1) h = 0;
+    const int l = (n - 1 <= h) ? h : h + 1;
+    hom[s] = (double)h;
+    ne_[s] = nel[s] != 0.0;
+    ef[s] = ne_[s] ? 0.5 * (c.srt[h] + c.srt[l]) : 0.0;
+    ef_used[s] = ef[s];
+  }
+  bool conv = false;
+  for (int it = 0; it < o.fermi_maxiter; ++it) {
+    double sf[2] = {0.0, 0.0}, sd[2] = {0.0, 0.0};
+    for (int k = threadIdx.x; k < n; k += NT) {
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const double e = ne_[s] ? c.eps[k] : 0.0;
+        const double ex = (e - ef[s]) / o.kt;
+        if (ex < 50.0) {
+          const double et = exp(ex);
+          sf[s] += 1.0 / (et + 1.0);
+          sd[s] += et / (o.kt * (et + 1.0) * (et + 1.0));
+        } else {
+          sd[s] += kEps;
+        }
+      }
+    }
+    const double f0 = block_sum(sf[0], c.red), f1 = block_sum(sf[1], c.red);
+    const double d0 = block_sum(sd[0], c.red), d1 = block_sum(sd[1], c.red);
+    const double r0 = hom[0] - f0 + 1.0, r1 = hom[1] - f1 + 1.0;
+    ef_used[0] = ef[0];
+    ef_used[1] = ef[1];
+    ef[0] += r0 / d0;
+    ef[1] += r1 / d1;
+    if (fabs(r0) <= o.fermi_thresh && fabs(r1) <= o.fermi_thresh) { conv = true; break; }
+  }
+  if (!conv) c.status |= XTB_STATUS_FERMI_FAILED;
+  double g = 0.0;
+  for (int k = threadIdx.x; k < n; k += NT) {
+    double ft = 0.0;
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      double f = 0.0;
+      if (ne_[s]) {
+        const double ex = (c.eps[k] - ef_used[s]) / o.kt;
+        if (ex < 50.0) f = 1.0 / (exp(ex) + 1.0);
+      }
+      ft += f;
+      const double o1 = fmax(f, kEps), o2 = fmax(1.0 - f, kEps);
+      g += o1 * log(o1) + o2 * log(o2);
+    }
+    c.focc[k] = ft;
+  }
+  g = block_sum(g, c.red);
+  __syncthreads();
+  return g * o.kt;
+}
+
+// q (orbital charges) -> shell/atom charges -> potential vout (scf/base.py:702-727, interactions/base.py:134-181)
+__device__ void potential(Ctx& c, const double* __restrict__ q, double* __restrict__ vout) {
+  for (int a = threadIdx.x; a < c.na; a += NT) {
+    const int s0 = c.at_sh0[a], nsa = c.at_nsh[a];
+    double qa = 0.0;
+    for (int k = 0; k < nsa; ++k) {
+      double qs = 0.0;
+      const int sh = s0 + k;
+      const int mu0 = c.sh_ao[sh], nmu = 2 * c.sh_l[sh] + 1;  // AOs of a shell are contiguous
+      for (int mu = mu0; mu < mu0 + nmu; ++mu) qs += q[mu];
+      c.qsh[sh] = qs;
+      qa += qs;
+    }
+    c.qat[a] = qa;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int k = w; k < c.ns; k += NT / 32) {
+    const double* gr = c.gam + (size_t)k * c.ns;
+    double acc = 0.0;
+    for (int l = lane; l < c.ns; l += 32) acc += gr[l] * c.qsh[l];
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      const int a = c.sh_atom[k];
+      const double qa = c.qat[a];
+      c.vsh[k] = acc + c.gam3[(size_t)a * XTB_ATPAR + XTB_AT_GAM3] * qa * qa;
+    }
+  }
+  __syncthreads();
+  for (int mu = threadIdx.x; mu < c.n; mu += NT) vout[mu] = c.vsh[c.ao_sh[mu]];
+  __syncthreads();
+}
+
+// One SCF map evaluation v -> q -> vnew (scf/base.py:651-675, 818-907, 765-792).
+// Returns the electronic free energy of this solve.
+__device__ double fcn(Ctx& c, const double* __restrict__ v, const xtb_scf_opts& o, double nel_a, double nel_b) {
+  const int n = c.n, ne = c.ne, ld = c.ld;
+  // F = H0 - 1/2 S (v_i + v_j)   -> A buffer (symmetric, zero padded)
+  for (int t = threadIdx.x; t < ne * ld; t += NT) {
+    const int i = t / ld, j = t - i * ld;
+    double f = 0.0;
+    if (i < n && j < n) {
+      const size_t ij = (size_t)i * n + j;
+      f = c.H0[ij] - 0.5 * c.S[ij] * (v[i] + v[j]);
+    }
+    c.A[t] = f;
+  }
+  __syncthreads();
+  gemm_tn(ne, ne, c.A, c.C, ld, c.X, ld, ne);  // X = F C   (F symmetric)
+  gemm_tn(ne, ne, c.C, c.X, ld, c.A, ld, ne);  // A = C^T X
+  // symmetrise (round-off) and keep the pad row/column exactly zero
+  for (int t = threadIdx.x; t < ne * ne; t += NT) {
+    const int i = t / ne, j = t - i * ne;
+    if (i < j) {
+      const double a = (i < n && j < n) ? 0.5 * (c.A[(size_t)i * ld + j] + c.A[(size_t)j * ld + i]) : 0.0;
+      c.A[(size_t)i * ld + j] = a;
+      c.A[(size_t)j * ld + i] = a;
+    }
+  }
+  __syncthreads();
+  const int sw = jacobi(c, c.A, c.C, ne, o.jacobi_tol, o.jacobi_max_sweeps);
+  if (sw < 0) c.status |= XTB_STATUS_JACOBI_NOT_CONVERGED;
+  for (int k = threadIdx.x; k < n; k += NT) c.eps[k] = c.A[(size_t)k * ld + k];
+  __syncthreads();
+  const double g = fermi_fill(c, nel_a, nel_b, o);
+  // compact list of occupied orbitals
+  if (threadIdx.x == 0) {
+    int no = 0;
+    for (int k = 0; k < n; ++k)
+      if (c.focc[k] > 0.0) c.occl[no++] = k;
+    c.occl[n] = no;
+  }
+  __syncthreads();
+  const int nocc = c.occl[n];
+  // Y[kk][i] = sqrt(f_k) C[i][k]  -> X buffer;  P = Y^T Y -> A buffer
+  for (int t = threadIdx.x; t < nocc * ld; t += NT) {
+    const int kk = t / ld, i = t - kk * ld;
+    const int k = c.occl[kk];
+    c.X[t] = (i < n) ? sqrt(c.focc[k]) * c.C[(size_t)i * ld + k] : 0.0;
+  }
+  __syncthreads();
+  gemm_tn(ne, nocc, c.X, c.X, ld, c.A, ld, ne);
+  // Mulliken populations and orbital-resolved H0 energies: one warp per row
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int mu = w; mu < n; mu += NT / 32) {
+    const double* pr = c.A + (size_t)mu * ld;
+    const double* sr = c.S + (size_t)mu * n;
+    const double* hr = c.H0 + (size_t)mu * n;
+    double pop = 0.0, e = 0.0;
+    for (int nu = lane; nu < n; nu += 32) {
+      const double p = pr[nu];
+      pop = fma(p, sr[nu], pop);
+      e = fma(p, hr[nu], e);
+    }
+    pop = warp_sum(pop);
+    e = warp_sum(e);
+    if (lane == 0) {
+      c.q[mu] = c.n0[mu] - pop;
+      c.eorb[mu] = e;
+    }
+  }
+  __syncthreads();
+  potential(c, c.q, c.vnew);
+  return g;
+}
+
+// 5x5 (or smaller) solve with partial pivoting, thread 0 only
+__device__ void small_solve(int n, double (*a)[5], double* b, double* x) {
+  for (int k = 0; k < n; ++k) {
+    int piv = k;
+    double best = fabs(a[k][k]);
+    for (int i = k + 1; i < n; ++i)
+      if (fabs(a[i][k]) > best) { best = fabs(a[i][k]); piv = i; }
+    if (piv != k) {
+      for (int j = 0; j < n; ++j) { const double t = a[k][j]; a[k][j] = a[piv][j]; a[piv][j] = t; }
+      const double t = b[k]; b[k] = b[piv]; b[piv] = t;
+    }
+    for (int i = k + 1; i < n; ++i) {
+      const double f = a[i][k] / a[k][k];
+      for (int j = k + 1; j < n; ++j) a[i][j] -= f * a[k][j];
+      b[i] -= f * b[k];
+    }
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    double s = b[i];
+    for (int j = i + 1; j < n; ++j) s -= a[i][j] * x[j];
+    x[i] = s / a[i][i];
+  }
+}
+
+struct Mixer {
+  int step, head;  // head: physical slot of logical history index 0
+};
+
+// Anderson / simple mixing (mixer/anderson.py:163-317, mixer/simple.py:88-151).  x_old is in c.v, x_new in
+// c.vnew; the mixed vector is written to c.v.  Returns true if converged (mixer/base.py:229-256).
+__device__ bool mix(Ctx& c, Mixer& mx, const xtb_scf_opts& o, double* sm_theta) {
+  const int n = c.n, G1 = o.generations + 1;
+  auto slot = [&](int i) { return (mx.head + i) % G1; };
+  double* f0 = c.fh + (size_t)slot(0) * n;
+  double* x0 = c.xh + (size_t)slot(0) * n;
+  if (mx.step == 0)
+    for (int k = threadIdx.x; k < n; k += NT) x0[k] = c.v[k];
+  mx.step += 1;
+  double l2 = 0.0, li = 0.0;
+  for (int k = threadIdx.x; k < n; k += NT) {
+    const double d = c.vnew[k] - c.v[k];
+    f0[k] = d;
+    l2 += d * d;
+    li = fmax(li, fabs(d));
+  }
+  l2 = block_sum(l2, c.red);
+  li = block_max(li, c.red);
+  __syncthreads();
+  const bool conv = (sqrt(l2) < o.x_atol) && (li < o.x_atol_max);
+
+  const bool anderson = o.mixer == 0 && (mx.step > o.generations || (mx.step > 1 && !o.soft_start));
+  if (o.mixer == 1) {
+    for (int k = threadIdx.x; k < n; k += NT) c.v[k] = c.v[k] + o.damp * f0[k];
+  } else if (anderson) {
+    int nh = mx.step - 1;
+    if (nh > o.generations) nh = o.generations;
+    if (nh > 5) nh = 5;
+    // a_ij = <dF_i, dF_j>, b_i = <dF_i, F0>, dF_i = F0 - F_i   (20 dot products, one warp each)
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int ndot = nh * (nh + 1) / 2 + nh;
+    for (int d = w; d < ndot; d += NT / 32) {
+      int i, j;
+      if (d < nh) { i = d; j = -1; }
+      else {
+        int r = d - nh; i = 0;
+        while (r > i) { r -= i + 1; ++i; }
+        j = r;
+      }
+      const double* fi = c.fh + (size_t)slot(i + 1) * n;
+      const double* fj = (j >= 0) ? c.fh + (size_t)slot(j + 1) * n : nullptr;
+      double acc = 0.0;
+      for (int k = lane; k < n; k += 32) {
+        const double di = f0[k] - fi[k];
+        const double dj = (j >= 0) ? f0[k] - fj[k] : f0[k];
+        acc = fma(di, dj, acc);
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        if (j < 0) sm_theta[25 + i] = acc;
+        else { sm_theta[i * 5 + j] = acc; sm_theta[j * 5 + i] = acc; }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a[5][5], bb[5], th[5];
+      for (int i = 0; i < nh; ++i) {
+        for (int j = 0; j < nh; ++j) a[i][j] = sm_theta[i * 5 + j];
+        a[i][i] *= 1.0 + o.diag_offset * o.diag_offset;
+        bb[i] = sm_theta[25 + i];
+      }
+      small_solve(nh, a, bb, th);
+      for (int i = 0; i < nh; ++i) sm_theta[30 + i] = th[i];
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < n; k += NT) {
+      double xb = x0[k], fb = f0[k];
+      for (int i = 0; i < nh; ++i) {
+        const double th = sm_theta[30 + i];
+        xb += th * (c.xh[(size_t)slot(i + 1) * n + k] - x0[k]);
+        fb -= th * (f0[k] - c.fh[(size_t)slot(i + 1) * n + k]);
+      }
+      c.v[k] = xb + o.damp * fb;
+    }
+  } else {
+    for (int k = threadIdx.x; k < n; k += NT) c.v[k] = x0[k] + o.damp_init * f0[k];
+  }
+  __syncthreads();
+  // roll histories and store the mixed vector as x_hist[0]
+  mx.head = (mx.head + G1 - 1) % G1;
+  double* xn = c.xh + (size_t)slot(0) * n;
+  for (int k = threadIdx.x; k < n; k += NT) xn[k] = c.v[k];
+  __syncthreads();
+  return conv;
+}
+
+__global__ void __launch_bounds__(NT, 1)
+k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, const double* __restrict__ H0,
+      const double* __restrict__ gamma, const double* __restrict__ nel_ab, const double* __restrict__ q0_at, double* __restrict__ work,
+      double* __restrict__ q_orb, double* __restrict__ q_sh, double* __restrict__ q_at, double* __restrict__ v_orb,
+      double* __restrict__ e_atom, double* __restrict__ fenergy, double* __restrict__ emo, double* __restrict__ occ,
+      int32_t* __restrict__ iterations, int32_t* __restrict__ status, double* __restrict__ Pout, double* __restrict__ Wout) {
+  extern __shared__ double sm[];
+  const int m = blockIdx.x;
+  Ctx c;
+  c.o0 = b.ao_off[m]; c.s0 = b.sh_off[m]; c.a0 = b.at_off[m];
+  c.n = b.ao_off[m + 1] - c.o0;
+  c.ns = b.sh_off[m + 1] - c.s0;
+  c.na = b.at_off[m + 1] - c.a0;
+  c.ne = c.n + (c.n & 1);
+  c.ld = c.ne + 1;
+  c.np = c.ne / 2;
+  c.status = 0;
+  const int n = c.n, ne = c.ne, ld = c.ld;
+  // shared-memory carve-up (sizes by batch maxima so the layout is launch-uniform)
+  const int nmx = b.nao_max + 2, nsx = b.nsh_max, nax = b.nat_max;
+  double* p = sm;
+  c.eps = p; p += nmx; c.srt = p; p += nmx; c.focc = p; p += nmx; c.v = p; p += nmx; c.vnew = p; p += nmx;
+  c.q = p; p += nmx; c.n0 = p; p += nmx; c.eorb = p; p += nmx;
+  c.qsh = p; p += nsx; c.vsh = p; p += nsx; c.qat = p; p += nax;
+  c.red = p; p += 32; c.cs = p; p += nmx;
+  double* sm_theta = p; p += 36;
+  c.pp = (int*)p; p += (nmx + 1) / 2; c.qq = (int*)p; p += (nmx + 1) / 2; c.occl = (int*)p; p += (nmx + 2) / 2 + 1;
+  const size_t msz = (size_t)(n + 1) * (n + 2);
+  if (o.use_smem) {
+    const size_t mszx = (size_t)(b.nao_max + 1) * (b.nao_max + 2);
+    c.C = p; c.A = p + mszx; c.X = p + 2 * mszx;
+  } else {
+    double* wm = work + (size_t)(o.generations + 1) * 2 * b.nao_tot + 3 * ((size_t)b.mat_off[m] + 3 * (size_t)c.o0 + 2 * (size_t)m);
+    c.C = wm; c.A = wm + msz; c.X = wm + 2 * msz;
+  }
+  c.xh = work + (size_t)(o.generations + 1) * 2 * c.o0;
+  c.fh = c.xh + (size_t)(o.generations + 1) * n;
+  c.S = S + b.mat_off[m];
+  c.H0 = H0 + b.mat_off[m];
+  c.gam = gamma + b.gam_off[m];
+  c.ao_sh = b.ao_sh + c.o0;
+  c.sh_atom = b.sh_atom + c.s0;
+  c.sh_ao = b.sh_ao + c.s0;
+  c.sh_l = b.sh_l + c.s0;
+  c.at_sh0 = b.at_sh0 + c.a0;
+  c.at_nsh = b.at_nsh + c.a0;
+  c.gam3 = b.at_par + (size_t)c.a0 * XTB_ATPAR;
+  const double nel_a = nel_ab[2 * m], nel_b = nel_ab[2 * m + 1];
+
+  // reference occupation per AO (scf/iterator.py:147-170)
+  for (int mu = threadIdx.x; mu < n; mu += NT) {
+    const int sh = c.ao_sh[mu];
+    c.n0[mu] = b.sh_par[(size_t)(c.s0 + sh) * XTB_SHPAR + XTB_SH_REFOCC] / (double)(2 * b.sh_l[c.s0 + sh] + 1);
+  }
+  // S-orthonormal start basis: S = U s U^T  ->  C0 = U s^{-1/2}
+  for (int t = threadIdx.x; t < ne * ld; t += NT) {
+    const int i = t / ld, j = t - i * ld;
+    c.A[t] = (i < n && j < n) ? c.S[(size_t)i * n + j] : ((i == j && i < ne) ? 1.0 : 0.0);
+    c.C[t] = (i == j && i < n) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  {
+    const int sw = jacobi(c, c.A, c.C, ne, 2e-14, o.jacobi_max_sweeps + 20);
+    if (sw < 0) c.status |= XTB_STATUS_JACOBI_NOT_CONVERGED;
+    bool bad = false;
+    for (int k = threadIdx.x; k < n; k += NT) {
+      const double s = c.A[(size_t)k * ld + k];
+      if (!(s > 0.0)) bad = true;
+      c.eps[k] = (s > 0.0) ? 1.0 / sqrt(s) : 0.0;
+    }
+    if (__syncthreads_or(bad)) c.status |= XTB_STATUS_S_NOT_POSDEF;
+    for (int t = threadIdx.x; t < n * n; t += NT) {
+      const int i = t / n, k = t - i * n;
+      c.C[(size_t)i * ld + k] *= c.eps[k];
+    }
+    __syncthreads();
+  }
+
+  // guess: atomic charges spread equally over shells, then over the AOs of a shell (scf/guess.py:122-182)
+  for (int mu = threadIdx.x; mu < n; mu += NT) {
+    const int sh = c.ao_sh[mu];
+    const int a = c.sh_atom[sh];
+    c.q[mu] = q0_at[c.a0 + a] / (double)c.at_nsh[a] / (double)(2 * b.sh_l[c.s0 + sh] + 1);
+  }
+  __syncthreads();
+  potential(c, c.q, c.v);  // guess potential (scf/base.py:363-420)
+
+  Mixer mx;
+  mx.step = 0;
+  mx.head = 0;
+  int iters = 1;
+  bool converged = true;
+  double g = fcn(c, c.v, o, nel_a, nel_b);  // evaluated outside the loop (unrolling/default.py:81)
+  if (o.maxiter > 0) {
+    converged = false;
+    mix(c, mx, o, sm_theta);  // mix_guess (unrolling/default.py:93-94); convergence is not tested here
+    for (int it = 0; it < o.maxiter; ++it) {
+      g = fcn(c, c.v, o, nel_a, nel_b);
+      ++iters;
+      if (mix(c, mx, o, sm_theta)) { converged = true; break; }
+    }
+    // converged_to_charges: one more solve with the UN-MIXED potential (scf/base.py:497-501, default.py:111-114)
+    for (int k = threadIdx.x; k < n; k += NT) c.v[k] = c.vnew[k];
+    __syncthreads();
+    g = fcn(c, c.v, o, nel_a, nel_b);
+  }
+  if (!converged) c.status |= XTB_STATUS_SCF_NOT_CONVERGED;
+
+  // ---- outputs -------------------------------------------------------------------------------
+  for (int mu = threadIdx.x; mu < n; mu += NT) {
+    q_orb[c.o0 + mu] = c.q[mu];
+    v_orb[c.o0 + mu] = c.vnew[mu];  // potential of the final charges (scf/base.py:468)
+    emo[c.o0 + mu] = c.eps[mu];
+    occ[c.o0 + mu] = c.focc[mu];
+  }
+  for (int k = threadIdx.x; k < c.ns; k += NT) q_sh[c.s0 + k] = c.qsh[k];
+  // atom-resolved energies (scf/base.py:514-534; interactions/base.py:305-360; secondorder.py:374-382; thirdorder.py:246-276)
+  for (int a = threadIdx.x; a < c.na; a += NT) {
+    double e = 0.0;
+    const int sh0 = c.at_sh0[a], nsa = c.at_nsh[a];
+    for (int k = 0; k < nsa; ++k) {
+      const int mu0 = c.sh_ao[sh0 + k], nmu = 2 * c.sh_l[sh0 + k] + 1;
+      for (int mu = mu0; mu < mu0 + nmu; ++mu) e += c.eorb[mu];
+    }
+    const double qa = c.qat[a];
+    const double g3 = c.gam3[(size_t)a * XTB_ATPAR + XTB_AT_GAM3];
+    for (int k = 0; k < nsa; ++k) {
+      const double ves2 = c.vsh[sh0 + k] - g3 * qa * qa;  // gamma.q_sh part of the shell potential
+      e += 0.5 * c.qsh[sh0 + k] * ves2;
+    }
+    e += g3 * qa * qa * qa / 3.0;
+    e += g / (double)c.na;
+    e_atom[c.a0 + a] = e;
+    q_at[c.a0 + a] = qa;
+  }
+  if (threadIdx.x == 0) {
+    fenergy[m] = g;
+    iterations[m] = iters;
+    status[m] = c.status;
+  }
+  if (o.want_density) {
+    double* Pm = Pout + b.mat_off[m];
+    double* Wm = Wout + b.mat_off[m];
+    for (int t = threadIdx.x; t < n * n; t += NT) {
+      const int i = t / n, j = t - i * n;
+      Pm[t] = c.A[(size_t)i * ld + j];
+    }
+    __syncthreads();
+    // W = C diag(f eps) C^T = Y1^T Y2 with Y1[kk][i] = f_k eps_k C[i][k] (X buffer), Y2[kk][i] = C[i][k] (A buffer)
+    const int nocc = c.occl[n];
+    for (int t = threadIdx.x; t < nocc * ld; t += NT) {
+      const int kk = t / ld, i = t - kk * ld;
+      const int k = c.occl[kk];
+      const double cv = (i < n) ? c.C[(size_t)i * ld + k] : 0.0;
+      c.X[t] = c.focc[k] * c.eps[k] * cv;
+      c.A[t] = cv;
+    }
+    __syncthreads();
+    gemm_tn(ne, nocc, c.X, c.A, ld, Wm, n, n);
+  }
+}
+
+int64_t vec_smem_bytes(const xtb_batch* b) {
+  const int64_t nmx = b->nao_max + 2, nsx = b->nsh_max, nax = b->nat_max;
+  int64_t d = 8 * nmx + 2 * nsx + nax + 32 + nmx + 36;
+  d += (nmx + 1) / 2 * 2 + (nmx + 2) / 2 + 1;
+  return d * 8;
+}
+
+}  // namespace
+
+extern "C" int64_t xtb_scf_smem_bytes(const xtb_batch* b) {
+  if (!b) return -1;
+  return vec_smem_bytes(b) + 3 * (int64_t)(b->nao_max + 1) * (b->nao_max + 2) * 8;
+}
+
+extern "C" int64_t xtb_scf_workspace_bytes(const xtb_batch* b, const xtb_scf_opts* o) {
+  if (!b || !o) return -1;
+  int64_t d = (int64_t)(o->generations + 1) * 2 * b->nao_tot;
+  if (!o->use_smem) {
+    // 3 matrices of (n+1)(n+2) per molecule: 3 (sum n^2 + 3 sum n + 2 nb)
+    d += 3 * (b->mat_total + 3 * (int64_t)b->nao_tot + 2 * (int64_t)b->nb);
+  }
+  return d * 8 + 256;
+}
+
+extern "C" int xtb_scf_run(const xtb_batch* b, const xtb_scf_opts* o, const double* S, const double* H0, const double* gamma,
+                           const double* nel_ab, const double* q0_at, void* work, double* q_orb, double* q_sh, double* q_at,
+                           double* v_orb, double* e_atom, double* fenergy, double* emo, double* occ, int32_t* iterations,
+                           int32_t* status, double* P, double* W, void* stream) {
+  if (!b || !o || !S || !H0 || !gamma || !nel_ab || !q0_at || !work || !q_orb || !q_sh || !q_at || !v_orb || !e_atom || !fenergy ||
+      !emo || !occ || !iterations || !status)
+    return -1;
+  if (o->want_density && (!P || !W)) return -1;
+  if (o->generations > 5 || o->generations < 1) return -3;
+  if (b->nb == 0) return 0;
+  int64_t smem = o->use_smem ? xtb_scf_smem_bytes(b) : vec_smem_bytes(b);
+  static int64_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_scf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = smem;
+  }
+  k_scf<<<b->nb, NT, (size_t)smem, (cudaStream_t)stream>>>(*b, *o, S, H0, gamma, nel_ab, q0_at, (double*)work, q_orb, q_sh, q_at,
+                                                            v_orb, e_atom, fenergy, emo, occ, iterations, status, P, W);
+  return launch_status();
+}

@@ -1,0 +1,155 @@
+/*
+ * xtb_b200.h -- C ABI of the B200-native GFN1-xTB single-point hot path.
+ *
+ * Every entry point replaces one stage of dxtb's Python hot path (paths relative to
+ * /root/reference/src/dxtb/_src, dxtb v0.4.0).  The reference has no FFI of its own (it is pure
+ * Python/PyTorch); the binding a maintainer would add is the ctypes stub in INTEGRATION.md, which
+ * is exactly what dxtb_b200/_abi.py does.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless stated otherwise; the library never allocates
+ *     persistent memory: every buffer (incl. workspaces) is owned by the caller (torch tensors)
+ *   - all floating point data is fp64, indices int32, matrix offsets int64
+ *   - molecules are stored ragged (CSR): atom a of molecule m is at_off[m] + a, etc.;
+ *     matrices S/H0/P/W of molecule m start at mat_off[m] (row-major nao x nao), gamma at gam_off[m]
+ *   - functions return 0 on success, <0 on argument errors, >0 = cudaError_t of the launch
+ *   - kernels are enqueued on `stream` (a cudaStream_t passed as void*) and never synchronise
+ */
+#ifndef XTB_B200_H
+#define XTB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XTB_ATPAR 12 /* doubles per atom in at_par   */
+#define XTB_SHPAR 6  /* doubles per shell in sh_par  */
+#define XTB_CGTO 16  /* doubles per CGTO table entry */
+#define XTB_MAXPRIM 7
+
+/* at_par[a][..] : replaces the per-species gathers of xtb/base.py:138-155, repulsion/base.py:229-243,
+ * thirdorder.py:232-244, halogen/hal.py:164-165 and the EEQ parameter lookup of tad-multicharge */
+enum { XTB_AT_RAD = 0, XTB_AT_RCOV, XTB_AT_EN, XTB_AT_AREP, XTB_AT_ZEFF, XTB_AT_GAM3, XTB_AT_XBOND,
+       XTB_AT_EEQ_CHI, XTB_AT_EEQ_ETA, XTB_AT_EEQ_KCN, XTB_AT_EEQ_RAD, XTB_AT_PAD };
+/* sh_par[s][..] : xtb/base.py:141-155 (levels, kcn in Hartree; shpoly; refocc), secondorder.py:838-839 (eta) */
+enum { XTB_SH_LEVEL = 0, XTB_SH_KCN, XTB_SH_SHPOLY, XTB_SH_ETA, XTB_SH_REFOCC, XTB_SH_PAD };
+
+/* Immutable batch descriptor (the IndexHelper + parameter gathers of basis/indexhelper.py:336-491,
+ * built once per calculator by the host and uploaded). */
+typedef struct xtb_batch {
+  int32_t nb;                         /* molecules in this shard */
+  int32_t nat_tot, nsh_tot, nao_tot;  /* totals over the shard */
+  int32_t nat_max, nsh_max, nao_max;  /* maxima over the shard */
+  int32_t nspecies;                   /* unique elements in the shard */
+  int32_t ncgto;                      /* rows of the cgto table */
+  int32_t pad0;
+  int64_t mat_total, gam_total, eeq_total; /* host copies of mat_off[nb], gam_off[nb], eeq_off[nb] */
+  const int32_t* at_off;  /* [nb+1] */
+  const int32_t* sh_off;  /* [nb+1] */
+  const int32_t* ao_off;  /* [nb+1] */
+  const int64_t* mat_off; /* [nb+1] prefix of nao^2 */
+  const int64_t* gam_off; /* [nb+1] prefix of nsh^2 */
+  const int64_t* eeq_off; /* [nb+1] prefix of (nat+1)^2 */
+  const int32_t* at_z;       /* [nat_tot] atomic number */
+  const int32_t* at_species; /* [nat_tot] index into kpair table */
+  const int32_t* at_sh0;     /* [nat_tot] first shell (molecule-local) */
+  const int32_t* at_nsh;     /* [nat_tot] number of shells */
+  const double* at_par;      /* [nat_tot][XTB_ATPAR] */
+  const int32_t* sh_atom;    /* [nsh_tot] atom (molecule-local) */
+  const int32_t* sh_l;       /* [nsh_tot] angular momentum */
+  const int32_t* sh_ao;      /* [nsh_tot] first AO (molecule-local) */
+  const int32_t* sh_cgto;    /* [nsh_tot] row of cgto table */
+  const int32_t* sh_type;    /* [nsh_tot] l + 3*(non-valence) : row of hscale */
+  const int32_t* sh_by_l;    /* [nsh_tot] molecule-local shell ids sorted by l */
+  const int32_t* nsh_l;      /* [nb][3] number of s/p/d shells */
+  const double* sh_par;      /* [nsh_tot][XTB_SHPAR] */
+  const int32_t* ao_sh;      /* [nao_tot] shell (molecule-local) */
+  const double* cgto;        /* [ncgto][XTB_CGTO]: nprim, alpha[7], coeff[7], 0 */
+  const double* kpair;       /* [nspecies][nspecies] */
+  double hscale[36];         /* [6][6] by sh_type (xtb/gfn1.py:66-165) */
+  double enscale;            /* hamiltonian.xtb.enscale */
+  double rep_kexp;           /* repulsion.effective.kexp */
+  double xb_damp, xb_rscale; /* halogen.classical */
+  double gexp;               /* charge.effective.gexp (only 2.0 is implemented) */
+  double int_cutoff, rep_cutoff, xb_cutoff, cn_cutoff;
+  double kcn_d3;             /* 16.0 */
+} xtb_batch;
+
+/* SCF options: resolved defaults of constants/defaults.py */
+typedef struct xtb_scf_opts {
+  int32_t maxiter;          /* 100 */
+  int32_t mixer;            /* 0 = Anderson (default path), 1 = simple */
+  int32_t generations;      /* 5 */
+  int32_t soft_start;       /* 1 */
+  int32_t fermi_maxiter;    /* 200 */
+  int32_t want_density;     /* 1: write P, W (needed by xtb_grad_bwd) */
+  int32_t use_smem;         /* 1: matrices in shared memory (host checks capacity) */
+  int32_t jacobi_max_sweeps;/* 30 */
+  double damp;              /* 0.5 */
+  double damp_init;         /* 0.1 */
+  double diag_offset;       /* 0.01 */
+  double x_atol;            /* 1e-4 (L2) */
+  double x_atol_max;        /* 1e-5 (Linf) */
+  double kt;                /* fermi_etemp * KELVIN2AU */
+  double fermi_thresh;      /* sqrt(eps) */
+  double jacobi_tol;        /* 1e-13 */
+} xtb_scf_opts;
+
+/* status bits written per molecule by xtb_scf_run */
+#define XTB_STATUS_SCF_NOT_CONVERGED 1
+#define XTB_STATUS_FERMI_FAILED 2
+#define XTB_STATUS_JACOBI_NOT_CONVERGED 4
+#define XTB_STATUS_S_NOT_POSDEF 8
+
+int xtb_version(void);
+
+/* sizeof checks for the ctypes mirror */
+int xtb_sizeof_batch(void);
+int xtb_sizeof_scf_opts(void);
+
+/* Classical, geometry-only stage: D3-type coordination number (tad-mctc cn_d3/exp_count, called at
+ * xtb/gfn1.py:57-64), repulsion (classicals/repulsion/base.py:269-334) and halogen-bond correction
+ * (classicals/halogen/hal.py:209-364).  pos [nat_tot][3]; cn, e_rep, e_xb [nat_tot]. */
+int xtb_geometry_fwd(const xtb_batch* b, const double* pos, double* cn, double* e_rep, double* e_xb, void* stream);
+
+/* EEQ guess charges (tad-multicharge get_eeq_charges, called at scf/guess.py:118-120).
+ * chrg [nb]; work [eeq_off[nb] + 2*(nat_tot+nb)]; q_at [nat_tot]. */
+int xtb_eeq_guess(const xtb_batch* b, const double* pos, const double* chrg, double* work, double* q_at, void* stream);
+
+/* Shell-resolved Coulomb matrix (coulomb/secondorder.py:799-870). gamma [gam_off[nb]]. */
+int xtb_gamma_fwd(const xtb_batch* b, const double* pos, double* gamma, void* stream);
+
+/* Overlap (integral/driver/pytorch/impls/overlap.py:147-243 + md/explicit.py:61-187) fused with the
+ * GFN1 H0 build (xtb/base.py:251-360).  S, H0 [mat_off[nb]]. */
+int xtb_overlap_h0_fwd(const xtb_batch* b, const double* pos, const double* cn, double* S, double* H0, void* stream);
+
+/* Bytes of workspace xtb_scf_run needs for this batch / option set. */
+int64_t xtb_scf_workspace_bytes(const xtb_batch* b, const xtb_scf_opts* o);
+/* Dynamic shared memory the SCF kernel needs with use_smem=1 (host compares with the device limit). */
+int64_t xtb_scf_smem_bytes(const xtb_batch* b);
+
+/* The whole SCF (scf/iterator.py:51-144, scf/unrolling/default.py:71-136, scf/base.py:651-907,
+ * mixer/anderson.py:163-317, wavefunction/filling.py:201-366): one CTA per molecule, no host round-trips.
+ *   nel_ab [nb][2]  alpha/beta electron numbers; q0_at [nat_tot] guess atomic charges
+ *   outputs: q_orb [nao_tot], q_sh [nsh_tot], q_at [nat_tot], v_orb [nao_tot] (potential of the final charges),
+ *            e_atom [nat_tot] (electronic + ES2 + ES3 + G/nat), fenergy [nb], emo [nao_tot], occ [nao_tot],
+ *            iterations [nb], status [nb]; P, W [mat_off[nb]] if want_density */
+int xtb_scf_run(const xtb_batch* b, const xtb_scf_opts* o, const double* S, const double* H0, const double* gamma,
+                const double* nel_ab, const double* q0_at, void* work, double* q_orb, double* q_sh, double* q_at,
+                double* v_orb, double* e_atom, double* fenergy, double* emo, double* occ, int32_t* iterations,
+                int32_t* status, double* P, double* W, void* stream);
+
+/* Analytic nuclear gradient of the converged single point (calculators/types/analytical.py:63-222,
+ * xtb/gfn1.py:185-408, secondorder.py:873-926, repulsion/base.py:337-406, ncoord/utils.py:30-52):
+ * grad[a] = ge[m] * dE_m/dR_a, ge [nb] being the upstream gradient of the molecular energies.
+ * dedcn [nat_tot] is scratch. */
+int xtb_grad_bwd(const xtb_batch* b, const double* pos, const double* cn, const double* S, const double* P,
+                 const double* W, const double* v_orb, const double* q_sh, const double* gamma, const double* ge,
+                 double* dedcn, double* grad, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XTB_B200_H */

@@ -736,7 +736,9 @@ def singlepoint(numbers, positions, chrg: float = 0.0, opts: dict | None = None,
     st = state
     res.iterations, res.converged = iters, converged
     res.q_orb, res.q_sh, res.q_at = st["q"], st["q_sh"], st["q_at"]
-    res.P, res.emo, res.occ, res.v_orb = st["P"], st["emo"], st["occ"], v_new
+    # potential of the FINAL charges: what the reference hands to its analytic gradient (scf/base.py:468)
+    v_fin = _potential(m, st["q"], gam, g3)[0]
+    res.P, res.emo, res.occ, res.v_orb = st["P"], st["emo"], st["occ"], v_fin
 
     # energies (scf/base.py:514-534, 558-607; interactions/base.py:305-360)
     v_es2 = gam @ st["q_sh"]
@@ -757,7 +759,7 @@ def singlepoint(numbers, positions, chrg: float = 0.0, opts: dict | None = None,
         focc = occ.sum(0)
         W = (st["C"] * (focc * st["emo"])[None, :]) @ st["C"].T
         res.W = W
-        g_tot += _electronic_gradient(m, pos, S, dS, st["P"], W, v_new, cn, dcfdr, st["q_sh"], gam)
+        g_tot += _electronic_gradient(m, pos, S, dS, st["P"], W, v_fin, cn, dcfdr, st["q_sh"], gam)
         res.gradient = g_tot
     return res
 
