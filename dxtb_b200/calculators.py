@@ -20,7 +20,7 @@ from . import _abi
 from .batch import INT_CUTOFF, BatchDescriptor
 from .exceptions import (DeviceError, DtypeError, MissingD3ReferenceError, SCFConvergenceError,
                          SCFConvergenceWarning)
-from .param import gfn1_param
+from .param import GFN1Param, gfn1_param
 
 __all__ = ["GFN1Calculator", "Calculator"]
 
@@ -110,6 +110,10 @@ class _SinglePoint(torch.autograd.Function):
         _abi.check(lib.xtb_overlap_h0_fwd(d.ptr, pos.data_ptr(), ws.cn.data_ptr(), ws.S.data_ptr(), ws.H0.data_ptr(), st), "xtb_overlap_h0_fwd")
 
         nel_ab = calc._electrons(chrg, spin)
+        ev = None
+        if calc.scf_events is not None:  # bench.py: device time of the SCF kernel alone
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record(torch.cuda.current_stream(d.device))
         _abi.check(
             lib.xtb_scf_run(
                 d.ptr, _abi.C.addressof(o), ws.S.data_ptr(), ws.H0.data_ptr(), ws.gamma.data_ptr(), nel_ab.data_ptr(),
@@ -120,6 +124,9 @@ class _SinglePoint(torch.autograd.Function):
             ),
             "xtb_scf_run",
         )
+        if ev is not None:
+            ev[1].record(torch.cuda.current_stream(d.device))
+            calc.scf_events.append(ev)
         e_at = ws.e_atom.clone()
         if "rep" not in excl:
             e_at += ws.e_rep
@@ -214,10 +221,11 @@ class GFN1Calculator:
         if "disp" not in self._exclude:
             raise MissingD3ReferenceError("loading an external D3 reference table is not implemented yet")
 
-        self.par = gfn1_param()
+        self.par = par if isinstance(par, GFN1Param) else gfn1_param()
         self.desc = BatchDescriptor(self.numbers, device, self.par, exclude=tuple(self._exclude), int_cutoff=float(o["int_cutoff"]))
         self.ihelp = self.desc  # index maps live in the descriptor
         self.cache: dict[str, Any] = {}
+        self.scf_events: list | None = None
         smem = _abi.lib().xtb_scf_smem_bytes(self.desc.ptr)
         self._use_smem = 1 if smem <= _SMEM_LIMIT else 0
 

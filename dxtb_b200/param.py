@@ -94,6 +94,16 @@ class GFN1Param:
         self.d3 = raw["dispersion_d3"]
         self._sto = {int(n): (np.array(v["coeff"]), np.array(v["alpha"])) for n, v in raw["sto_ng"].items()}
 
+    def with_ev2au(self, ev2au: float) -> "GFN1Param":
+        """Copy with another eV->Hartree factor (tblite's goldens use 1 Eh = 27.21138505 eV)."""
+        import copy
+
+        new = copy.copy(self)
+        new.level = self.level * (ev2au / self.EV2AU)
+        new.kcn = self.kcn * (ev2au / self.EV2AU)
+        new.EV2AU = ev2au
+        return new
+
     # ------------------------------------------------------------------------------------------
     def hscale_table(self) -> np.ndarray:
         """6x6 table over shell type = l + 3*(non-valence) (xtb/gfn1.py:66-165)."""
@@ -116,21 +126,24 @@ class GFN1Param:
         if n == 6 and ng == 6:
             itype = 15 + l
         ctab, atab = self._sto[ng]
-        alpha = atab[itype] * zeta * zeta
+        alpha = atab[itype] * (zeta * zeta)
         dfact = (1.0, 1.0, 3.0, 15.0, 105.0)[l]
         coeff = ctab[itype] * (2.0 / math.pi * alpha) ** 0.75 * np.sqrt(4.0 * alpha) ** l / math.sqrt(dfact)
         return alpha, coeff
 
-    @lru_cache(maxsize=None)
     def cgto(self, z: int, k: int) -> tuple[np.ndarray, np.ndarray]:
         """Primitive exponents / contraction coefficients of shell ``k`` of element ``z``; a non-valence
         shell (H 2s) is orthonormalised against the preceding one (basis/bas.py:149-193, basis/ortho.py:78-110)."""
+        cache = self.__dict__.setdefault("_cgto_cache", {})
+        if (z, k) in cache:
+            return cache[(z, k)]
         alpha, coeff = self._slater_to_gauss(int(self.ngauss[z, k]), int(self.pqn[z, k]), int(self.ang[z, k]), float(self.slater[z, k]))
         if not self.valence[z, k]:
             ai, ci = self.cgto(z, k - 1)
 
             def sint(a1, a2, c1, c2):
-                return float((np.sqrt(math.pi / (a1[:, None] + a2[None, :])) ** 3 * c1[:, None] * c2[None, :]).sum())
+                o = 1.0 / (a1[:, None] + a2[None, :])  # basis/ortho.py:57-59
+                return float((np.sqrt(math.pi * o) ** 3 * c1[:, None] * c2[None, :]).sum())
 
             ovl = sint(ai, alpha, ci, coeff)
             alpha = np.concatenate([alpha, ai])
@@ -138,6 +151,7 @@ class GFN1Param:
             coeff = coeff / math.sqrt(sint(alpha, alpha, coeff, coeff))
         if alpha.size > MAX_PRIM:
             raise NotImplementedError("more than 7 primitives per shell")
+        cache[(z, k)] = (alpha, coeff)
         return alpha, coeff
 
 

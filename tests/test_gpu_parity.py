@@ -1,0 +1,273 @@
+"""Parity of the CUDA path (through the C ABI / GFN1Calculator) with the CPU oracle and the reference goldens.
+
+Tolerances are the north-star ones: energy 1e-9 Eh, charges 1e-7 e, forces 1e-7 Eh/bohr, identical SCF
+iteration counts.
+"""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gfn1_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+E_TOL, Q_TOL, F_TOL = 1e-9, 1e-7, 1e-7
+NODISP = {"exclude": ["disp"]}
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def _pack(mols, names, dev):
+    nat = max(len(mols[n]["numbers"]) for n in names)
+    numbers = torch.zeros((len(names), nat), dtype=torch.long)
+    pos = torch.zeros((len(names), nat, 3), dtype=torch.float64)
+    chrg = torch.zeros(len(names), dtype=torch.float64)
+    for i, n in enumerate(names):
+        k = len(mols[n]["numbers"])
+        numbers[i, :k] = torch.tensor(mols[n]["numbers"])
+        pos[i, :k] = torch.tensor(mols[n]["positions"], dtype=torch.float64)
+        chrg[i] = mols[n]["charge"]
+    return numbers.to(dev), pos.to(dev), chrg.to(dev)
+
+
+def _oracle(mols, name, opts=None, grad=False):
+    m = mols[name]
+    o = {"exclude": ("disp",)}
+    o.update(opts or {})
+    return O.singlepoint(m["numbers"], np.array(m["positions"]), m["charge"], opts=o, grad=grad)
+
+
+MIXED = ["H", "H2", "LiH", "H2O", "NO2", "CH4", "SiH4", "MB16_43_01", "LYS_xao", "AD7en+", "caffeine"]
+
+
+@pytest.fixture(scope="module")
+def mixed_run(mols):
+    from dxtb_b200 import GFN1Calculator
+
+    dev = _dev()
+    numbers, pos, chrg = _pack(mols, MIXED, dev)
+    calc = GFN1Calculator(numbers, opts=NODISP, device=dev, dtype=torch.float64)
+    p = pos.clone().requires_grad_(True)
+    e = calc.get_energy(p, chrg)
+    (g,) = torch.autograd.grad(e.sum(), p)
+    return calc, e.detach().cpu().numpy(), g.cpu().numpy()
+
+
+@pytest.mark.parametrize("i", range(len(MIXED)))
+def test_padded_mixed_batch_matches_oracle(mols, mixed_run, i):
+    calc, e, g = mixed_run
+    name = MIXED[i]
+    r = _oracle(mols, name, grad=True)
+    d, ws = calc.desc, calc.cache["ws"]
+    nat, nao = len(mols[name]["numbers"]), r.S.shape[0]
+    sl = slice(int(d.mat_off[i]), int(d.mat_off[i + 1]))
+    S = ws.S[sl].cpu().numpy().reshape(nao, nao)
+    H = ws.H0[sl].cpu().numpy().reshape(nao, nao)
+    assert np.abs(S - r.S).max() < 1e-13
+    assert np.abs(H - r.H0).max() < 1e-13
+    assert np.abs(ws.cn[int(d.at_off[i]) : int(d.at_off[i + 1])].cpu().numpy() - r.cn).max() < 1e-12
+    assert abs(e[i] - r.energy) < E_TOL
+    q = calc.get_charges()[i, :nao].cpu().numpy()
+    assert np.abs(q - r.q_orb).max() < Q_TOL
+    qa = calc.get_mulliken_charges()[i, :nat].cpu().numpy()
+    assert np.abs(qa - r.q_at).max() < Q_TOL
+    assert int(calc.get_iterations()[i]) == r.iterations
+    assert np.abs(g[i, :nat] - r.gradient).max() < F_TOL
+    assert np.abs(g[i, nat:]).max() == 0.0 if g.shape[1] > nat else True
+
+
+@pytest.mark.parametrize("name", ["H2", "LiH", "H2O", "CH4", "SiH4", "LYS_xao"])
+def test_overlap_h0_vs_reference_goldens(mols, goldens, name):
+    from dxtb_b200 import GFN1Calculator
+    from dxtb_b200.param import gfn1_param
+
+    dev = _dev()
+    numbers, pos, chrg = _pack(mols, [name], dev)
+    par = gfn1_param().with_ev2au(1.0 / 27.21138505)  # tblite's eV
+    calc = GFN1Calculator(numbers[0], par, opts=NODISP, device=dev, dtype=torch.float64)
+    calc.get_energy(pos[0], chrg[0])
+    ws = calc.cache["ws"]
+    n = goldens[f"overlap/{name}"].shape[0]
+    assert np.abs(ws.S.cpu().numpy().reshape(n, n) - goldens[f"overlap/{name}"]).max() < 1e-7
+    assert np.abs(ws.H0.cpu().numpy().reshape(n, n) - goldens[f"h0/{name}"]).max() < 1e-7
+
+
+@pytest.mark.parametrize("name", ["H", "H2", "LiH", "H2O", "CH4", "SiH4", "MB16_43_01", "LYS_xao", "C60"])
+def test_scf_energy_vs_tblite_goldens(mols, energies, name):
+    """Reference KATs (test/test_scf/samples.py) straight against the CUDA path (tight SCF, tblite units)."""
+    from dxtb_b200 import GFN1Calculator
+    from dxtb_b200.param import gfn1_param
+
+    dev = _dev()
+    numbers, pos, chrg = _pack(mols, [name], dev)
+    par = gfn1_param().with_ev2au(1.0 / 27.21138505)
+    opts = {"exclude": ["disp", "rep", "hal"], "x_atol": 1e-10, "x_atol_max": 1e-10}
+    calc = GFN1Calculator(numbers[0], par, opts=opts, device=dev, dtype=torch.float64)
+    e = float(calc.get_energy(pos[0], chrg[0]))
+    assert abs(e - energies["scf_gfn1_tblite"][name]) < 2e-9
+
+
+def test_readme_example_forces_equal_minus_gradient(mols):
+    """README.md:93-123: LiH, get_energy + autograd.grad vs get_forces after reset()."""
+    from dxtb_b200 import GFN1Calculator
+
+    dev = _dev()
+    numbers = torch.tensor([3, 1], device=dev)
+    positions = torch.tensor([[0.0, 0.0, 0.0], [0.0, 0.0, 1.5]], dtype=torch.float64, device=dev, requires_grad=True)
+    calc = GFN1Calculator(numbers, opts=NODISP, device=dev, dtype=torch.float64)
+    energy = calc.get_energy(positions)
+    (g,) = torch.autograd.grad(energy, positions)
+    calc.reset()
+    forces = calc.get_forces(positions)
+    assert energy.shape == () and forces.shape == (2, 3)
+    assert torch.allclose(forces, -g, rtol=0, atol=1e-14)
+    r = _oracle(mols, "LiH_readme", grad=True)
+    assert abs(float(energy) - r.energy) < E_TOL
+    assert np.abs(-forces.cpu().numpy() - r.gradient).max() < F_TOL
+
+
+def test_forces_tight_convergence(mols):
+    from dxtb_b200 import GFN1Calculator
+
+    dev = _dev()
+    names = ["H2O", "NO2", "SiH4", "caffeine"]
+    numbers, pos, chrg = _pack(mols, names, dev)
+    tight = {"exclude": ["disp"], "x_atol": 1e-10, "x_atol_max": 1e-10}
+    calc = GFN1Calculator(numbers, opts=tight, device=dev, dtype=torch.float64)
+    f = calc.get_forces(pos.clone().requires_grad_(True), chrg).cpu().numpy()
+    for i, n in enumerate(names):
+        r = _oracle(mols, n, opts={"x_atol": 1e-10, "x_atol_max": 1e-10}, grad=True)
+        k = len(mols[n]["numbers"])
+        assert np.abs(-f[i, :k] - r.gradient).max() < F_TOL
+        assert int(calc.get_iterations()[i]) == r.iterations
+
+
+def test_global_memory_variant_matches_shared_memory_variant(mols):
+    from dxtb_b200 import GFN1Calculator
+
+    dev = _dev()
+    numbers, pos, chrg = _pack(mols, ["H2O", "CH4", "caffeine", "NO2"], dev)
+    a = GFN1Calculator(numbers, opts=NODISP, device=dev, dtype=torch.float64)
+    b = GFN1Calculator(numbers, opts=NODISP, device=dev, dtype=torch.float64)
+    assert a._use_smem == 1
+    b._use_smem = 0
+    ea, eb = a.get_energy(pos, chrg), b.get_energy(pos, chrg)
+    assert torch.allclose(ea, eb, rtol=0, atol=1e-11)
+    assert torch.equal(a.get_iterations(), b.get_iterations())
+
+
+def test_large_molecule_global_path(mols):
+    """vancoh2 (176 atoms, nao 550) runs the global-memory variant."""
+    from dxtb_b200 import GFN1Calculator
+
+    dev = _dev()
+    numbers, pos, chrg = _pack(mols, ["vancoh2"], dev)
+    calc = GFN1Calculator(numbers, opts=NODISP, device=dev, dtype=torch.float64)
+    assert calc._use_smem == 0
+    e = calc.get_energy(pos, chrg)
+    r = _oracle(mols, "vancoh2")
+    assert abs(float(e[0]) - r.energy) < E_TOL
+    assert int(calc.get_iterations()[0]) == r.iterations
+
+
+def test_options_sad_guess_simple_mixer_and_nonconvergence(mols):
+    from dxtb_b200 import GFN1Calculator
+    from dxtb_b200.exceptions import SCFConvergenceError, SCFConvergenceWarning
+
+    dev = _dev()
+    numbers, pos, chrg = _pack(mols, ["H2O", "CH4"], dev)
+    for extra in ({"guess": "sad"}, {"mixer": "simple", "damp": 0.3}, {"fermi_etemp": 1000.0}, {"damp_soft_start": False}):
+        calc = GFN1Calculator(numbers, opts={**NODISP, **extra}, device=dev, dtype=torch.float64)
+        e = calc.get_energy(pos, chrg).cpu().numpy()
+        for i, n in enumerate(["H2O", "CH4"]):
+            r = _oracle(mols, n, opts=extra)
+            assert abs(e[i] - r.energy) < E_TOL, extra
+            assert int(calc.get_iterations()[i]) == r.iterations, extra
+    calc = GFN1Calculator(numbers, opts={**NODISP, "maxiter": 3}, device=dev, dtype=torch.float64)
+    with pytest.warns(SCFConvergenceWarning):
+        e = calc.get_energy(pos, chrg)
+    assert calc.get_iterations().tolist() == [4, 4]
+    r = _oracle(mols, "H2O", opts={"maxiter": 3})
+    assert abs(float(e[0]) - r.energy) < E_TOL and not r.converged
+    calc = GFN1Calculator(numbers, opts={**NODISP, "maxiter": 3, "force_convergence": True}, device=dev, dtype=torch.float64)
+    with pytest.raises(SCFConvergenceError):
+        calc.get_energy(pos, chrg)
+
+
+def test_api_errors(mols):
+    from dxtb_b200 import GFN1Calculator
+    from dxtb_b200.exceptions import DeviceError, DtypeError
+
+    dev = _dev()
+    numbers, pos, chrg = _pack(mols, ["H2O"], dev)
+    calc = GFN1Calculator(numbers[0], opts=NODISP, device=dev, dtype=torch.float64)
+    with pytest.raises(DtypeError):
+        calc.get_energy(pos[0].float())
+    with pytest.raises(DeviceError):
+        calc.get_energy(pos[0].cpu())
+    with pytest.raises(RuntimeError):
+        calc.get_forces(pos[0])  # requires_grad missing (reference: decorators.py:63-82)
+    with pytest.raises(ValueError):
+        calc.get_energy(pos[0, :2])
+
+
+def _conformers(mols, name, nb, sigma, seed, dev):
+    m = mols[name]
+    g = torch.Generator().manual_seed(seed)
+    base = torch.tensor(m["positions"], dtype=torch.float64)
+    pos = base[None] + sigma * torch.randn((nb, *base.shape), generator=g, dtype=torch.float64)
+    numbers = torch.tensor(m["numbers"])[None].expand(nb, -1).contiguous()
+    return numbers.to(dev), pos.to(dev)
+
+
+def test_full_size_conformer_batch_properties(mols):
+    """BASELINE config 2 at full size (1024 caffeine conformers): size-independent properties + oracle spot checks."""
+    from dxtb_b200 import GFN1Calculator
+
+    dev = _dev()
+    nb = 1024
+    numbers, pos = _conformers(mols, "caffeine", nb, 0.05, 0, dev)
+    chrg = torch.zeros(nb, dtype=torch.float64, device=dev)
+    calc = GFN1Calculator(numbers, opts=NODISP, device=dev, dtype=torch.float64)
+    p = pos.clone().requires_grad_(True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        e = calc.get_energy(p, chrg)
+    (g,) = torch.autograd.grad(e.sum(), p)
+    it = calc.get_iterations()
+    assert torch.isfinite(e).all() and torch.isfinite(g).all()
+    # total charge conserved, forces sum to zero (translational invariance)
+    assert calc.get_mulliken_charges().sum(-1).abs().max() < 1e-9
+    assert g.sum(1).abs().max() < 1e-8
+    # rigid rotation + translation + permutation of the batch leave energies (and iteration counts) unchanged
+    th = 0.7
+    R = torch.tensor([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1.0]], dtype=torch.float64, device=dev)
+    perm = torch.randperm(nb, generator=torch.Generator().manual_seed(1)).to(dev)
+    e2 = calc.get_energy((pos @ R.T + 3.0)[perm], chrg)
+    assert (e2 - e.detach()[perm]).abs().max() < 1e-9
+    assert (calc.get_iterations() - it[perm]).abs().max() <= 1  # thresholds may flip at round-off level
+    for i in (0, 17, 511, 1023):
+        r = O.singlepoint(mols["caffeine"]["numbers"], pos[i].cpu().numpy(), 0.0, opts={"exclude": ("disp",)}, grad=True)
+        assert abs(float(e[i]) - r.energy) < E_TOL
+        assert int(it[i]) == r.iterations
+        assert np.abs(g[i].cpu().numpy() - r.gradient).max() < F_TOL
+
+
+def test_single_molecule_unbatched_shapes(mols):
+    from dxtb_b200 import GFN1Calculator
+
+    dev = _dev()
+    numbers, pos, chrg = _pack(mols, ["CH4"], dev)
+    calc = GFN1Calculator(numbers[0], opts=NODISP, device=dev, dtype=torch.float64)
+    e = calc.get_energy(pos[0])
+    assert e.shape == ()
+    assert calc.get_charges().shape == (12,)
+    assert calc.get_mulliken_charges().shape == (5,)
+    r = _oracle(mols, "CH4")
+    assert abs(float(e) - r.energy) < E_TOL
