@@ -305,7 +305,7 @@ class GFN1Calculator:
     def energy(self, positions: torch.Tensor, chrg: Any = 0, spin: Any = None, **_: Any) -> torch.Tensor:
         chrg_t, spin_t = self._prep(positions, chrg, spin)
         e = _SinglePoint.apply(positions, chrg_t, spin_t, self)
-        return e[0] if self.desc.single else e
+        return e  # () for a single molecule, (nb,) for a batch
 
     def get_energy(self, positions: torch.Tensor, chrg: Any = 0, spin: Any = None, **kw: Any) -> torch.Tensor:
         return self.energy(positions, chrg, spin, **kw)
