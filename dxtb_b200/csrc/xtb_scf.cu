@@ -18,7 +18,7 @@ using namespace xtb;
 
 namespace {
 
-constexpr int NT = 512;  // threads per CTA
+constexpr int NT = 1024;  // threads per CTA (64 registers per thread)
 
 struct Ctx {
   int n, ne, ld, ns, na, np;
@@ -27,33 +27,43 @@ struct Ctx {
   const double *S, *H0, *gam;    // global, n x n / ns x ns
   double *eps, *srt, *focc, *v, *vnew, *q, *n0, *eorb, *qsh, *vsh, *qat, *red, *cs;
   int *pp, *qq, *occl;
+  unsigned* blk;                 // (kp << 16 | kq) for the lower-triangular pair blocks
+  bool smem;                     // matrices live in shared memory
   const int *ao_sh, *sh_atom, *at_sh0, *at_nsh, *sh_ao, *sh_l;
   const double* gam3;            // at_par base (stride XTB_ATPAR)
   double *xh, *fh;               // Anderson history [gen+1][n] (global)
   int status;
 };
 
-// Out[i][j] = sum_{k<K} L[k*ld+i] * R[k*ld+j], i,j < ne; 4x4 register tiles.
+// Address-space hint: lets the compiler emit LDS/STS (32-bit addressing) instead of generic LD/ST.
+#define XTB_ASSUME_SHARED(ptr) __builtin_assume(__isShared(ptr))
+
+// Out[i][j] = sum_{k<K} L[k*ld+i] * R[k*ld+j], i,j < ne.  4x4 register tiles whose rows/columns are
+// INTERLEAVED (row ti + r*nt4, column tj + c*nt4): lanes of a warp read consecutive fp64 words of R (no bank
+// conflicts) and broadcast the words of L.
+template <bool SM>
 __device__ void gemm_tn(int ne, int K, const double* __restrict__ L, const double* __restrict__ R, int ld, double* __restrict__ Out,
                         int ldo, int nout) {
+  if (SM) { XTB_ASSUME_SHARED(L); XTB_ASSUME_SHARED(R); }
   const int nt4 = (ne + 3) >> 2;
   for (int t = threadIdx.x; t < nt4 * nt4; t += NT) {
     const int ti = t / nt4, tj = t - ti * nt4;
-    const int i0 = ti << 2, j0 = tj << 2;
     double acc[4][4];
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
       for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
-    // ne is even and ld = ne + 1, so i0+3 <= ne+1 may touch the pad column: it is kept zero / ignored
+    bool vi[4], vj[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) { vi[r] = ti + r * nt4 < ne; vj[r] = tj + r * nt4 < ne; }
     for (int k = 0; k < K; ++k) {
-      const double* lr = L + (size_t)k * ld + i0;
-      const double* rr = R + (size_t)k * ld + j0;
+      const double* lr = L + (size_t)k * ld + ti;
+      const double* rr = R + (size_t)k * ld + tj;
       double a[4], bv[4];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) a[r] = (i0 + r < ne) ? lr[r] : 0.0;
+      for (int r = 0; r < 4; ++r) a[r] = vi[r] ? lr[r * nt4] : 0.0;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) bv[c] = (j0 + c < ne) ? rr[c] : 0.0;
+      for (int c = 0; c < 4; ++c) bv[c] = vj[c] ? rr[c * nt4] : 0.0;
 #pragma unroll
       for (int r = 0; r < 4; ++r)
 #pragma unroll
@@ -62,24 +72,39 @@ __device__ void gemm_tn(int ne, int K, const double* __restrict__ L, const doubl
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        if (i0 + r < nout && j0 + c < nout) Out[(size_t)(i0 + r) * ldo + j0 + c] = acc[r][c];
+      for (int c = 0; c < 4; ++c) {
+        const int i = ti + r * nt4, j = tj + c * nt4;
+        if (i < nout && j < nout) Out[(size_t)i * ldo + j] = acc[r][c];
+      }
   }
   __syncthreads();
 }
 
-// Cyclic Jacobi with round-robin parallel ordering on the symmetric ne x ne matrix A (full storage),
-// accumulating the rotations into the columns of V (nrow rows).  Returns the number of sweeps, or
-// -sweeps if the off-diagonal did not drop below tol.
+// Cyclic Jacobi with round-robin parallel ordering on the symmetric ne x ne matrix A (full storage, both
+// triangles kept consistent), accumulating the rotations into the columns of V (nrow rows).
+// Per round: (1) np = ne/2 threads compute the rotations of the disjoint pairs, (2) the 2x2 blocks
+// (pair kp) x (pair kq), kp >= kq, are transformed J_kp^T a J_kq and written to both triangles, and every
+// row of V gets its np column rotations.  Loads of a batch are issued before the dependent math/stores so
+// that several independent items are in flight per thread.  Returns the number of sweeps, or -sweeps if the
+// off-diagonal did not drop below tol.
+template <bool SM>
 __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, int nrow, double tol, int maxsweeps) {
   const int ne = c.ne, ld = c.ld, np = c.np;
+  const int nblk = np * (np + 1) / 2;
+  int2* pq = reinterpret_cast<int2*>(c.pp);
+  double2* cs = reinterpret_cast<double2*>(c.cs);
+  const unsigned* blk = c.blk;
+  XTB_ASSUME_SHARED(pq); XTB_ASSUME_SHARED(cs); XTB_ASSUME_SHARED(blk);
+  if (SM) { XTB_ASSUME_SHARED(A); XTB_ASSUME_SHARED(V); }
+  // fixed thread -> (column pair, first row) map of the V update
+  const int vk = threadIdx.x % np, vi0 = threadIdx.x / np, vstep = NT / np;
   int sweep = 0;
-  // already diagonal?  (converged SCF: the warm-started matrix needs no rotation at all)
   for (;;) {
     double off = 0.0;
-    for (int t = threadIdx.x; t < ne * ne; t += NT) {
-      const int i = t / ne, j = t - i * ne;
-      if (i != j) off = fmax(off, fabs(A[(size_t)i * ld + j]));
+    for (int i = threadIdx.x / 32; i < ne; i += NT / 32) {
+      const double* row = A + (size_t)i * ld;
+      for (int j = threadIdx.x & 31; j < ne; j += 32)
+        if (i != j) off = fmax(off, fabs(row[j]));
     }
     off = block_max(off, c.red);
     if (off <= tol) return sweep;
@@ -89,43 +114,87 @@ __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, in
       for (int k = threadIdx.x; k < np; k += NT) {
         int p, q;
         if (k == 0) { p = r; q = ne - 1; }
-        else { p = (r + k) % (ne - 1); q = (r - k + ne - 1) % (ne - 1); }
+        else {
+          p = r + k; if (p >= ne - 1) p -= ne - 1;
+          q = r - k; if (q < 0) q += ne - 1;
+        }
         if (p > q) { const int t = p; p = q; q = t; }
         const double app = A[(size_t)p * ld + p], aqq = A[(size_t)q * ld + q], apq = A[(size_t)p * ld + q];
         double cc = 1.0, ss = 0.0;
-        if (apq != 0.0) {
-          const double tau = (aqq - app) / (2.0 * apq);
-          const double t = copysign(1.0, tau) / (fabs(tau) + sqrt(1.0 + tau * tau));
-          cc = 1.0 / sqrt(1.0 + t * t);
+        if (fabs(apq) > 1e-150) {
+          // t = 2 apq / (d + sign(d) sqrt(d^2 + 4 apq^2)); c = 1/sqrt(1+t^2); s = t c.
+          // Only c^2 + s^2 = 1 has to hold to round-off (rsqrt is ~1 ulp); the angle itself may be approximate.
+          const double d = aqq - app;
+          const double x = d * d + 4.0 * apq * apq;
+          const double y = d + copysign(x * rsqrt(x), d);
+          const double t = 2.0 * apq * copysign(rsqrt(y * y), y);
+          cc = rsqrt(1.0 + t * t);
           ss = t * cc;
         }
-        c.pp[k] = p; c.qq[k] = q; c.cs[2 * k] = cc; c.cs[2 * k + 1] = ss;
+        pq[k] = make_int2(p, q);
+        cs[k] = make_double2(cc, ss);
       }
       __syncthreads();
-      // A <- J^T A J on disjoint 2x2 blocks (pair kp) x (pair kq)
-      for (int t = threadIdx.x; t < np * np; t += NT) {
-        const int kp = t / np, kq = t - kp * np;
-        const int p1 = c.pp[kp], q1 = c.qq[kp], p2 = c.pp[kq], q2 = c.qq[kq];
-        const double c1 = c.cs[2 * kp], s1 = c.cs[2 * kp + 1], c2 = c.cs[2 * kq], s2 = c.cs[2 * kq + 1];
-        double* r0 = A + (size_t)p1 * ld;
-        double* r1 = A + (size_t)q1 * ld;
-        const double a00 = r0[p2], a01 = r0[q2], a10 = r1[p2], a11 = r1[q2];
-        const double x00 = c1 * a00 - s1 * a10, x01 = c1 * a01 - s1 * a11;
-        const double x10 = s1 * a00 + c1 * a10, x11 = s1 * a01 + c1 * a11;
-        double y00 = c2 * x00 - s2 * x01, y01 = s2 * x00 + c2 * x01;
-        double y10 = c2 * x10 - s2 * x11, y11 = s2 * x10 + c2 * x11;
-        if (kp == kq) { y01 = 0.0; y10 = 0.0; }
-        r0[p2] = y00; r0[q2] = y01; r1[p2] = y10; r1[q2] = y11;
+      // ---- A <- J^T A J on the blocks kp >= kq --------------------------------------------------
+      constexpr int UA = 1;
+      for (int tb = threadIdx.x; tb < nblk; tb += NT * UA) {
+        int p1[UA], q1[UA], p2[UA], q2[UA];
+        double c1[UA], s1[UA], c2[UA], s2[UA], a00[UA], a01[UA], a10[UA], a11[UA];
+        bool dg[UA], ok[UA];
+#pragma unroll
+        for (int u = 0; u < UA; ++u) {
+          const int t = tb + u * NT;
+          ok[u] = t < nblk;
+          const unsigned code = ok[u] ? blk[t] : 0u;
+          const int kp = (int)(code >> 16), kq = (int)(code & 0xffffu);
+          dg[u] = kp == kq;
+          if (ok[u]) {
+            const int2 a = pq[kp], b = pq[kq];
+            const double2 ca = cs[kp], cb = cs[kq];
+            p1[u] = a.x; q1[u] = a.y; p2[u] = b.x; q2[u] = b.y;
+            c1[u] = ca.x; s1[u] = ca.y; c2[u] = cb.x; s2[u] = cb.y;
+            const double* r0 = A + (size_t)p1[u] * ld;
+            const double* r1 = A + (size_t)q1[u] * ld;
+            a00[u] = r0[p2[u]]; a01[u] = r0[q2[u]]; a10[u] = r1[p2[u]]; a11[u] = r1[q2[u]];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UA; ++u) {
+          if (!ok[u]) continue;
+          const double x00 = c1[u] * a00[u] - s1[u] * a10[u], x01 = c1[u] * a01[u] - s1[u] * a11[u];
+          const double x10 = s1[u] * a00[u] + c1[u] * a10[u], x11 = s1[u] * a01[u] + c1[u] * a11[u];
+          double y00 = c2[u] * x00 - s2[u] * x01, y01 = s2[u] * x00 + c2[u] * x01;
+          double y10 = c2[u] * x10 - s2[u] * x11, y11 = s2[u] * x10 + c2[u] * x11;
+          if (dg[u]) { y01 = 0.0; y10 = 0.0; }
+          A[(size_t)p1[u] * ld + p2[u]] = y00; A[(size_t)p1[u] * ld + q2[u]] = y01;
+          A[(size_t)q1[u] * ld + p2[u]] = y10; A[(size_t)q1[u] * ld + q2[u]] = y11;
+          if (!dg[u]) {
+            A[(size_t)p2[u] * ld + p1[u]] = y00; A[(size_t)q2[u] * ld + p1[u]] = y01;
+            A[(size_t)p2[u] * ld + q1[u]] = y10; A[(size_t)q2[u] * ld + q1[u]] = y11;
+          }
+        }
       }
-      // V <- V J
-      for (int t = threadIdx.x; t < nrow * np; t += NT) {
-        const int i = t / np, k = t - i * np;
-        const int p = c.pp[k], q = c.qq[k];
-        const double cc = c.cs[2 * k], ss = c.cs[2 * k + 1];
-        double* row = V + (size_t)i * ld;
-        const double vp = row[p], vq = row[q];
-        row[p] = cc * vp - ss * vq;
-        row[q] = ss * vp + cc * vq;
+      // ---- V <- V J: thread owns column pair vk and rows vi0, vi0 + vstep, ... --------------------
+      if (vi0 < vstep) {
+        const int2 a = pq[vk];
+        const double2 ca = cs[vk];
+        constexpr int UV = 3;
+        for (int ib = vi0; ib < nrow; ib += vstep * UV) {
+          double vp[UV], vq[UV];
+#pragma unroll
+          for (int u = 0; u < UV; ++u) {
+            const int i = ib + u * vstep;
+            if (i < nrow) { vp[u] = V[(size_t)i * ld + a.x]; vq[u] = V[(size_t)i * ld + a.y]; }
+          }
+#pragma unroll
+          for (int u = 0; u < UV; ++u) {
+            const int i = ib + u * vstep;
+            if (i < nrow) {
+              V[(size_t)i * ld + a.x] = ca.x * vp[u] - ca.y * vq[u];
+              V[(size_t)i * ld + a.y] = ca.y * vp[u] + ca.x * vq[u];
+            }
+          }
+        }
       }
       __syncthreads();
     }
@@ -258,6 +327,7 @@ __device__ void potential(Ctx& c, const double* __restrict__ q, double* __restri
 
 // One SCF map evaluation v -> q -> vnew (scf/base.py:651-675, 818-907, 765-792).
 // Returns the electronic free energy of this solve.
+template <bool SM>
 __device__ double fcn(Ctx& c, const double* __restrict__ v, const xtb_scf_opts& o, double nel_a, double nel_b) {
   const int n = c.n, ne = c.ne, ld = c.ld;
   // F = H0 - 1/2 S (v_i + v_j)   -> A buffer (symmetric, zero padded)
@@ -271,8 +341,8 @@ __device__ double fcn(Ctx& c, const double* __restrict__ v, const xtb_scf_opts& 
     c.A[t] = f;
   }
   __syncthreads();
-  gemm_tn(ne, ne, c.A, c.C, ld, c.X, ld, ne);  // X = F C   (F symmetric)
-  gemm_tn(ne, ne, c.C, c.X, ld, c.A, ld, ne);  // A = C^T X
+  gemm_tn<SM>(ne, ne, c.A, c.C, ld, c.X, ld, ne);  // X = F C   (F symmetric)
+  gemm_tn<SM>(ne, ne, c.C, c.X, ld, c.A, ld, ne);  // A = C^T X
   // symmetrise (round-off) and keep the pad row/column exactly zero
   for (int t = threadIdx.x; t < ne * ne; t += NT) {
     const int i = t / ne, j = t - i * ne;
@@ -283,7 +353,7 @@ __device__ double fcn(Ctx& c, const double* __restrict__ v, const xtb_scf_opts& 
     }
   }
   __syncthreads();
-  const int sw = jacobi(c, c.A, c.C, ne, o.jacobi_tol, o.jacobi_max_sweeps);
+  const int sw = jacobi<SM>(c, c.A, c.C, ne, o.jacobi_tol, o.jacobi_max_sweeps);
   if (sw < 0) c.status |= XTB_STATUS_JACOBI_NOT_CONVERGED;
   for (int k = threadIdx.x; k < n; k += NT) c.eps[k] = c.A[(size_t)k * ld + k];
   __syncthreads();
@@ -304,7 +374,7 @@ __device__ double fcn(Ctx& c, const double* __restrict__ v, const xtb_scf_opts& 
     c.X[t] = (i < n) ? sqrt(c.focc[k]) * c.C[(size_t)i * ld + k] : 0.0;
   }
   __syncthreads();
-  gemm_tn(ne, nocc, c.X, c.X, ld, c.A, ld, ne);
+  gemm_tn<SM>(ne, nocc, c.X, c.X, ld, c.A, ld, ne);
   // Mulliken populations and orbital-resolved H0 energies: one warp per row
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   for (int mu = w; mu < n; mu += NT / 32) {
@@ -444,6 +514,7 @@ __device__ bool mix(Ctx& c, Mixer& mx, const xtb_scf_opts& o, double* sm_theta) 
   return conv;
 }
 
+template <bool SM>
 __global__ void __launch_bounds__(NT, 1)
 k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, const double* __restrict__ H0,
       const double* __restrict__ gamma, const double* __restrict__ nel_ab, const double* __restrict__ q0_at, double* __restrict__ work,
@@ -465,14 +536,23 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
   // shared-memory carve-up (sizes by batch maxima so the layout is launch-uniform)
   const int nmx = b.nao_max + 2, nsx = b.nsh_max, nax = b.nat_max;
   double* p = sm;
+  c.cs = p; p += nmx + (nmx & 1);  // double2 per pair: keep 16-byte alignment
+  c.pp = (int*)p; p += nmx + (nmx & 1);  // int2 per pair (over-allocated, keeps the matrices 16-byte aligned)
+  c.qq = c.pp;
   c.eps = p; p += nmx; c.srt = p; p += nmx; c.focc = p; p += nmx; c.v = p; p += nmx; c.vnew = p; p += nmx;
   c.q = p; p += nmx; c.n0 = p; p += nmx; c.eorb = p; p += nmx;
   c.qsh = p; p += nsx; c.vsh = p; p += nsx; c.qat = p; p += nax;
-  c.red = p; p += 32; c.cs = p; p += nmx;
+  c.red = p; p += 32;
   double* sm_theta = p; p += 36;
-  c.pp = (int*)p; p += (nmx + 1) / 2; c.qq = (int*)p; p += (nmx + 1) / 2; c.occl = (int*)p; p += (nmx + 2) / 2 + 1;
+  c.occl = (int*)p; p += (nmx + 2) / 2 + 1;
+  {
+    const int npx = nmx / 2;
+    c.blk = (unsigned*)p; p += (npx * (npx + 1) / 2 + 1) / 2;
+  }
+  p += ((p - sm) & 1);
+  c.smem = SM;
   const size_t msz = (size_t)(n + 1) * (n + 2);
-  if (o.use_smem) {
+  if (SM) {
     const size_t mszx = (size_t)(b.nao_max + 1) * (b.nao_max + 2);
     c.C = p; c.A = p + mszx; c.X = p + 2 * mszx;
   } else {
@@ -498,6 +578,9 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
     const int sh = c.ao_sh[mu];
     c.n0[mu] = b.sh_par[(size_t)(c.s0 + sh) * XTB_SHPAR + XTB_SH_REFOCC] / (double)(2 * b.sh_l[c.s0 + sh] + 1);
   }
+  // (kp, kq) of the lower-triangular pair blocks, kp >= kq (fixed for the whole kernel)
+  for (int kp = threadIdx.x; kp < c.np; kp += NT)
+    for (int kq = 0; kq <= kp; ++kq) c.blk[kp * (kp + 1) / 2 + kq] = ((unsigned)kp << 16) | (unsigned)kq;
   // S-orthonormal start basis: S = U s U^T  ->  C0 = U s^{-1/2}
   for (int t = threadIdx.x; t < ne * ld; t += NT) {
     const int i = t / ld, j = t - i * ld;
@@ -506,7 +589,7 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
   }
   __syncthreads();
   {
-    const int sw = jacobi(c, c.A, c.C, ne, 2e-14, o.jacobi_max_sweeps + 20);
+    const int sw = jacobi<SM>(c, c.A, c.C, ne, 2e-14, o.jacobi_max_sweeps + 20);
     if (sw < 0) c.status |= XTB_STATUS_JACOBI_NOT_CONVERGED;
     bool bad = false;
     for (int k = threadIdx.x; k < n; k += NT) {
@@ -536,19 +619,19 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
   mx.head = 0;
   int iters = 1;
   bool converged = true;
-  double g = fcn(c, c.v, o, nel_a, nel_b);  // evaluated outside the loop (unrolling/default.py:81)
+  double g = fcn<SM>(c, c.v, o, nel_a, nel_b);  // evaluated outside the loop (unrolling/default.py:81)
   if (o.maxiter > 0) {
     converged = false;
     mix(c, mx, o, sm_theta);  // mix_guess (unrolling/default.py:93-94); convergence is not tested here
     for (int it = 0; it < o.maxiter; ++it) {
-      g = fcn(c, c.v, o, nel_a, nel_b);
+      g = fcn<SM>(c, c.v, o, nel_a, nel_b);
       ++iters;
       if (mix(c, mx, o, sm_theta)) { converged = true; break; }
     }
     // converged_to_charges: one more solve with the UN-MIXED potential (scf/base.py:497-501, default.py:111-114)
     for (int k = threadIdx.x; k < n; k += NT) c.v[k] = c.vnew[k];
     __syncthreads();
-    g = fcn(c, c.v, o, nel_a, nel_b);
+    g = fcn<SM>(c, c.v, o, nel_a, nel_b);
   }
   if (!converged) c.status |= XTB_STATUS_SCF_NOT_CONVERGED;
 
@@ -602,14 +685,14 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
       c.A[t] = cv;
     }
     __syncthreads();
-    gemm_tn(ne, nocc, c.X, c.A, ld, Wm, n, n);
+    gemm_tn<SM>(ne, nocc, c.X, c.A, ld, Wm, n, n);
   }
 }
 
 int64_t vec_smem_bytes(const xtb_batch* b) {
-  const int64_t nmx = b->nao_max + 2, nsx = b->nsh_max, nax = b->nat_max;
-  int64_t d = 8 * nmx + 2 * nsx + nax + 32 + nmx + 36;
-  d += (nmx + 1) / 2 * 2 + (nmx + 2) / 2 + 1;
+  const int64_t nmx = b->nao_max + 2, nsx = b->nsh_max, nax = b->nat_max, npx = nmx / 2;
+  int64_t d = 2 * (nmx + (nmx & 1)) + 8 * nmx + 2 * nsx + nax + 32 + 36 + (nmx + 2) / 2 + 1 + (npx * (npx + 1) / 2 + 1) / 2;
+  d += d & 1;
   return d * 8;
 }
 
@@ -641,13 +724,14 @@ extern "C" int xtb_scf_run(const xtb_batch* b, const xtb_scf_opts* o, const doub
   if (o->generations > 5 || o->generations < 1) return -3;
   if (b->nb == 0) return 0;
   int64_t smem = o->use_smem ? xtb_scf_smem_bytes(b) : vec_smem_bytes(b);
-  static int64_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_scf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static int64_t configured[2] = {0, 0};
+  auto kern = o->use_smem ? k_scf<true> : k_scf<false>;
+  if (smem > configured[o->use_smem ? 1 : 0]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    configured = smem;
+    configured[o->use_smem ? 1 : 0] = smem;
   }
-  k_scf<<<b->nb, NT, (size_t)smem, (cudaStream_t)stream>>>(*b, *o, S, H0, gamma, nel_ab, q0_at, (double*)work, q_orb, q_sh, q_at,
-                                                            v_orb, e_atom, fenergy, emo, occ, iterations, status, P, W);
+  kern<<<b->nb, NT, (size_t)smem, (cudaStream_t)stream>>>(*b, *o, S, H0, gamma, nel_ab, q0_at, (double*)work, q_orb, q_sh, q_at,
+                                                           v_orb, e_atom, fenergy, emo, occ, iterations, status, P, W);
   return launch_status();
 }
