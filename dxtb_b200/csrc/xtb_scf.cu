@@ -27,12 +27,13 @@ struct Ctx {
   const double *S, *H0, *gam;    // global, n x n / ns x ns
   double *eps, *srt, *focc, *v, *vnew, *q, *n0, *eorb, *qsh, *vsh, *qat, *red, *cs;
   int *pp, *qq, *occl;
-  unsigned* blk;                 // (kp << 16 | kq) for the lower-triangular pair blocks
+  double *jq, *jm, *jr;          // block-Jacobi scratch: accumulated rotations / sub-problem copies / rotation params
   bool smem;                     // matrices live in shared memory
   const int *ao_sh, *sh_atom, *at_sh0, *at_nsh, *sh_ao, *sh_l;
   const double* gam3;            // at_par base (stride XTB_ATPAR)
   double *xh, *fh;               // Anderson history [gen+1][n] (global)
   int status;
+  int sweeps;                    // diagnostic: total Jacobi sweeps of this molecule
 };
 
 // Address-space hint: lets the compiler emit LDS/STS (32-bit addressing) instead of generic LD/ST.
@@ -80,119 +81,192 @@ __device__ void gemm_tn(int ne, int K, const double* __restrict__ L, const doubl
   __syncthreads();
 }
 
-// Cyclic Jacobi with round-robin parallel ordering on the symmetric ne x ne matrix A (full storage, both
-// triangles kept consistent), accumulating the rotations into the columns of V (nrow rows).
-// Per round: (1) np = ne/2 threads compute the rotations of the disjoint pairs, (2) the 2x2 blocks
-// (pair kp) x (pair kq), kp >= kq, are transformed J_kp^T a J_kq and written to both triangles, and every
-// row of V gets its np column rotations.  Loads of a batch are issued before the dependent math/stores so
-// that several independent items are in flight per thread.  Returns the number of sweeps, or -sweeps if the
-// off-diagonal did not drop below tol.
+// fp64 tensor-core MMA, D(8x8) += A(8x4, row) * B(4x8, col).  Lane l holds A[l/4][l%4], B[l%4][l/4],
+// D[l/4][2*(l%4) + {0,1}].  SASS: DMMA.8x8x4.
+XTB_DEV void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// named barrier for a group of 4 warps (ids 1..8; id 0 is __syncthreads)
+XTB_DEV void group_bar(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
+
+constexpr int JB = 8;        // Jacobi block size
+constexpr int JB2 = 2 * JB;  // indices of a block pair
+constexpr int MLD = 17;      // leading dimension of the 16x16 sub-problem copy
+constexpr int QLD = 20;      // leading dimension of the accumulated 16x16 rotation (== 4 mod 16: conflict-free DMMA fragments)
+
+// Global index of local index l (0..15) of block pair (I, J).
+XTB_DEV int bp_index(int I, int J, int l) { return (l < JB ? I * JB : J * JB - JB) + l; }
+
+// BLOCKED two-sided Jacobi (block size 8) on the symmetric ne x ne matrix A (ne % 16 == 0), accumulating
+// the transformation into the columns of V (ne rows).
+//   Per block round (round-robin over the ne/8 blocks, ne/16 disjoint block pairs):
+//   1. one warp per block pair copies its 16x16 sub-matrix, runs the scalar rotations of the pair on the
+//      copy (warp-synchronous, no CTA barrier) and accumulates them into a 16x16 orthogonal Q;
+//   2. all warps apply the Q's with fp64 tensor-core MMAs: A <- A Q (columns), V <- V Q, then A <- Q^T A (rows).
+//   A sweep = one "self" round (pairs (0,1),(2,3),.. with all 120 index pairs of the 16) followed by the
+//   nblk-1 round-robin rounds in which only the 64 cross pairs of a block pair are rotated.
+// Compared with rotating the full matrix after every scalar rotation round this moves A and V through
+// shared memory ~10x instead of ~80x per sweep.  Returns the number of sweeps, or -sweeps if not converged.
 template <bool SM>
 __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, int nrow, double tol, int maxsweeps) {
-  const int ne = c.ne, ld = c.ld, np = c.np;
-  const int nblk = np * (np + 1) / 2;
-  int2* pq = reinterpret_cast<int2*>(c.pp);
-  double2* cs = reinterpret_cast<double2*>(c.cs);
-  const unsigned* blk = c.blk;
-  XTB_ASSUME_SHARED(pq); XTB_ASSUME_SHARED(cs); XTB_ASSUME_SHARED(blk);
-  if (SM) { XTB_ASSUME_SHARED(A); XTB_ASSUME_SHARED(V); }
-  // fixed thread -> (column pair, first row) map of the V update
-  const int vk = threadIdx.x % np, vi0 = threadIdx.x / np, vstep = NT / np;
+  const int ne = c.ne, ld = c.ld;
+  const int nblk = ne / JB, nbp = nblk / 2, ntile = ne / 8;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = NT / 32;
+  constexpr int NG = NW / 4;  // thread groups of 4 warps for the sub-problems
+  const int grp = warp >> 2, gt = threadIdx.x & 127;
+  double* Qs = c.jq;  // [nbp][16][QLD]
+  double* Ms = c.jm;  // [nbp][16][MLD]
+  double* Rs = c.jr;  // [nbp][32] rotation parameters of the current inner round
+  int* bij = c.pp;    // [nbp][2] blocks of the pairs of this round
+  XTB_ASSUME_SHARED(bij);
+  if (SM) { XTB_ASSUME_SHARED(A); XTB_ASSUME_SHARED(V); XTB_ASSUME_SHARED(Qs); XTB_ASSUME_SHARED(Ms); XTB_ASSUME_SHARED(Rs); }
+  (void)nrow;
   int sweep = 0;
   for (;;) {
     double off = 0.0;
-    for (int i = threadIdx.x / 32; i < ne; i += NT / 32) {
+    for (int i = warp; i < ne; i += NW) {
       const double* row = A + (size_t)i * ld;
-      for (int j = threadIdx.x & 31; j < ne; j += 32)
+      for (int j = lane; j < ne; j += 32)
         if (i != j) off = fmax(off, fabs(row[j]));
     }
     off = block_max(off, c.red);
     if (off <= tol) return sweep;
     if (sweep >= maxsweeps) return -sweep;
     ++sweep;
-    for (int r = 0; r < ne - 1; ++r) {
-      for (int k = threadIdx.x; k < np; k += NT) {
-        int p, q;
-        if (k == 0) { p = r; q = ne - 1; }
+    for (int r = -1; r < nblk - 1; ++r) {
+      // ---- 1. sub-problems: a group of 4 warps (128 threads, named barrier) owns a block pair ----------
+      for (int w = grp; w < nbp; w += NG) {
+        int I, J;
+        if (r < 0) { I = 2 * w; J = 2 * w + 1; }
+        else if (w == 0) { I = r; J = nblk - 1; }
         else {
-          p = r + k; if (p >= ne - 1) p -= ne - 1;
-          q = r - k; if (q < 0) q += ne - 1;
+          I = (r + w) % (nblk - 1);
+          J = (r - w + 2 * (nblk - 1)) % (nblk - 1);
         }
-        if (p > q) { const int t = p; p = q; q = t; }
-        const double app = A[(size_t)p * ld + p], aqq = A[(size_t)q * ld + q], apq = A[(size_t)p * ld + q];
-        double cc = 1.0, ss = 0.0;
-        if (fabs(apq) > 1e-150) {
-          // t = 2 apq / (d + sign(d) sqrt(d^2 + 4 apq^2)); c = 1/sqrt(1+t^2); s = t c.
-          // Only c^2 + s^2 = 1 has to hold to round-off (rsqrt is ~1 ulp); the angle itself may be approximate.
-          const double d = aqq - app;
-          const double x = d * d + 4.0 * apq * apq;
-          const double y = d + copysign(x * rsqrt(x), d);
-          const double t = 2.0 * apq * copysign(rsqrt(y * y), y);
-          cc = rsqrt(1.0 + t * t);
-          ss = t * cc;
+        if (I > J) { const int t = I; I = J; J = t; }
+        double* M = Ms + w * (JB2 * MLD);
+        double* Q = Qs + w * (JB2 * QLD);
+        double* rcs = Rs + w * 32;                          // [8][c, s]
+        int* rpq = reinterpret_cast<int*>(rcs + 16);        // [8][p, q]
+        if (gt == 0) { bij[2 * w] = I; bij[2 * w + 1] = J; }
+        for (int e = gt; e < JB2 * JB2; e += 128) {
+          const int rr = e >> 4, cc = e & 15;
+          M[rr * MLD + cc] = A[(size_t)bp_index(I, J, rr) * ld + bp_index(I, J, cc)];
+          Q[rr * QLD + cc] = (rr == cc) ? 1.0 : 0.0;
         }
-        pq[k] = make_int2(p, q);
-        cs[k] = make_double2(cc, ss);
+        group_bar(grp);
+        const int nin = (r < 0) ? JB2 - 1 : JB;
+        for (int t = 0; t < nin; ++t) {
+          if (gt < 8) {
+            // the 8 disjoint index pairs of this inner round
+            const int l = gt;
+            int p, q;
+            if (r < 0) {
+              if (l == 0) { p = t; q = JB2 - 1; }
+              else { p = t + l; if (p >= JB2 - 1) p -= JB2 - 1; q = t - l; if (q < 0) q += JB2 - 1; }
+              if (p > q) { const int x = p; p = q; q = x; }
+            } else {
+              p = l; q = JB + ((l + t) & (JB - 1));
+            }
+            const double app = M[p * MLD + p], aqq = M[q * MLD + q], apq = M[p * MLD + q];
+            double cs_ = 1.0, sn = 0.0;
+            // Rotation angle in fp32 (its accuracy only affects how completely apq is annihilated: the next
+            // digit-doubling sweep removes any residual), c and s in fp64 with c^2 + s^2 = 1 to round-off:
+            //   t = 2 apq / (d + sign(d) sqrt(d^2 + 4 apq^2)),  c = 1/sqrt(1 + t^2),  s = t c.
+            const float df = (float)(aqq - app), af = (float)apq;
+            const float x = df * df + 4.0f * af * af;
+            if (x > 1e-36f) {
+              const float y = df + copysignf(sqrtf(x), df);
+              const double tt = (double)__fdividef(2.0f * af, y);
+              const double z = 1.0 + tt * tt;  // in [1, 2]: rsqrt by fp32 seed + 2 Newton steps, no special cases
+              double rs = (double)rsqrtf((float)z);
+              rs = rs * (1.5 - 0.5 * z * rs * rs);
+              rs = rs * (1.5 - 0.5 * z * rs * rs);
+              cs_ = rs;
+              sn = tt * rs;
+            }
+            rcs[2 * l] = cs_; rcs[2 * l + 1] = sn;
+            rpq[2 * l] = p; rpq[2 * l + 1] = q;
+          }
+          group_bar(grp);
+          if (gt < 64) {  // M <- J^T M J on the 8x8 grid of 2x2 blocks
+            const int kp = gt >> 3, kq = gt & 7;
+            const int p1 = rpq[2 * kp], q1 = rpq[2 * kp + 1], p2 = rpq[2 * kq], q2 = rpq[2 * kq + 1];
+            const double c1 = rcs[2 * kp], s1 = rcs[2 * kp + 1], c2 = rcs[2 * kq], s2 = rcs[2 * kq + 1];
+            const double a00 = M[p1 * MLD + p2], a01 = M[p1 * MLD + q2], a10 = M[q1 * MLD + p2], a11 = M[q1 * MLD + q2];
+            const double x00 = c1 * a00 - s1 * a10, x01 = c1 * a01 - s1 * a11;
+            const double x10 = s1 * a00 + c1 * a10, x11 = s1 * a01 + c1 * a11;
+            double y00 = c2 * x00 - s2 * x01, y01 = s2 * x00 + c2 * x01;
+            double y10 = c2 * x10 - s2 * x11, y11 = s2 * x10 + c2 * x11;
+            if (kp == kq) { y01 = 0.0; y10 = 0.0; }
+            M[p1 * MLD + p2] = y00; M[p1 * MLD + q2] = y01; M[q1 * MLD + p2] = y10; M[q1 * MLD + q2] = y11;
+          }
+          {  // Q <- Q J: 16 rows x 8 pairs, one item per thread
+            const int i = gt >> 3, k = gt & 7;
+            const int p = rpq[2 * k], q = rpq[2 * k + 1];
+            const double cs_ = rcs[2 * k], sn = rcs[2 * k + 1];
+            const double vp = Q[i * QLD + p], vq = Q[i * QLD + q];
+            Q[i * QLD + p] = cs_ * vp - sn * vq;
+            Q[i * QLD + q] = sn * vp + cs_ * vq;
+          }
+          group_bar(grp);
+        }
       }
       __syncthreads();
-      // ---- A <- J^T A J on the blocks kp >= kq --------------------------------------------------
-      constexpr int UA = 1;
-      for (int tb = threadIdx.x; tb < nblk; tb += NT * UA) {
-        int p1[UA], q1[UA], p2[UA], q2[UA];
-        double c1[UA], s1[UA], c2[UA], s2[UA], a00[UA], a01[UA], a10[UA], a11[UA];
-        bool dg[UA], ok[UA];
+      // ---- 2a. column passes: A[:, idx] <- A[:, idx] Q and V[:, idx] <- V[:, idx] Q (m8 n16 k16 per unit) ----
+      {
+        const int nunit = 2 * ntile * nbp;
+        const int g = lane >> 2, tg = lane & 3;
+        for (int u = warp; u < nunit; u += NW) {
+          const int which = u >= ntile * nbp;
+          const int rem = u - which * (ntile * nbp);
+          const int k = (int)__fdividef((float)rem + 0.5f, (float)ntile), rt = rem - k * ntile;
+          double* Mx = which ? V : A;
+          const int I = bij[2 * k], J = bij[2 * k + 1];
+          const double* Q = Qs + k * (JB2 * QLD);
+          double* row = Mx + (size_t)(rt * 8 + g) * ld;
+          double af[4];
 #pragma unroll
-        for (int u = 0; u < UA; ++u) {
-          const int t = tb + u * NT;
-          ok[u] = t < nblk;
-          const unsigned code = ok[u] ? blk[t] : 0u;
-          const int kp = (int)(code >> 16), kq = (int)(code & 0xffffu);
-          dg[u] = kp == kq;
-          if (ok[u]) {
-            const int2 a = pq[kp], b = pq[kq];
-            const double2 ca = cs[kp], cb = cs[kq];
-            p1[u] = a.x; q1[u] = a.y; p2[u] = b.x; q2[u] = b.y;
-            c1[u] = ca.x; s1[u] = ca.y; c2[u] = cb.x; s2[u] = cb.y;
-            const double* r0 = A + (size_t)p1[u] * ld;
-            const double* r1 = A + (size_t)q1[u] * ld;
-            a00[u] = r0[p2[u]]; a01[u] = r0[q2[u]]; a10[u] = r1[p2[u]]; a11[u] = r1[q2[u]];
+          for (int kk = 0; kk < 4; ++kk) af[kk] = row[bp_index(I, J, 4 * kk + tg)];
+          double d[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) dmma884(d[nt][0], d[nt][1], af[kk], Q[(4 * kk + tg) * QLD + 8 * nt + g]);
           }
-        }
 #pragma unroll
-        for (int u = 0; u < UA; ++u) {
-          if (!ok[u]) continue;
-          const double x00 = c1[u] * a00[u] - s1[u] * a10[u], x01 = c1[u] * a01[u] - s1[u] * a11[u];
-          const double x10 = s1[u] * a00[u] + c1[u] * a10[u], x11 = s1[u] * a01[u] + c1[u] * a11[u];
-          double y00 = c2[u] * x00 - s2[u] * x01, y01 = s2[u] * x00 + c2[u] * x01;
-          double y10 = c2[u] * x10 - s2[u] * x11, y11 = s2[u] * x10 + c2[u] * x11;
-          if (dg[u]) { y01 = 0.0; y10 = 0.0; }
-          A[(size_t)p1[u] * ld + p2[u]] = y00; A[(size_t)p1[u] * ld + q2[u]] = y01;
-          A[(size_t)q1[u] * ld + p2[u]] = y10; A[(size_t)q1[u] * ld + q2[u]] = y11;
-          if (!dg[u]) {
-            A[(size_t)p2[u] * ld + p1[u]] = y00; A[(size_t)q2[u] * ld + p1[u]] = y01;
-            A[(size_t)p2[u] * ld + q1[u]] = y10; A[(size_t)q2[u] * ld + q1[u]] = y11;
+          for (int nt = 0; nt < 2; ++nt) {
+            const int col = bp_index(I, J, 8 * nt + 2 * tg);  // 2*tg and 2*tg+1 are in the same 8-block: contiguous
+            row[col] = d[nt][0];
+            row[col + 1] = d[nt][1];
           }
         }
       }
-      // ---- V <- V J: thread owns column pair vk and rows vi0, vi0 + vstep, ... --------------------
-      if (vi0 < vstep) {
-        const int2 a = pq[vk];
-        const double2 ca = cs[vk];
-        constexpr int UV = 3;
-        for (int ib = vi0; ib < nrow; ib += vstep * UV) {
-          double vp[UV], vq[UV];
+      __syncthreads();
+      // ---- 2b. row pass: A[idx, :] <- Q^T A[idx, :] (m16 n8 k16 per unit) ------------------------------
+      {
+        const int nunit = ntile * nbp;
+        const int g = lane >> 2, tg = lane & 3;
+        for (int u = warp; u < nunit; u += NW) {
+          const int k = (int)__fdividef((float)u + 0.5f, (float)ntile), ct = u - k * ntile;
+          const int I = bij[2 * k], J = bij[2 * k + 1];
+          const double* Q = Qs + k * (JB2 * QLD);
+          double bf[4];
 #pragma unroll
-          for (int u = 0; u < UV; ++u) {
-            const int i = ib + u * vstep;
-            if (i < nrow) { vp[u] = V[(size_t)i * ld + a.x]; vq[u] = V[(size_t)i * ld + a.y]; }
+          for (int kk = 0; kk < 4; ++kk) bf[kk] = A[(size_t)bp_index(I, J, 4 * kk + tg) * ld + ct * 8 + g];
+          double d[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) dmma884(d[mt][0], d[mt][1], Q[(4 * kk + tg) * QLD + 8 * mt + g], bf[kk]);
           }
 #pragma unroll
-          for (int u = 0; u < UV; ++u) {
-            const int i = ib + u * vstep;
-            if (i < nrow) {
-              V[(size_t)i * ld + a.x] = ca.x * vp[u] - ca.y * vq[u];
-              V[(size_t)i * ld + a.y] = ca.y * vp[u] + ca.x * vq[u];
-            }
+          for (int mt = 0; mt < 2; ++mt) {
+            double* row = A + (size_t)bp_index(I, J, 8 * mt + g) * ld + ct * 8 + 2 * tg;
+            row[0] = d[mt][0];
+            row[1] = d[mt][1];
           }
         }
       }
@@ -355,6 +429,7 @@ __device__ double fcn(Ctx& c, const double* __restrict__ v, const xtb_scf_opts& 
   __syncthreads();
   const int sw = jacobi<SM>(c, c.A, c.C, ne, o.jacobi_tol, o.jacobi_max_sweeps);
   if (sw < 0) c.status |= XTB_STATUS_JACOBI_NOT_CONVERGED;
+  c.sweeps += sw < 0 ? -sw : sw;
   for (int k = threadIdx.x; k < n; k += NT) c.eps[k] = c.A[(size_t)k * ld + k];
   __syncthreads();
   const double g = fermi_fill(c, nel_a, nel_b, o);
@@ -528,10 +603,11 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
   c.n = b.ao_off[m + 1] - c.o0;
   c.ns = b.sh_off[m + 1] - c.s0;
   c.na = b.at_off[m + 1] - c.a0;
-  c.ne = c.n + (c.n & 1);
-  c.ld = c.ne + 1;
+  c.ne = (c.n + 15) & ~15;  // padded to a multiple of 16 (block-pair size of the Jacobi solver)
+  c.ld = c.ne + 4;          // == 4 (mod 16): conflict-free tensor-core fragment loads
   c.np = c.ne / 2;
   c.status = 0;
+  c.sweeps = 0;
   const int n = c.n, ne = c.ne, ld = c.ld;
   // shared-memory carve-up (sizes by batch maxima so the layout is launch-uniform)
   const int nmx = b.nao_max + 2, nsx = b.nsh_max, nax = b.nat_max;
@@ -545,19 +621,26 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
   c.red = p; p += 32;
   double* sm_theta = p; p += 36;
   c.occl = (int*)p; p += (nmx + 2) / 2 + 1;
-  {
-    const int npx = nmx / 2;
-    c.blk = (unsigned*)p; p += (npx * (npx + 1) / 2 + 1) / 2;
+  if (SM) {
+    const int nbpx = (b.nao_max + 15) / 16;
+    c.jq = p; p += nbpx * JB2 * QLD;
+    c.jm = p; p += nbpx * JB2 * MLD;
+    c.jr = p; p += nbpx * 32;
   }
   p += ((p - sm) & 1);
   c.smem = SM;
-  const size_t msz = (size_t)(n + 1) * (n + 2);
+  const size_t msz = (size_t)ne * ld;
   if (SM) {
-    const size_t mszx = (size_t)(b.nao_max + 1) * (b.nao_max + 2);
+    const size_t nex = (size_t)((b.nao_max + 15) & ~15);
+    const size_t mszx = nex * (nex + 4);
     c.C = p; c.A = p + mszx; c.X = p + 2 * mszx;
   } else {
-    double* wm = work + (size_t)(o.generations + 1) * 2 * b.nao_tot + 3 * ((size_t)b.mat_off[m] + 3 * (size_t)c.o0 + 2 * (size_t)m);
+    double* wm = work + (size_t)(o.generations + 1) * 2 * b.nao_tot + 3 * ((size_t)b.mat_off[m] + 34 * (size_t)c.o0 + 285 * (size_t)m);  // sum of (n+15)(n+19) bounds ne*ld
     c.C = wm; c.A = wm + msz; c.X = wm + 2 * msz;
+    // block-Jacobi scratch of this molecule: nbp * (16 * (QLD + MLD) + 32) <= 39 n + 624 doubles
+    double* ws = work + (size_t)(o.generations + 1) * 2 * b.nao_tot + 3 * ((size_t)b.mat_total + 34 * (size_t)b.nao_tot + 285 * (size_t)b.nb) +
+                 39 * (size_t)c.o0 + 624 * (size_t)m;
+    c.jq = ws; c.jm = ws + (size_t)(ne / 16) * JB2 * QLD; c.jr = c.jm + (size_t)(ne / 16) * JB2 * MLD;
   }
   c.xh = work + (size_t)(o.generations + 1) * 2 * c.o0;
   c.fh = c.xh + (size_t)(o.generations + 1) * n;
@@ -578,9 +661,6 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
     const int sh = c.ao_sh[mu];
     c.n0[mu] = b.sh_par[(size_t)(c.s0 + sh) * XTB_SHPAR + XTB_SH_REFOCC] / (double)(2 * b.sh_l[c.s0 + sh] + 1);
   }
-  // (kp, kq) of the lower-triangular pair blocks, kp >= kq (fixed for the whole kernel)
-  for (int kp = threadIdx.x; kp < c.np; kp += NT)
-    for (int kq = 0; kq <= kp; ++kq) c.blk[kp * (kp + 1) / 2 + kq] = ((unsigned)kp << 16) | (unsigned)kq;
   // S-orthonormal start basis: S = U s U^T  ->  C0 = U s^{-1/2}
   for (int t = threadIdx.x; t < ne * ld; t += NT) {
     const int i = t / ld, j = t - i * ld;
@@ -591,6 +671,7 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
   {
     const int sw = jacobi<SM>(c, c.A, c.C, ne, 2e-14, o.jacobi_max_sweeps + 20);
     if (sw < 0) c.status |= XTB_STATUS_JACOBI_NOT_CONVERGED;
+    c.sweeps += sw < 0 ? -sw : sw;
     bool bad = false;
     for (int k = threadIdx.x; k < n; k += NT) {
       const double s = c.A[(size_t)k * ld + k];
@@ -665,7 +746,7 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
   if (threadIdx.x == 0) {
     fenergy[m] = g;
     iterations[m] = iters;
-    status[m] = c.status;
+    status[m] = c.status | (c.sweeps << 8);  // bits 8..: total Jacobi sweeps (diagnostic)
   }
   if (o.want_density) {
     double* Pm = Pout + b.mat_off[m];
@@ -690,8 +771,8 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
 }
 
 int64_t vec_smem_bytes(const xtb_batch* b) {
-  const int64_t nmx = b->nao_max + 2, nsx = b->nsh_max, nax = b->nat_max, npx = nmx / 2;
-  int64_t d = 2 * (nmx + (nmx & 1)) + 8 * nmx + 2 * nsx + nax + 32 + 36 + (nmx + 2) / 2 + 1 + (npx * (npx + 1) / 2 + 1) / 2;
+  const int64_t nmx = b->nao_max + 2, nsx = b->nsh_max, nax = b->nat_max;
+  int64_t d = 2 * (nmx + (nmx & 1)) + 8 * nmx + 2 * nsx + nax + 32 + 36 + (nmx + 2) / 2 + 1;
   d += d & 1;
   return d * 8;
 }
@@ -700,7 +781,8 @@ int64_t vec_smem_bytes(const xtb_batch* b) {
 
 extern "C" int64_t xtb_scf_smem_bytes(const xtb_batch* b) {
   if (!b) return -1;
-  return vec_smem_bytes(b) + 3 * (int64_t)(b->nao_max + 1) * (b->nao_max + 2) * 8;
+  const int64_t nex = (b->nao_max + 15) & ~15;
+  return vec_smem_bytes(b) + (3 * nex * (nex + 4) + (nex / 16) * (JB2 * (QLD + MLD) + 32)) * 8;
 }
 
 extern "C" int64_t xtb_scf_workspace_bytes(const xtb_batch* b, const xtb_scf_opts* o) {
@@ -708,7 +790,8 @@ extern "C" int64_t xtb_scf_workspace_bytes(const xtb_batch* b, const xtb_scf_opt
   int64_t d = (int64_t)(o->generations + 1) * 2 * b->nao_tot;
   if (!o->use_smem) {
     // 3 matrices of (n+1)(n+2) per molecule: 3 (sum n^2 + 3 sum n + 2 nb)
-    d += 3 * (b->mat_total + 3 * (int64_t)b->nao_tot + 2 * (int64_t)b->nb);
+    d += 3 * (b->mat_total + 34 * (int64_t)b->nao_tot + 285 * (int64_t)b->nb);
+    d += 39 * (int64_t)b->nao_tot + 624 * (int64_t)b->nb;
   }
   return d * 8 + 256;
 }

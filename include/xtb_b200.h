@@ -102,6 +102,7 @@ typedef struct xtb_scf_opts {
 #define XTB_STATUS_FERMI_FAILED 2
 #define XTB_STATUS_JACOBI_NOT_CONVERGED 4
 #define XTB_STATUS_S_NOT_POSDEF 8
+#define XTB_STATUS_SWEEPS_SHIFT 8 /* bits 8..: total Jacobi sweeps of the molecule (diagnostic) */
 
 int xtb_version(void);
 

@@ -22,4 +22,5 @@ for s in range(reps):
     e = calc.get_energy(p, chrg)
     (g,) = torch.autograd.grad(e.sum(), p)
 torch.cuda.synchronize()
-print("ok", float(e.sum()))
+st = calc.cache["status"]
+print("ok", float(e.sum()), "mean sweeps", float((st >> 8).float().mean()), "mean iters", float(calc.get_iterations().float().mean()))
