@@ -46,7 +46,7 @@ class XtbScfOpts(C.Structure):
         ("fermi_maxiter", C.c_int32), ("want_density", C.c_int32), ("use_smem", C.c_int32), ("jacobi_max_sweeps", C.c_int32),
         ("damp", C.c_double), ("damp_init", C.c_double), ("diag_offset", C.c_double),
         ("x_atol", C.c_double), ("x_atol_max", C.c_double), ("kt", C.c_double), ("fermi_thresh", C.c_double),
-        ("jacobi_tol", C.c_double),
+        ("jacobi_tol", C.c_double), ("jacobi_tol_iter", C.c_double),
     ]
 
 

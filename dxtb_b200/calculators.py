@@ -246,6 +246,8 @@ class GFN1Calculator:
         s.kt = float(o["fermi_etemp"]) * self.par.KELVIN2AU  # scf/base.py:291
         s.fermi_thresh = math.sqrt(torch.finfo(torch.float64).eps) if o["fermi_thresh"] is None else float(o["fermi_thresh"])
         s.jacobi_tol = 1e-13
+        # intermediate map evaluations: eigensolver residual 4 orders below the SCF convergence threshold
+        s.jacobi_tol_iter = min(2e-9, max(s.jacobi_tol, 1e-4 * min(s.x_atol, s.x_atol_max)))
         return s
 
     def _electrons(self, chrg: torch.Tensor, spin: torch.Tensor | None) -> torch.Tensor:

@@ -172,44 +172,40 @@ __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, in
             }
             const double app = M[p * MLD + p], aqq = M[q * MLD + q], apq = M[p * MLD + q];
             double cs_ = 1.0, sn = 0.0;
-            // Rotation angle in fp32 (its accuracy only affects how completely apq is annihilated: the next
-            // digit-doubling sweep removes any residual), c and s in fp64 with c^2 + s^2 = 1 to round-off:
-            //   t = 2 apq / (d + sign(d) sqrt(d^2 + 4 apq^2)),  c = 1/sqrt(1 + t^2),  s = t c.
-            const float df = (float)(aqq - app), af = (float)apq;
-            const float x = df * df + 4.0f * af * af;
-            if (x > 1e-36f) {
-              const float y = df + copysignf(sqrtf(x), df);
-              const double tt = (double)__fdividef(2.0f * af, y);
-              const double z = 1.0 + tt * tt;  // in [1, 2]: rsqrt by fp32 seed + 2 Newton steps, no special cases
-              double rs = (double)rsqrtf((float)z);
-              rs = rs * (1.5 - 0.5 * z * rs * rs);
-              rs = rs * (1.5 - 0.5 * z * rs * rs);
-              cs_ = rs;
-              sn = tt * rs;
+            // t = 2 apq / (d + sign(d) sqrt(d^2 + 4 apq^2)),  c = 1/sqrt(1 + t^2),  s = t c.  Reciprocals via rsqrt
+            // (62-cycle chain on sm_100a, tools/microbench): only c^2 + s^2 = 1 has to hold to round-off, the angle
+            // itself may carry a few ulp (the next digit-doubling sweep removes any residual).
+            const double d = aqq - app;
+            const double x = d * d + 4.0 * apq * apq;
+            if (x > 1e-280) {
+              const double y = d + copysign(x * rsqrt(x), d);  // |y| >= sqrt(x) > 0
+              const double tt = 2.0 * apq * copysign(rsqrt(y * y), y);
+              cs_ = rsqrt(1.0 + tt * tt);
+              sn = tt * cs_;
             }
             rcs[2 * l] = cs_; rcs[2 * l + 1] = sn;
             rpq[2 * l] = p; rpq[2 * l + 1] = q;
           }
           group_bar(grp);
-          if (gt < 64) {  // M <- J^T M J on the 8x8 grid of 2x2 blocks
-            const int kp = gt >> 3, kq = gt & 7;
+          {
+            // M <- J^T M J on the 8x8 grid of 2x2 blocks (threads 0..63) and Q <- Q J (16 rows x 8 pairs, all 128
+            // threads); every load is issued before the first dependent store
+            const int kp = (gt >> 3) & 7, kq = gt & 7, qi = gt >> 3;
             const int p1 = rpq[2 * kp], q1 = rpq[2 * kp + 1], p2 = rpq[2 * kq], q2 = rpq[2 * kq + 1];
             const double c1 = rcs[2 * kp], s1 = rcs[2 * kp + 1], c2 = rcs[2 * kq], s2 = rcs[2 * kq + 1];
-            const double a00 = M[p1 * MLD + p2], a01 = M[p1 * MLD + q2], a10 = M[q1 * MLD + p2], a11 = M[q1 * MLD + q2];
-            const double x00 = c1 * a00 - s1 * a10, x01 = c1 * a01 - s1 * a11;
-            const double x10 = s1 * a00 + c1 * a10, x11 = s1 * a01 + c1 * a11;
-            double y00 = c2 * x00 - s2 * x01, y01 = s2 * x00 + c2 * x01;
-            double y10 = c2 * x10 - s2 * x11, y11 = s2 * x10 + c2 * x11;
-            if (kp == kq) { y01 = 0.0; y10 = 0.0; }
-            M[p1 * MLD + p2] = y00; M[p1 * MLD + q2] = y01; M[q1 * MLD + p2] = y10; M[q1 * MLD + q2] = y11;
-          }
-          {  // Q <- Q J: 16 rows x 8 pairs, one item per thread
-            const int i = gt >> 3, k = gt & 7;
-            const int p = rpq[2 * k], q = rpq[2 * k + 1];
-            const double cs_ = rcs[2 * k], sn = rcs[2 * k + 1];
-            const double vp = Q[i * QLD + p], vq = Q[i * QLD + q];
-            Q[i * QLD + p] = cs_ * vp - sn * vq;
-            Q[i * QLD + q] = sn * vp + cs_ * vq;
+            const double vp = Q[qi * QLD + p2], vq = Q[qi * QLD + q2];
+            double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+            if (gt < 64) { a00 = M[p1 * MLD + p2]; a01 = M[p1 * MLD + q2]; a10 = M[q1 * MLD + p2]; a11 = M[q1 * MLD + q2]; }
+            Q[qi * QLD + p2] = c2 * vp - s2 * vq;
+            Q[qi * QLD + q2] = s2 * vp + c2 * vq;
+            if (gt < 64) {
+              const double x00 = c1 * a00 - s1 * a10, x01 = c1 * a01 - s1 * a11;
+              const double x10 = s1 * a00 + c1 * a10, x11 = s1 * a01 + c1 * a11;
+              double y00 = c2 * x00 - s2 * x01, y01 = s2 * x00 + c2 * x01;
+              double y10 = c2 * x10 - s2 * x11, y11 = s2 * x10 + c2 * x11;
+              if (kp == kq) { y01 = 0.0; y10 = 0.0; }
+              M[p1 * MLD + p2] = y00; M[p1 * MLD + q2] = y01; M[q1 * MLD + p2] = y10; M[q1 * MLD + q2] = y11;
+            }
           }
           group_bar(grp);
         }
@@ -399,10 +395,69 @@ __device__ void potential(Ctx& c, const double* __restrict__ q, double* __restri
   __syncthreads();
 }
 
+// In-CTA right-looking Cholesky S = L L^T (lower triangle, in the A buffer), X = L^{-1} by forward substitution
+// (thread per column, X buffer), C = X^T.  Returns false if S is not positive definite.
+template <bool SM>
+__device__ bool cholesky_start_basis(Ctx& c) {
+  const int n = c.n, ne = c.ne, ld = c.ld;
+  double* A = c.A; double* X = c.X; double* C = c.C; double* lk = c.srt;
+  if (SM) { XTB_ASSUME_SHARED(A); XTB_ASSUME_SHARED(X); XTB_ASSUME_SHARED(C); }
+  XTB_ASSUME_SHARED(lk);
+  for (int t = threadIdx.x; t < ne * ld; t += NT) {
+    const int i = t / ld, j = t - i * ld;
+    A[t] = (i < n && j < n) ? c.S[(size_t)i * n + j] : 0.0;
+    X[t] = 0.0;
+    C[t] = 0.0;
+  }
+  __syncthreads();
+  bool ok = true;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k = 0; k < n; ++k) {
+    const double akk = A[(size_t)k * ld + k];
+    if (!(akk > 0.0)) ok = false;
+    const double inv = (akk > 0.0) ? rsqrt(akk) : 0.0;
+    // column k of L, also staged contiguously in lk[]
+    for (int i = k + threadIdx.x; i < n; i += NT) lk[i] = (i == k) ? akk * inv : A[(size_t)i * ld + k] * inv;
+    __syncthreads();
+    for (int i = k + threadIdx.x; i < n; i += NT) A[(size_t)i * ld + k] = lk[i];
+    // trailing update of the lower triangle: A[i][j] -= L[i][k] L[j][k], k < j <= i
+    for (int i = k + 1 + warp; i < n; i += NT / 32) {
+      const double li = lk[i];
+      double* row = A + (size_t)i * ld;
+      for (int j = k + 1 + lane; j <= i; j += 32) row[j] = fma(-li, lk[j], row[j]);
+    }
+    __syncthreads();
+  }
+  // X = L^{-1}: thread j owns column j (consecutive threads -> consecutive words: no bank conflicts)
+  for (int j = threadIdx.x; j < n; j += NT) {
+    for (int i = j; i < n; ++i) {
+      const double* lrow = A + (size_t)i * ld;
+      double s0 = (i == j) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int k = j;
+      for (; k + 3 < i; k += 4) {
+        s0 = fma(-lrow[k], X[(size_t)k * ld + j], s0);
+        s1 = fma(-lrow[k + 1], X[(size_t)(k + 1) * ld + j], s1);
+        s2 = fma(-lrow[k + 2], X[(size_t)(k + 2) * ld + j], s2);
+        s3 = fma(-lrow[k + 3], X[(size_t)(k + 3) * ld + j], s3);
+      }
+      for (; k < i; ++k) s0 = fma(-lrow[k], X[(size_t)k * ld + j], s0);
+      X[(size_t)i * ld + j] = ((s0 + s1) + (s2 + s3)) / lrow[i];
+    }
+  }
+  __syncthreads();
+  // C0 = X^T  (upper triangular): C0^T S C0 = L^{-1} L L^T L^{-T} = I
+  for (int t = threadIdx.x; t < n * n; t += NT) {
+    const int a = t / n, b = t - a * n;
+    C[(size_t)a * ld + b] = (b >= a) ? X[(size_t)b * ld + a] : 0.0;
+  }
+  __syncthreads();
+  return ok;
+}
+
 // One SCF map evaluation v -> q -> vnew (scf/base.py:651-675, 818-907, 765-792).
 // Returns the electronic free energy of this solve.
 template <bool SM>
-__device__ double fcn(Ctx& c, const double* __restrict__ v, const xtb_scf_opts& o, double nel_a, double nel_b) {
+__device__ double fcn(Ctx& c, const double* __restrict__ v, const xtb_scf_opts& o, double nel_a, double nel_b, double jtol) {
   const int n = c.n, ne = c.ne, ld = c.ld;
   // F = H0 - 1/2 S (v_i + v_j)   -> A buffer (symmetric, zero padded)
   for (int t = threadIdx.x; t < ne * ld; t += NT) {
@@ -427,7 +482,7 @@ __device__ double fcn(Ctx& c, const double* __restrict__ v, const xtb_scf_opts& 
     }
   }
   __syncthreads();
-  const int sw = jacobi<SM>(c, c.A, c.C, ne, o.jacobi_tol, o.jacobi_max_sweeps);
+  const int sw = jacobi<SM>(c, c.A, c.C, ne, jtol, o.jacobi_max_sweeps);
   if (sw < 0) c.status |= XTB_STATUS_JACOBI_NOT_CONVERGED;
   c.sweeps += sw < 0 ? -sw : sw;
   for (int k = threadIdx.x; k < n; k += NT) c.eps[k] = c.A[(size_t)k * ld + k];
@@ -661,30 +716,9 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
     const int sh = c.ao_sh[mu];
     c.n0[mu] = b.sh_par[(size_t)(c.s0 + sh) * XTB_SHPAR + XTB_SH_REFOCC] / (double)(2 * b.sh_l[c.s0 + sh] + 1);
   }
-  // S-orthonormal start basis: S = U s U^T  ->  C0 = U s^{-1/2}
-  for (int t = threadIdx.x; t < ne * ld; t += NT) {
-    const int i = t / ld, j = t - i * ld;
-    c.A[t] = (i < n && j < n) ? c.S[(size_t)i * n + j] : ((i == j && i < ne) ? 1.0 : 0.0);
-    c.C[t] = (i == j && i < n) ? 1.0 : 0.0;
-  }
-  __syncthreads();
-  {
-    const int sw = jacobi<SM>(c, c.A, c.C, ne, 2e-14, o.jacobi_max_sweeps + 20);
-    if (sw < 0) c.status |= XTB_STATUS_JACOBI_NOT_CONVERGED;
-    c.sweeps += sw < 0 ? -sw : sw;
-    bool bad = false;
-    for (int k = threadIdx.x; k < n; k += NT) {
-      const double s = c.A[(size_t)k * ld + k];
-      if (!(s > 0.0)) bad = true;
-      c.eps[k] = (s > 0.0) ? 1.0 / sqrt(s) : 0.0;
-    }
-    if (__syncthreads_or(bad)) c.status |= XTB_STATUS_S_NOT_POSDEF;
-    for (int t = threadIdx.x; t < n * n; t += NT) {
-      const int i = t / n, k = t - i * n;
-      c.C[(size_t)i * ld + k] *= c.eps[k];
-    }
-    __syncthreads();
-  }
+  // S-orthonormal start basis C0 = L^{-T} from the Cholesky factor S = L L^T (done once; the reference
+  // re-factorises S in every iteration inside storch.eighb, scf/unrolling/base.py:141-175)
+  if (!cholesky_start_basis<SM>(c)) c.status |= XTB_STATUS_S_NOT_POSDEF;
 
   // guess: atomic charges spread equally over shells, then over the AOs of a shell (scf/guess.py:122-182)
   for (int mu = threadIdx.x; mu < n; mu += NT) {
@@ -700,19 +734,21 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
   mx.head = 0;
   int iters = 1;
   bool converged = true;
-  double g = fcn<SM>(c, c.v, o, nel_a, nel_b);  // evaluated outside the loop (unrolling/default.py:81)
+  // intermediate map evaluations only steer the SCF trajectory: a looser eigensolver tolerance saves the last
+  // (verification) sweep; the final solve that defines charges / energies / P / W uses the tight one
+  double g = fcn<SM>(c, c.v, o, nel_a, nel_b, o.maxiter > 0 ? o.jacobi_tol_iter : o.jacobi_tol);  // outside the loop (unrolling/default.py:81)
   if (o.maxiter > 0) {
     converged = false;
     mix(c, mx, o, sm_theta);  // mix_guess (unrolling/default.py:93-94); convergence is not tested here
     for (int it = 0; it < o.maxiter; ++it) {
-      g = fcn<SM>(c, c.v, o, nel_a, nel_b);
+      g = fcn<SM>(c, c.v, o, nel_a, nel_b, o.jacobi_tol_iter);
       ++iters;
       if (mix(c, mx, o, sm_theta)) { converged = true; break; }
     }
     // converged_to_charges: one more solve with the UN-MIXED potential (scf/base.py:497-501, default.py:111-114)
     for (int k = threadIdx.x; k < n; k += NT) c.v[k] = c.vnew[k];
     __syncthreads();
-    g = fcn<SM>(c, c.v, o, nel_a, nel_b);
+    g = fcn<SM>(c, c.v, o, nel_a, nel_b, o.jacobi_tol);
   }
   if (!converged) c.status |= XTB_STATUS_SCF_NOT_CONVERGED;
 

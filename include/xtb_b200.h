@@ -94,7 +94,8 @@ typedef struct xtb_scf_opts {
   double x_atol_max;        /* 1e-5 (Linf) */
   double kt;                /* fermi_etemp * KELVIN2AU */
   double fermi_thresh;      /* sqrt(eps) */
-  double jacobi_tol;        /* 1e-13 */
+  double jacobi_tol;        /* 1e-13: max |off-diagonal| of the final solve */
+  double jacobi_tol_iter;   /* 2e-9: the same for intermediate SCF map evaluations */
 } xtb_scf_opts;
 
 /* status bits written per molecule by xtb_scf_run */

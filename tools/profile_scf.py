@@ -24,3 +24,22 @@ for s in range(reps):
 torch.cuda.synchronize()
 st = calc.cache["status"]
 print("ok", float(e.sum()), "mean sweeps", float((st >> 8).float().mean()), "mean iters", float(calc.get_iterations().float().mean()))
+
+# ---- step breakdown (wall clock, synchronised) ----
+import time
+pp = torch.from_numpy(bench.conformers(base, nb, 99)).to(dev)
+for rep in range(3):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    p = pp.detach().requires_grad_(True)
+    e = calc.get_energy(p, chrg)
+    torch.cuda.synchronize(); t1 = time.perf_counter()
+    (g,) = torch.autograd.grad(e.sum(), p)
+    torch.cuda.synchronize(); t2 = time.perf_counter()
+    print(f"forward {1e3*(t1-t0):.2f} ms  backward {1e3*(t2-t1):.2f} ms")
+from torch.profiler import profile, ProfilerActivity
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+    p = pp.detach().requires_grad_(True)
+    e = calc.get_energy(p, chrg)
+    (g,) = torch.autograd.grad(e.sum(), p)
+    torch.cuda.synchronize()
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=14, max_name_column_width=60))
