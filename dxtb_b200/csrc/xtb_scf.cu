@@ -92,7 +92,7 @@ XTB_DEV void group_bar(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1
 
 constexpr int JB = 8;        // Jacobi block size
 constexpr int JB2 = 2 * JB;  // indices of a block pair
-constexpr int MLD = 17;      // leading dimension of the 16x16 sub-problem copy
+constexpr int MLD = 24;      // leading dimension of the 16x16 sub-problem copy (== 8 mod 16: conflict-free 2x2-block updates)
 constexpr int QLD = 20;      // leading dimension of the accumulated 16x16 rotation (== 4 mod 16: conflict-free DMMA fragments)
 
 // Global index of local index l (0..15) of block pair (I, J).
@@ -148,8 +148,8 @@ __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, in
         if (I > J) { const int t = I; I = J; J = t; }
         double* M = Ms + w * (JB2 * MLD);
         double* Q = Qs + w * (JB2 * QLD);
-        double* rcs = Rs + w * 32;                          // [8][c, s]
-        int* rpq = reinterpret_cast<int*>(rcs + 16);        // [8][p, q]
+        double2* rcs = reinterpret_cast<double2*>(Rs + w * 32);   // [8] (c, s)
+        int2* rpq = reinterpret_cast<int2*>(Rs + w * 32 + 16);    // [8] (p, q)
         if (gt == 0) { bij[2 * w] = I; bij[2 * w + 1] = J; }
         for (int e = gt; e < JB2 * JB2; e += 128) {
           const int rr = e >> 4, cc = e & 15;
@@ -183,21 +183,26 @@ __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, in
               cs_ = rsqrt(1.0 + tt * tt);
               sn = tt * cs_;
             }
-            rcs[2 * l] = cs_; rcs[2 * l + 1] = sn;
-            rpq[2 * l] = p; rpq[2 * l + 1] = q;
+            rcs[l] = make_double2(cs_, sn);
+            rpq[l] = make_int2(p, q);
           }
           group_bar(grp);
           {
             // M <- J^T M J on the 8x8 grid of 2x2 blocks (threads 0..63) and Q <- Q J (16 rows x 8 pairs, all 128
             // threads); every load is issued before the first dependent store
-            const int kp = (gt >> 3) & 7, kq = gt & 7, qi = gt >> 3;
-            const int p1 = rpq[2 * kp], q1 = rpq[2 * kp + 1], p2 = rpq[2 * kq], q2 = rpq[2 * kq + 1];
-            const double c1 = rcs[2 * kp], s1 = rcs[2 * kp + 1], c2 = rcs[2 * kq], s2 = rcs[2 * kq + 1];
-            const double vp = Q[qi * QLD + p2], vq = Q[qi * QLD + q2];
+            // M blocks: thread -> (kp, kq) = (gt >> 3, gt & 7); Q items: every half-warp covers 4 rows x 4 pairs
+            // (conflict-free for QLD == 4 mod 16): pair qk, row qi
+            const int kp = (gt >> 3) & 7, kq = gt & 7;
+            const int qk = (gt & 3) + 4 * ((gt >> 4) & 1), qi = ((gt >> 2) & 3) + 4 * (gt >> 5);
+            const int2 pq1 = rpq[kp], pq2 = rpq[kq], pqq = rpq[qk];
+            const double2 cs1 = rcs[kp], cs2 = rcs[kq], csq = rcs[qk];
+            const int p1 = pq1.x, q1 = pq1.y, p2 = pq2.x, q2 = pq2.y;
+            const double c1 = cs1.x, s1 = cs1.y, c2 = cs2.x, s2 = cs2.y;
+            const double vp = Q[qi * QLD + pqq.x], vq = Q[qi * QLD + pqq.y];
             double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
             if (gt < 64) { a00 = M[p1 * MLD + p2]; a01 = M[p1 * MLD + q2]; a10 = M[q1 * MLD + p2]; a11 = M[q1 * MLD + q2]; }
-            Q[qi * QLD + p2] = c2 * vp - s2 * vq;
-            Q[qi * QLD + q2] = s2 * vp + c2 * vq;
+            Q[qi * QLD + pqq.x] = csq.x * vp - csq.y * vq;
+            Q[qi * QLD + pqq.y] = csq.y * vp + csq.x * vq;
             if (gt < 64) {
               const double x00 = c1 * a00 - s1 * a10, x01 = c1 * a01 - s1 * a11;
               const double x10 = s1 * a00 + c1 * a10, x11 = s1 * a01 + c1 * a11;
@@ -676,6 +681,7 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
   c.red = p; p += 32;
   double* sm_theta = p; p += 36;
   c.occl = (int*)p; p += (nmx + 2) / 2 + 1;
+  p += ((p - sm) & 1);  // 16-byte alignment for the double2 / int2 scratch and the matrices
   if (SM) {
     const int nbpx = (b.nao_max + 15) / 16;
     c.jq = p; p += nbpx * JB2 * QLD;
@@ -692,9 +698,10 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
   } else {
     double* wm = work + (size_t)(o.generations + 1) * 2 * b.nao_tot + 3 * ((size_t)b.mat_off[m] + 34 * (size_t)c.o0 + 285 * (size_t)m);  // sum of (n+15)(n+19) bounds ne*ld
     c.C = wm; c.A = wm + msz; c.X = wm + 2 * msz;
-    // block-Jacobi scratch of this molecule: nbp * (16 * (QLD + MLD) + 32) <= 39 n + 624 doubles
+    // block-Jacobi scratch of this molecule: nbp * (16 * (QLD + MLD) + 32) <= 46 n + 736 doubles (+2 for 16-byte alignment)
     double* ws = work + (size_t)(o.generations + 1) * 2 * b.nao_tot + 3 * ((size_t)b.mat_total + 34 * (size_t)b.nao_tot + 285 * (size_t)b.nb) +
-                 39 * (size_t)c.o0 + 624 * (size_t)m;
+                 46 * (size_t)c.o0 + 738 * (size_t)m;
+    ws = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(ws) + 15) & ~(uintptr_t)15);
     c.jq = ws; c.jm = ws + (size_t)(ne / 16) * JB2 * QLD; c.jr = c.jm + (size_t)(ne / 16) * JB2 * MLD;
   }
   c.xh = work + (size_t)(o.generations + 1) * 2 * c.o0;
@@ -827,7 +834,7 @@ extern "C" int64_t xtb_scf_workspace_bytes(const xtb_batch* b, const xtb_scf_opt
   if (!o->use_smem) {
     // 3 matrices of (n+1)(n+2) per molecule: 3 (sum n^2 + 3 sum n + 2 nb)
     d += 3 * (b->mat_total + 34 * (int64_t)b->nao_tot + 285 * (int64_t)b->nb);
-    d += 39 * (int64_t)b->nao_tot + 624 * (int64_t)b->nb;
+    d += 46 * (int64_t)b->nao_tot + 738 * (int64_t)b->nb;
   }
   return d * 8 + 256;
 }
