@@ -47,6 +47,8 @@ class XtbScfOpts(C.Structure):
         ("damp", C.c_double), ("damp_init", C.c_double), ("diag_offset", C.c_double),
         ("x_atol", C.c_double), ("x_atol_max", C.c_double), ("kt", C.c_double), ("fermi_thresh", C.c_double),
         ("jacobi_tol", C.c_double), ("jacobi_tol_iter", C.c_double),
+        ("mol_list", _vp), ("list_len", C.c_int32), ("list_nao_max", C.c_int32), ("list_nsh_max", C.c_int32),
+        ("list_nat_max", C.c_int32),
     ]
 
 
@@ -60,6 +62,7 @@ EXPORTS = {
     "xtb_overlap_h0_fwd": (C.c_int, [_vp] * 6),
     "xtb_scf_workspace_bytes": (C.c_int64, [_vp, _vp]),
     "xtb_scf_smem_bytes": (C.c_int64, [_vp]),
+    "xtb_scf_smem_bytes_for": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     "xtb_scf_run": (C.c_int, [_vp] * 21),
     "xtb_grad_bwd": (C.c_int, [_vp] * 13),
 }

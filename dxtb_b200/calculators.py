@@ -67,7 +67,7 @@ def _stream_ptr(device: torch.device) -> int:
 class _Workspace:
     """Per-call device buffers (all torch-owned; the C side never allocates)."""
 
-    def __init__(self, d: BatchDescriptor, want_density: bool, scf_opts: _abi.XtbScfOpts):
+    def __init__(self, d: BatchDescriptor, want_density: bool, scf_opts: _abi.XtbScfOpts, need_global: bool = True):
         dev, f64 = d.device, torch.float64
         z = lambda n, dt=f64: torch.zeros(int(n), dtype=dt, device=dev)  # noqa: E731
         self.cn, self.e_rep, self.e_xb = z(d.nat_tot), z(d.nat_tot), z(d.nat_tot)
@@ -78,6 +78,7 @@ class _Workspace:
         self.q_sh, self.q_at, self.e_atom = z(d.nsh_tot), z(d.nat_tot), z(d.nat_tot)
         self.fenergy = z(d.nb)
         self.iterations, self.status = z(d.nb, torch.int32), z(d.nb, torch.int32)
+        scf_opts.use_smem = 0 if need_global else 1
         nbytes = _abi.lib().xtb_scf_workspace_bytes(d.ptr, _abi.C.addressof(scf_opts))
         self.work = torch.empty(int(nbytes) // 8 + 1, dtype=f64, device=dev)
         if want_density:
@@ -98,7 +99,8 @@ class _SinglePoint(torch.autograd.Function):
         need_grad = bool(ctx.needs_input_grad[0])
         pos = d.gather_atoms(positions.detach())
         o = calc._scf_struct(want_density=need_grad)
-        ws = _Workspace(d, need_grad, o)
+        need_global = calc._use_smem_override == 0 or any(not bk["use_smem"] for bk in calc._buckets)
+        ws = _Workspace(d, need_grad, o, need_global)
         excl = calc._exclude
 
         _abi.check(lib.xtb_geometry_fwd(d.ptr, pos.data_ptr(), ws.cn.data_ptr(), ws.e_rep.data_ptr(), ws.e_xb.data_ptr(), st), "xtb_geometry_fwd")
@@ -114,16 +116,20 @@ class _SinglePoint(torch.autograd.Function):
         if calc.scf_events is not None:  # bench.py: device time of the SCF kernel alone
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record(torch.cuda.current_stream(d.device))
-        _abi.check(
-            lib.xtb_scf_run(
-                d.ptr, _abi.C.addressof(o), ws.S.data_ptr(), ws.H0.data_ptr(), ws.gamma.data_ptr(), nel_ab.data_ptr(),
-                ws.q0_at.data_ptr(), ws.work.data_ptr(), ws.q_orb.data_ptr(), ws.q_sh.data_ptr(), ws.q_at.data_ptr(),
-                ws.v_orb.data_ptr(), ws.e_atom.data_ptr(), ws.fenergy.data_ptr(), ws.emo.data_ptr(), ws.occ.data_ptr(),
-                ws.iterations.data_ptr(), ws.status.data_ptr(), ws.P.data_ptr() if need_grad else None,
-                ws.W.data_ptr() if need_grad else None, st,
-            ),
-            "xtb_scf_run",
-        )
+        for bk in calc._buckets:
+            o.use_smem = bk["use_smem"] if calc._use_smem_override is None else calc._use_smem_override
+            o.mol_list, o.list_len = bk["list"].data_ptr(), bk["len"]
+            o.list_nao_max, o.list_nsh_max, o.list_nat_max = bk["nao"], bk["nsh"], bk["nat"]
+            _abi.check(
+                lib.xtb_scf_run(
+                    d.ptr, _abi.C.addressof(o), ws.S.data_ptr(), ws.H0.data_ptr(), ws.gamma.data_ptr(), nel_ab.data_ptr(),
+                    ws.q0_at.data_ptr(), ws.work.data_ptr(), ws.q_orb.data_ptr(), ws.q_sh.data_ptr(), ws.q_at.data_ptr(),
+                    ws.v_orb.data_ptr(), ws.e_atom.data_ptr(), ws.fenergy.data_ptr(), ws.emo.data_ptr(), ws.occ.data_ptr(),
+                    ws.iterations.data_ptr(), ws.status.data_ptr(), ws.P.data_ptr() if need_grad else None,
+                    ws.W.data_ptr() if need_grad else None, st,
+                ),
+                "xtb_scf_run",
+            )
         if ev is not None:
             ev[1].record(torch.cuda.current_stream(d.device))
             calc.scf_events.append(ev)
@@ -226,10 +232,36 @@ class GFN1Calculator:
         self.ihelp = self.desc  # index maps live in the descriptor
         self.cache: dict[str, Any] = {}
         self.scf_events: list | None = None
-        smem = _abi.lib().xtb_scf_smem_bytes(self.desc.ptr)
-        self._use_smem = 1 if smem <= _SMEM_LIMIT else 0
+        self._use_smem_override: int | None = None  # tests: force the global-memory variant
+        self._buckets = self._make_buckets()
+        self._use_smem = 1 if all(bk["use_smem"] for bk in self._buckets) else 0
 
     # ------------------------------------------------------------------------------------------
+    def _make_buckets(self) -> list[dict[str, Any]]:
+        """Size buckets of the SCF launch: molecules whose matrices fit in shared memory run the shared-memory
+        variant of the kernel, the others the global-memory one (largest first, so the long CTAs start first).
+        Replaces the reference's padding + culling of ragged batches (scf/unrolling/default.py:240-321)."""
+        import numpy as np
+
+        d, lib = self.desc, _abi.lib()
+        fits = np.array([lib.xtb_scf_smem_bytes_for(int(n), int(s), int(a)) <= _SMEM_LIMIT
+                         for n, s, a in zip(d.nao, d.nsh, d.nat)]) if d.nb <= 4096 else None
+        if fits is None:  # vectorised bound for very large batches: the layout grows monotonically with nao
+            nao_cap = max([n for n in range(1, 200) if lib.xtb_scf_smem_bytes_for(n, 3 * n, n) <= _SMEM_LIMIT] or [0])
+            fits = d.nao <= nao_cap
+        buckets = []
+        for use_smem, sel in ((0, ~fits), (1, fits)):
+            idx = np.flatnonzero(sel)
+            if idx.size == 0:
+                continue
+            idx = idx[np.argsort(-d.nao[idx], kind="stable")]
+            buckets.append({
+                "use_smem": use_smem,
+                "list": torch.from_numpy(idx.astype(np.int32)).to(self.device),
+                "len": int(idx.size), "nao": int(d.nao[idx].max()), "nsh": int(d.nsh[idx].max()), "nat": int(d.nat[idx].max()),
+            })
+        return buckets
+
     def _scf_struct(self, want_density: bool) -> _abi.XtbScfOpts:
         o, s = self.opts, _abi.XtbScfOpts()
         s.maxiter = int(o["maxiter"])
@@ -238,7 +270,7 @@ class GFN1Calculator:
         s.soft_start = 1 if o["damp_soft_start"] else 0
         s.fermi_maxiter = int(o["fermi_maxiter"])
         s.want_density = 1 if want_density else 0
-        s.use_smem = self._use_smem
+        s.use_smem = 0  # set per bucket
         s.jacobi_max_sweeps = 30
         s.damp, s.damp_init = float(o["damp"]), float(o["damp_init"])
         s.diag_offset = float(o["damp_diagonal_offset"])

@@ -657,7 +657,9 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
       double* __restrict__ e_atom, double* __restrict__ fenergy, double* __restrict__ emo, double* __restrict__ occ,
       int32_t* __restrict__ iterations, int32_t* __restrict__ status, double* __restrict__ Pout, double* __restrict__ Wout) {
   extern __shared__ double sm[];
-  const int m = blockIdx.x;
+  const int m = o.mol_list ? o.mol_list[blockIdx.x] : (int)blockIdx.x;
+  const int lnao = o.mol_list ? o.list_nao_max : b.nao_max, lnsh = o.mol_list ? o.list_nsh_max : b.nsh_max,
+            lnat = o.mol_list ? o.list_nat_max : b.nat_max;
   Ctx c;
   c.o0 = b.ao_off[m]; c.s0 = b.sh_off[m]; c.a0 = b.at_off[m];
   c.n = b.ao_off[m + 1] - c.o0;
@@ -670,7 +672,7 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
   c.sweeps = 0;
   const int n = c.n, ne = c.ne, ld = c.ld;
   // shared-memory carve-up (sizes by batch maxima so the layout is launch-uniform)
-  const int nmx = b.nao_max + 2, nsx = b.nsh_max, nax = b.nat_max;
+  const int nmx = lnao + 2, nsx = lnsh, nax = lnat;
   double* p = sm;
   c.cs = p; p += nmx + (nmx & 1);  // double2 per pair: keep 16-byte alignment
   c.pp = (int*)p; p += nmx + (nmx & 1);  // int2 per pair (over-allocated, keeps the matrices 16-byte aligned)
@@ -683,7 +685,7 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
   c.occl = (int*)p; p += (nmx + 2) / 2 + 1;
   p += ((p - sm) & 1);  // 16-byte alignment for the double2 / int2 scratch and the matrices
   if (SM) {
-    const int nbpx = (b.nao_max + 15) / 16;
+    const int nbpx = (lnao + 15) / 16;
     c.jq = p; p += nbpx * JB2 * QLD;
     c.jm = p; p += nbpx * JB2 * MLD;
     c.jr = p; p += nbpx * 32;
@@ -692,7 +694,7 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
   c.smem = SM;
   const size_t msz = (size_t)ne * ld;
   if (SM) {
-    const size_t nex = (size_t)((b.nao_max + 15) & ~15);
+    const size_t nex = (size_t)((lnao + 15) & ~15);
     const size_t mszx = nex * (nex + 4);
     c.C = p; c.A = p + mszx; c.X = p + 2 * mszx;
   } else {
@@ -813,8 +815,8 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
   }
 }
 
-int64_t vec_smem_bytes(const xtb_batch* b) {
-  const int64_t nmx = b->nao_max + 2, nsx = b->nsh_max, nax = b->nat_max;
+int64_t vec_smem_bytes(int64_t nao_max, int64_t nsx, int64_t nax) {
+  const int64_t nmx = nao_max + 2;
   int64_t d = 2 * (nmx + (nmx & 1)) + 8 * nmx + 2 * nsx + nax + 32 + 36 + (nmx + 2) / 2 + 1;
   d += d & 1;
   return d * 8;
@@ -822,10 +824,14 @@ int64_t vec_smem_bytes(const xtb_batch* b) {
 
 }  // namespace
 
+extern "C" int64_t xtb_scf_smem_bytes_for(int32_t nao_max, int32_t nsh_max, int32_t nat_max) {
+  const int64_t nex = (nao_max + 15) & ~15;
+  return vec_smem_bytes(nao_max, nsh_max, nat_max) + (3 * nex * (nex + 4) + (nex / 16) * (JB2 * (QLD + MLD) + 32)) * 8;
+}
+
 extern "C" int64_t xtb_scf_smem_bytes(const xtb_batch* b) {
   if (!b) return -1;
-  const int64_t nex = (b->nao_max + 15) & ~15;
-  return vec_smem_bytes(b) + (3 * nex * (nex + 4) + (nex / 16) * (JB2 * (QLD + MLD) + 32)) * 8;
+  return xtb_scf_smem_bytes_for(b->nao_max, b->nsh_max, b->nat_max);
 }
 
 extern "C" int64_t xtb_scf_workspace_bytes(const xtb_batch* b, const xtb_scf_opts* o) {
@@ -849,7 +855,11 @@ extern "C" int xtb_scf_run(const xtb_batch* b, const xtb_scf_opts* o, const doub
   if (o->want_density && (!P || !W)) return -1;
   if (o->generations > 5 || o->generations < 1) return -3;
   if (b->nb == 0) return 0;
-  int64_t smem = o->use_smem ? xtb_scf_smem_bytes(b) : vec_smem_bytes(b);
+  const int nblocks = o->mol_list ? o->list_len : b->nb;
+  if (nblocks <= 0) return 0;
+  const int lnao = o->mol_list ? o->list_nao_max : b->nao_max, lnsh = o->mol_list ? o->list_nsh_max : b->nsh_max,
+            lnat = o->mol_list ? o->list_nat_max : b->nat_max;
+  int64_t smem = o->use_smem ? xtb_scf_smem_bytes_for(lnao, lnsh, lnat) : vec_smem_bytes(lnao, lnsh, lnat);
   static int64_t configured[2] = {0, 0};
   auto kern = o->use_smem ? k_scf<true> : k_scf<false>;
   if (smem > configured[o->use_smem ? 1 : 0]) {
@@ -857,7 +867,7 @@ extern "C" int xtb_scf_run(const xtb_batch* b, const xtb_scf_opts* o, const doub
     if (e != cudaSuccess) return (int)e;
     configured[o->use_smem ? 1 : 0] = smem;
   }
-  kern<<<b->nb, NT, (size_t)smem, (cudaStream_t)stream>>>(*b, *o, S, H0, gamma, nel_ab, q0_at, (double*)work, q_orb, q_sh, q_at,
+  kern<<<nblocks, NT, (size_t)smem, (cudaStream_t)stream>>>(*b, *o, S, H0, gamma, nel_ab, q0_at, (double*)work, q_orb, q_sh, q_at,
                                                            v_orb, e_atom, fenergy, emo, occ, iterations, status, P, W);
   return launch_status();
 }

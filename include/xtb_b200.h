@@ -96,6 +96,10 @@ typedef struct xtb_scf_opts {
   double fermi_thresh;      /* sqrt(eps) */
   double jacobi_tol;        /* 1e-13: max |off-diagonal| of the final solve */
   double jacobi_tol_iter;   /* 2e-9: the same for intermediate SCF map evaluations */
+  /* optional size bucket: this launch handles molecules mol_list[0..list_len) only (device pointer; NULL = all).
+   * list_*_max are the maxima over the bucket (they size the shared-memory layout). */
+  const int32_t* mol_list;
+  int32_t list_len, list_nao_max, list_nsh_max, list_nat_max;
 } xtb_scf_opts;
 
 /* status bits written per molecule by xtb_scf_run */
@@ -131,6 +135,7 @@ int xtb_overlap_h0_fwd(const xtb_batch* b, const double* pos, const double* cn, 
 int64_t xtb_scf_workspace_bytes(const xtb_batch* b, const xtb_scf_opts* o);
 /* Dynamic shared memory the SCF kernel needs with use_smem=1 (host compares with the device limit). */
 int64_t xtb_scf_smem_bytes(const xtb_batch* b);
+int64_t xtb_scf_smem_bytes_for(int32_t nao_max, int32_t nsh_max, int32_t nat_max);
 
 /* The whole SCF (scf/iterator.py:51-144, scf/unrolling/default.py:71-136, scf/base.py:651-907,
  * mixer/anderson.py:163-317, wavefunction/filling.py:201-366): one CTA per molecule, no host round-trips.

@@ -156,7 +156,7 @@ def test_global_memory_variant_matches_shared_memory_variant(mols):
     a = GFN1Calculator(numbers, opts=NODISP, device=dev, dtype=torch.float64)
     b = GFN1Calculator(numbers, opts=NODISP, device=dev, dtype=torch.float64)
     assert a._use_smem == 1
-    b._use_smem = 0
+    b._use_smem_override = 0
     ea, eb = a.get_energy(pos, chrg), b.get_energy(pos, chrg)
     assert torch.allclose(ea, eb, rtol=0, atol=1e-11)
     assert torch.equal(a.get_iterations(), b.get_iterations())
@@ -271,3 +271,25 @@ def test_single_molecule_unbatched_shapes(mols):
     assert calc.get_mulliken_charges().shape == (5,)
     r = _oracle(mols, "CH4")
     assert abs(float(e) - r.energy) < E_TOL
+
+
+def test_mixed_sizes_use_two_buckets(mols):
+    """Ragged batch (SURVEY 8a row 14 'culling'): small molecules run the shared-memory variant, large ones the
+    global-memory variant, results independent of the bucketing."""
+    from dxtb_b200 import GFN1Calculator
+
+    dev = _dev()
+    names = ["H2O", "LYS_xao", "caffeine", "capsaicin", "CH4", "nicotine"]
+    numbers, pos, chrg = _pack(mols, names, dev)
+    calc = GFN1Calculator(numbers, opts=NODISP, device=dev, dtype=torch.float64)
+    assert sorted(bk["use_smem"] for bk in calc._buckets) == [0, 1]
+    assert sum(bk["len"] for bk in calc._buckets) == len(names)
+    p = pos.clone().requires_grad_(True)
+    e = calc.get_energy(p, chrg)
+    (g,) = torch.autograd.grad(e.sum(), p)
+    for i, n in enumerate(names):
+        r = _oracle(mols, n, grad=True)
+        k = len(mols[n]["numbers"])
+        assert abs(float(e[i]) - r.energy) < E_TOL
+        assert int(calc.get_iterations()[i]) == r.iterations
+        assert np.abs(g[i, :k].cpu().numpy() - r.gradient).max() < F_TOL
