@@ -11,7 +11,7 @@ from pathlib import Path
 _SO = Path(__file__).resolve().parent / "_C.so"
 
 ATPAR, SHPAR, CGTO, MAXPRIM = 12, 6, 16, 7
-(AT_RAD, AT_RCOV, AT_EN, AT_AREP, AT_ZEFF, AT_GAM3, AT_XBOND, AT_EEQ_CHI, AT_EEQ_ETA, AT_EEQ_KCN, AT_EEQ_RAD) = range(11)
+(AT_RAD, AT_RCOV, AT_EN, AT_AREP, AT_ZEFF, AT_GAM3, AT_XBOND, AT_EEQ_CHI, AT_EEQ_ETA, AT_EEQ_KCN, AT_EEQ_RAD, AT_R4R2) = range(12)
 (SH_LEVEL, SH_KCN, SH_SHPOLY, SH_ETA, SH_REFOCC) = range(5)
 
 STATUS_SCF_NOT_CONVERGED = 1
@@ -37,6 +37,9 @@ class XtbBatch(C.Structure):
         ("gexp", C.c_double),
         ("int_cutoff", C.c_double), ("rep_cutoff", C.c_double), ("xb_cutoff", C.c_double), ("cn_cutoff", C.c_double),
         ("kcn_d3", C.c_double),
+        ("d3_refcn", _vp), ("d3_c6", _vp),
+        ("d3_s6", C.c_double), ("d3_s8", C.c_double), ("d3_a1", C.c_double), ("d3_a2", C.c_double),
+        ("d3_cutoff", C.c_double), ("d3_wf", C.c_double),
     ]
 
 
@@ -64,7 +67,8 @@ EXPORTS = {
     "xtb_scf_smem_bytes": (C.c_int64, [_vp]),
     "xtb_scf_smem_bytes_for": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     "xtb_scf_run": (C.c_int, [_vp] * 21),
-    "xtb_grad_bwd": (C.c_int, [_vp] * 13),
+    "xtb_grad_bwd": (C.c_int, [_vp] * 14),
+    "xtb_d3_fwd": (C.c_int, [_vp] * 6),
 }
 
 _lib = None

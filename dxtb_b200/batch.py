@@ -21,6 +21,8 @@ REP_CUTOFF = 25.0  # constants/xtb.py:33
 XB_CUTOFF = 20.0  # constants/xtb.py:37
 CN_CUTOFF = 25.0  # tad-mctc ncoord default
 KCN_D3 = 16.0
+D3_DISP_CUTOFF = 50.0  # tad-dftd3 defaults.D3_DISP_CUTOFF
+D3_WF = 4.0  # tad-dftd3 Gaussian weighting factor
 
 
 def _excl_cumsum(x: np.ndarray, dtype=np.int64) -> np.ndarray:
@@ -33,7 +35,7 @@ class BatchDescriptor:
     """CSR description of a batch of molecules + all per-atom/per-shell GFN1 parameters on ``device``."""
 
     def __init__(self, numbers: torch.Tensor, device: torch.device, par: GFN1Param | None = None,
-                 exclude: tuple[str, ...] = (), int_cutoff: float = INT_CUTOFF):
+                 exclude: tuple[str, ...] = (), int_cutoff: float = INT_CUTOFF, d3_table: dict | None = None):
         par = par or gfn1_param()
         self.par = par
         self.device = device
@@ -116,6 +118,8 @@ class BatchDescriptor:
         at_par[:, _abi.AT_EEQ_ETA] = par.eeq_eta[z]
         at_par[:, _abi.AT_EEQ_KCN] = par.eeq_kcn[z]
         at_par[:, _abi.AT_EEQ_RAD] = par.eeq_rad[z]
+        if d3_table is not None:
+            at_par[:, _abi.AT_R4R2] = np.asarray(d3_table["r4r2"], dtype=np.float64)[z]
         sh_par = np.zeros((nsh_tot, _abi.SHPAR))
         sh_par[:, _abi.SH_LEVEL] = par.level[sh_z, sh_k]
         sh_par[:, _abi.SH_KCN] = par.kcn[sh_z, sh_k]
@@ -139,6 +143,13 @@ class BatchDescriptor:
             sh_type=dev(sh_type, i32), sh_by_l=dev(sh_by_l, i32), nsh_l=dev(nsh_l, i32), sh_par=dev(sh_par, f64),
             ao_sh=dev(ao_sh, i32), cgto=dev(cg, f64), kpair=dev(kpair, f64),
         )
+        if d3_table is not None:  # per-species slices of the D3 reference data
+            refcn = np.asarray(d3_table["cn"], dtype=np.float64)[species]
+            c6 = np.asarray(d3_table["c6"], dtype=np.float64)[np.ix_(species, species)]
+            if refcn.shape[1] != 7 or c6.shape[2:] != (7, 7):
+                raise ValueError("D3 reference table must have 7 references per element")
+            self._t["d3_refcn"] = dev(refcn, f64)
+            self._t["d3_c6"] = dev(c6, f64)
         # scatter/gather maps between the padded (nb, nat_pad) layout and the ragged one
         self.atom_index = torch.from_numpy(np.flatnonzero(mask.reshape(-1))).to(device)  # ragged -> flat padded
         self.at_mol = dev(at_mol, i64)
@@ -157,6 +168,9 @@ class BatchDescriptor:
         s.hscale = (C.c_double * 36)(*par.hscale_table().reshape(-1).tolist())
         s.enscale, s.rep_kexp, s.xb_damp, s.xb_rscale, s.gexp = par.enscale, par.rep_kexp, par.xb_damp, par.xb_rscale, par.gexp
         s.int_cutoff, s.rep_cutoff, s.xb_cutoff, s.cn_cutoff, s.kcn_d3 = int_cutoff, REP_CUTOFF, XB_CUTOFF, CN_CUTOFF, KCN_D3
+        s.d3_s6, s.d3_s8, s.d3_a1, s.d3_a2 = par.d3["s6"], par.d3["s8"], par.d3["a1"], par.d3["a2"]
+        s.d3_cutoff, s.d3_wf = D3_DISP_CUTOFF, D3_WF
+        self.has_d3 = d3_table is not None
         self.struct = s
 
     @property

@@ -71,6 +71,8 @@ class _Workspace:
         dev, f64 = d.device, torch.float64
         z = lambda n, dt=f64: torch.zeros(int(n), dtype=dt, device=dev)  # noqa: E731
         self.cn, self.e_rep, self.e_xb = z(d.nat_tot), z(d.nat_tot), z(d.nat_tot)
+        self.e_disp = z(d.nat_tot) if d.has_d3 else None
+        self.d3w = torch.empty((d.nat_tot, 14), dtype=f64, device=dev) if d.has_d3 else None
         self.q0_at = z(d.nat_tot)
         self.gamma = z(d.struct.gam_total)
         self.S, self.H0 = torch.empty(d.struct.mat_total, dtype=f64, device=dev), torch.empty(d.struct.mat_total, dtype=f64, device=dev)
@@ -104,6 +106,8 @@ class _SinglePoint(torch.autograd.Function):
         excl = calc._exclude
 
         _abi.check(lib.xtb_geometry_fwd(d.ptr, pos.data_ptr(), ws.cn.data_ptr(), ws.e_rep.data_ptr(), ws.e_xb.data_ptr(), st), "xtb_geometry_fwd")
+        if d.has_d3:
+            _abi.check(lib.xtb_d3_fwd(d.ptr, pos.data_ptr(), ws.cn.data_ptr(), ws.d3w.data_ptr(), ws.e_disp.data_ptr(), st), "xtb_d3_fwd")
         if calc.opts["guess"] == "eeq":
             eeq_work = torch.empty(int(d.struct.eeq_total) + 2 * (d.nat_tot + d.nb), dtype=torch.float64, device=d.device)
             _abi.check(lib.xtb_eeq_guess(d.ptr, pos.data_ptr(), chrg.data_ptr(), eeq_work.data_ptr(), ws.q0_at.data_ptr(), st), "xtb_eeq_guess")
@@ -138,12 +142,15 @@ class _SinglePoint(torch.autograd.Function):
             e_at += ws.e_rep
         if "hal" not in excl:
             e_at += ws.e_xb
+        if d.has_d3:
+            e_at += ws.e_disp
         e_pad = d.scatter_atoms(e_at)
         energy = e_pad.sum(-1)
         calc._store(ws, e_pad, nel_ab)
         if need_grad:
             ctx.calc = calc
             ctx.excl_rep = "rep" in excl
+            ctx.d3w = ws.d3w
             ctx.save_for_backward(pos, ws.cn, ws.S, ws.P, ws.W, ws.v_orb, ws.q_sh, ws.gamma)
         return energy
 
@@ -161,7 +168,8 @@ class _SinglePoint(torch.autograd.Function):
             raise NotImplementedError("analytic gradient with exclude=['rep'] is not implemented")
         _abi.check(
             _abi.lib().xtb_grad_bwd(d.ptr, pos.data_ptr(), cn.data_ptr(), S.data_ptr(), P.data_ptr(), W.data_ptr(), v_orb.data_ptr(),
-                                    q_sh.data_ptr(), gamma.data_ptr(), ge.data_ptr(), dedcn.data_ptr(), grad.data_ptr(),
+                                    q_sh.data_ptr(), gamma.data_ptr(), ge.data_ptr(),
+                                    ctx.d3w.data_ptr() if ctx.d3w is not None else None, dedcn.data_ptr(), grad.data_ptr(),
                                     _stream_ptr(d.device)),
             "xtb_grad_bwd",
         )
@@ -219,16 +227,25 @@ class GFN1Calculator:
         self._exclude = set(o["exclude"] or [])
         if "all" in self._exclude or "scf" in self._exclude:
             raise NotImplementedError("exclude=['scf'/'all'] is outside the hot path")
-        if "disp" not in self._exclude and not os.environ.get("DXTB_B200_D3_REFERENCE"):
-            raise MissingD3ReferenceError(
-                "D3(BJ) dispersion needs the reference C6 table that ships with tad-dftd3 (third-party data, not "
-                "available offline). Pass opts={'exclude': ['disp']} (a reference option) for now."
-            )
+        d3_table = None
         if "disp" not in self._exclude:
-            raise MissingD3ReferenceError("loading an external D3 reference table is not implemented yet")
+            d3_table = kwargs.pop("d3_reference", None) or os.environ.get("DXTB_B200_D3_REFERENCE")
+            if d3_table is None:
+                raise MissingD3ReferenceError(
+                    "D3(BJ) dispersion needs the reference data that ships with tad-dftd3 (reference CNs, C6 table, "
+                    "r4r2: third-party data, not available offline). Pass d3_reference=<dict or .npz path with keys "
+                    "cn (Z+1,7), c6 (Z+1,Z+1,7,7), r4r2 (Z+1)>, set DXTB_B200_D3_REFERENCE, or use "
+                    "opts={'exclude': ['disp']} (a reference option)."
+                )
+            if not isinstance(d3_table, dict):
+                import numpy as np
+
+                with np.load(d3_table) as f:
+                    d3_table = {k: f[k] for k in ("cn", "c6", "r4r2")}
 
         self.par = par if isinstance(par, GFN1Param) else gfn1_param()
-        self.desc = BatchDescriptor(self.numbers, device, self.par, exclude=tuple(self._exclude), int_cutoff=float(o["int_cutoff"]))
+        self.desc = BatchDescriptor(self.numbers, device, self.par, exclude=tuple(self._exclude), int_cutoff=float(o["int_cutoff"]),
+                                    d3_table=d3_table)
         self.ihelp = self.desc  # index maps live in the descriptor
         self.cache: dict[str, Any] = {}
         self.scf_events: list | None = None

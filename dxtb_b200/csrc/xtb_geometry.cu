@@ -254,6 +254,87 @@ __global__ void k_grad_atoms(const xtb_batch b, const double* __restrict__ pos, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// D3(BJ) dispersion (tad-dftd3 0.6.0 dftd3(): weight_references + atomic_c6 + dispersion/rational_damping)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_d3_weights(const xtb_batch b, const double* __restrict__ cn, double* __restrict__ d3w) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= b.nat_tot) return;
+  const double* rc = b.d3_refcn + 7 * b.at_species[a];
+  double w[7], dw[7], norm = 0.0, dnorm = 0.0;
+#pragma unroll
+  for (int r = 0; r < 7; ++r) {
+    const bool ok = rc[r] >= 0.0;
+    const double d = ok ? rc[r] - cn[a] : 0.0;
+    w[r] = ok ? exp(-b.d3_wf * d * d) : 0.0;
+    dw[r] = ok ? 2.0 * b.d3_wf * d * w[r] : 0.0;
+    norm += w[r];
+    dnorm += dw[r];
+  }
+  norm += kEps;
+#pragma unroll
+  for (int r = 0; r < 7; ++r) {
+    d3w[14 * (size_t)a + r] = w[r] / norm;
+    d3w[14 * (size_t)a + 7 + r] = dw[r] / norm - w[r] * dnorm / (norm * norm);
+  }
+}
+
+// GRAD = false: atom-resolved energies; GRAD = true: direct gradient and dE/dCN (added to grad / dedcn)
+template <bool GRAD>
+__global__ void k_d3_pairs(const xtb_batch b, const double* __restrict__ pos, const double* __restrict__ d3w,
+                           const double* __restrict__ ge, double* __restrict__ edisp, double* __restrict__ dedcn,
+                           double* __restrict__ grad) {
+  const int m = blockIdx.x;
+  const int a0 = b.at_off[m], na = b.at_off[m + 1] - a0;
+  const double* p = pos + 3 * (size_t)a0;
+  for (int a = threadIdx.x; a < na; a += blockDim.x) {
+    const double* wa = d3w + 14 * (size_t)(a0 + a);
+    const int sa = b.at_species[a0 + a];
+    const double ra = b.at_par[(size_t)(a0 + a) * XTB_ATPAR + XTB_AT_R4R2];
+    double e = 0.0, gx = 0.0, gy = 0.0, gz = 0.0, dcn = 0.0;
+    for (int c = 0; c < na; ++c) {
+      if (c == a) continue;
+      const double dx = p[3 * a] - p[3 * c], dy = p[3 * a + 1] - p[3 * c + 1], dz = p[3 * a + 2] - p[3 * c + 2];
+      const double d = safe_dist(dx, dy, dz);
+      if (d > b.d3_cutoff) continue;
+      const double* wc = d3w + 14 * (size_t)(a0 + c);
+      const double* rc6 = b.d3_c6 + 49 * ((size_t)sa * b.nspecies + b.at_species[a0 + c]);
+      double c6 = 0.0, dc6 = 0.0;
+#pragma unroll
+      for (int r = 0; r < 7; ++r) {
+        double t = 0.0;
+#pragma unroll
+        for (int s = 0; s < 7; ++s) t = fma(wc[s], rc6[7 * r + s], t);
+        c6 = fma(wa[r], t, c6);
+        if (GRAD) dc6 = fma(wa[7 + r], t, dc6);
+      }
+      const double qq = 3.0 * ra * b.at_par[(size_t)(a0 + c) * XTB_ATPAR + XTB_AT_R4R2];
+      const double r0 = b.d3_a1 * sqrt(qq) + b.d3_a2;
+      const double d2 = d * d, d6 = d2 * d2 * d2, d8 = d6 * d2;
+      const double r2 = r0 * r0, r6 = r2 * r2 * r2, r8 = r6 * r2;
+      const double t6 = 1.0 / (d6 + r6), t8 = 1.0 / (d8 + r8);
+      const double f = b.d3_s6 * t6 + b.d3_s8 * qq * t8;
+      if (!GRAD) {
+        e -= 0.5 * c6 * f;
+      } else {
+        const double df = -(b.d3_s6 * 6.0 * (d6 / d) * t6 * t6 + b.d3_s8 * qq * 8.0 * (d8 / d) * t8 * t8);
+        const double fr = -c6 * df / d;
+        gx += fr * dx; gy += fr * dy; gz += fr * dz;
+        dcn -= dc6 * f;
+      }
+    }
+    if (!GRAD) {
+      edisp[a0 + a] = e;
+    } else {
+      const double sc = ge[m];
+      atomicAdd(&grad[3 * (size_t)(a0 + a)], sc * gx);
+      atomicAdd(&grad[3 * (size_t)(a0 + a) + 1], sc * gy);
+      atomicAdd(&grad[3 * (size_t)(a0 + a) + 2], sc * gz);
+      atomicAdd(&dedcn[a0 + a], dcn);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------
 extern "C" int xtb_version(void) { return 100; }
@@ -284,6 +365,23 @@ extern "C" int xtb_gamma_fwd(const xtb_batch* b, const double* pos, double* gamm
   int gx = (b->nsh_max * b->nsh_max + nt - 1) / nt;
   if (gx > 64) gx = 64;
   k_gamma<<<dim3(gx, b->nb), nt, 0, (cudaStream_t)stream>>>(*b, pos, gamma);
+  return launch_status();
+}
+
+extern "C" int xtb_d3_fwd(const xtb_batch* b, const double* pos, const double* cn, double* d3w, double* e_disp, void* stream) {
+  if (!b || !pos || !cn || !d3w || !e_disp) return -1;
+  if (!b->d3_refcn || !b->d3_c6) return -4;
+  if (b->nb == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  k_d3_weights<<<(b->nat_tot + 127) / 128, 128, 0, st>>>(*b, cn, d3w);
+  k_d3_pairs<false><<<b->nb, 128, 0, st>>>(*b, pos, d3w, nullptr, e_disp, nullptr, nullptr);
+  return launch_status();
+}
+
+// used by xtb_grad_bwd (xtb_integrals.cu)
+int xtb_launch_d3_grad(const xtb_batch* b, const double* pos, const double* d3w, const double* ge, double* dedcn, double* grad,
+                       cudaStream_t st) {
+  k_d3_pairs<true><<<b->nb, 128, 0, st>>>(*b, pos, d3w, ge, nullptr, dedcn, grad);
   return launch_status();
 }
 

@@ -364,6 +364,8 @@ int launch_grad_pair(const xtb_batch* b, const double* pos, const double* cn, co
 
 int xtb_launch_grad_atoms(const xtb_batch* b, const double* pos, const double* q_sh, const double* gamma,
                           const double* dedcn, const double* ge, double* grad, cudaStream_t st);
+int xtb_launch_d3_grad(const xtb_batch* b, const double* pos, const double* d3w, const double* ge, double* dedcn, double* grad,
+                       cudaStream_t st);
 
 extern "C" int xtb_overlap_h0_fwd(const xtb_batch* b, const double* pos, const double* cn, double* S, double* H0, void* stream) {
   if (!b || !pos || !cn || !S || !H0) return -1;
@@ -386,7 +388,7 @@ extern "C" int xtb_overlap_h0_fwd(const xtb_batch* b, const double* pos, const d
 
 extern "C" int xtb_grad_bwd(const xtb_batch* b, const double* pos, const double* cn, const double* S, const double* P,
                             const double* W, const double* v_orb, const double* q_sh, const double* gamma, const double* ge,
-                            double* dedcn, double* grad, void* stream) {
+                            const double* d3w, double* dedcn, double* grad, void* stream) {
   (void)S;
   if (!b || !pos || !cn || !P || !W || !v_orb || !q_sh || !gamma || !ge || !dedcn || !grad) return -1;
   if (b->nb == 0) return 0;
@@ -403,5 +405,7 @@ extern "C" int xtb_grad_bwd(const xtb_batch* b, const double* pos, const double*
   int gx = (b->nao_max + 127) / 128;
   k_dedcn_diag<<<dim3(gx, b->nb), 128, 0, st>>>(*b, P, dedcn);
   if ((rc = launch_status())) return rc;
+  // dispersion: direct part into grad, dE/dCN into dedcn (the exp-count CN is shared with H0)
+  if (d3w && (rc = xtb_launch_d3_grad(b, pos, d3w, ge, dedcn, grad, st))) return rc;
   return xtb_launch_grad_atoms(b, pos, q_sh, gamma, dedcn, ge, grad, st);
 }

@@ -32,7 +32,7 @@ extern "C" {
 /* at_par[a][..] : replaces the per-species gathers of xtb/base.py:138-155, repulsion/base.py:229-243,
  * thirdorder.py:232-244, halogen/hal.py:164-165 and the EEQ parameter lookup of tad-multicharge */
 enum { XTB_AT_RAD = 0, XTB_AT_RCOV, XTB_AT_EN, XTB_AT_AREP, XTB_AT_ZEFF, XTB_AT_GAM3, XTB_AT_XBOND,
-       XTB_AT_EEQ_CHI, XTB_AT_EEQ_ETA, XTB_AT_EEQ_KCN, XTB_AT_EEQ_RAD, XTB_AT_PAD };
+       XTB_AT_EEQ_CHI, XTB_AT_EEQ_ETA, XTB_AT_EEQ_KCN, XTB_AT_EEQ_RAD, XTB_AT_R4R2 /* D3: sqrt(Z) r4/r2 */ };
 /* sh_par[s][..] : xtb/base.py:141-155 (levels, kcn in Hartree; shpoly; refocc), secondorder.py:838-839 (eta) */
 enum { XTB_SH_LEVEL = 0, XTB_SH_KCN, XTB_SH_SHPOLY, XTB_SH_ETA, XTB_SH_REFOCC, XTB_SH_PAD };
 
@@ -75,6 +75,10 @@ typedef struct xtb_batch {
   double gexp;               /* charge.effective.gexp (only 2.0 is implemented) */
   double int_cutoff, rep_cutoff, xb_cutoff, cn_cutoff;
   double kcn_d3;             /* 16.0 */
+  /* D3(BJ) dispersion (tad-dftd3; dispersion/d3.py:93-211).  NULL tables = dispersion excluded. */
+  const double* d3_refcn;    /* [nspecies][7] reference CNs, -1 = missing */
+  const double* d3_c6;       /* [nspecies][nspecies][7][7] reference C6 */
+  double d3_s6, d3_s8, d3_a1, d3_a2, d3_cutoff, d3_wf;
 } xtb_batch;
 
 /* SCF options: resolved defaults of constants/defaults.py */
@@ -151,10 +155,15 @@ int xtb_scf_run(const xtb_batch* b, const xtb_scf_opts* o, const double* S, cons
 /* Analytic nuclear gradient of the converged single point (calculators/types/analytical.py:63-222,
  * xtb/gfn1.py:185-408, secondorder.py:873-926, repulsion/base.py:337-406, ncoord/utils.py:30-52):
  * grad[a] = ge[m] * dE_m/dR_a, ge [nb] being the upstream gradient of the molecular energies.
- * dedcn [nat_tot] is scratch. */
+ * dedcn [nat_tot] is scratch; d3w = weights of xtb_d3_fwd, or NULL when dispersion is excluded. */
 int xtb_grad_bwd(const xtb_batch* b, const double* pos, const double* cn, const double* S, const double* P,
                  const double* W, const double* v_orb, const double* q_sh, const double* gamma, const double* ge,
-                 double* dedcn, double* grad, void* stream);
+                 const double* d3w, double* dedcn, double* grad, void* stream);
+
+/* D3(BJ) two-body dispersion energy (tad-dftd3 dftd3: weight_references, atomic_c6, dispersion with
+ * rational_damping; s9 = 0 for GFN1).  cn is the exp-count CN of xtb_geometry_fwd; d3w [nat_tot][14] receives
+ * the Gaussian reference weights and their CN derivatives (input of xtb_grad_bwd); e_disp [nat_tot]. */
+int xtb_d3_fwd(const xtb_batch* b, const double* pos, const double* cn, double* d3w, double* e_disp, void* stream);
 
 #ifdef __cplusplus
 }

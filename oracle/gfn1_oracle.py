@@ -459,6 +459,76 @@ def halogen(m: Mol, pos: np.ndarray):
 
 
 # --------------------------------------------------------------------------------------
+# D3(BJ) dispersion (tad-dftd3 0.6.0: dftd3 -> weight_references / atomic_c6 / dispersion with
+# rational_damping; wrapper components/classicals/dispersion/d3.py:93-211).  The reference data
+# (reference CNs, C6 table, sqrt(Z) r4/r2) are THIRD-PARTY DATA that is not available offline, so the
+# table is an argument: dict(cn=(Z+1,7) with -1 for missing references, c6=(Z+1,Z+1,7,7), r4r2=(Z+1,)).
+# --------------------------------------------------------------------------------------
+D3_WF = 4.0
+D3_DISP_CUTOFF = 50.0
+
+
+def d3_weights(z, cn, table, grad=False):
+    refcn = table["cn"][z]  # (nat, 7)
+    mask = refcn >= 0
+    dcn = np.where(mask, refcn - cn[:, None], 0.0)
+    w = np.where(mask, np.exp(-D3_WF * dcn * dcn), 0.0)
+    norm = w.sum(-1, keepdims=True) + EPS
+    gw = w / norm
+    if not grad:
+        return gw, None
+    dw = np.where(mask, 2.0 * D3_WF * dcn * w, 0.0)  # d w / d cn
+    dgw = dw / norm - w * dw.sum(-1, keepdims=True) / norm**2
+    return gw, dgw
+
+
+def d3_dispersion(numbers, pos, table, cn=None, grad=False):
+    """Atom-resolved D3(BJ) energy (s9 = 0) and, optionally, (dE/dR direct part, dE/dCN)."""
+    par = params()
+    z = np.asarray(numbers)
+    m = make_mol(z)
+    if cn is None:
+        cn, _ = cn_d3(m, pos)
+    s6, s8, a1, a2 = par.d3["s6"], par.d3["s8"], par.d3["a1"], par.d3["a2"]
+    gw, dgw = d3_weights(z, cn, table, grad=grad)
+    rc6 = table["c6"][z[:, None], z[None, :]]  # (nat,nat,7,7)
+    c6 = np.einsum("ia,jb,ijab->ij", gw, gw, rc6)
+    n = len(z)
+    offd = ~np.eye(n, dtype=bool)
+    dist = np.where(offd, _cdist(pos), EPS)
+    qq = 3.0 * table["r4r2"][z][:, None] * table["r4r2"][z][None, :]
+    r0 = a1 * np.sqrt(qq) + a2
+    ok = offd & (dist <= D3_DISP_CUTOFF)
+    t6 = np.where(ok, 1.0 / (dist**6 + r0**6), 0.0)
+    t8 = np.where(ok, 1.0 / (dist**8 + r0**8), 0.0)
+    f = s6 * t6 + s8 * qq * t8
+    e = -0.5 * (c6 * f).sum(-1)
+    if not grad:
+        return e, None, None
+    df = np.where(ok, -(s6 * 6.0 * dist**5 * t6**2 + s8 * qq * 8.0 * dist**7 * t8**2), 0.0)  # d f / d R
+    rij = pos[:, None, :] - pos[None, :, :]
+    g_direct = ((-c6 * df / dist)[:, :, None] * rij).sum(1)
+    dc6 = np.einsum("ia,jb,ijab->ij", dgw, gw, rc6)  # d c6_ij / d cn_i
+    dedcn = -(dc6 * f).sum(-1)
+    return e, g_direct, dedcn
+
+
+def synthetic_d3_table(seed: int = 7, zmax: int = 86):
+    """A made-up table with the SHAPE of tad-dftd3's reference data: for testing the arithmetic only."""
+    rng = np.random.default_rng(seed)
+    cn = -np.ones((zmax + 1, 7))
+    nref = rng.integers(2, 6, size=zmax + 1)
+    for z in range(1, zmax + 1):
+        cn[z, : nref[z]] = np.sort(rng.uniform(0.0, 4.5, size=nref[z]))
+        cn[z, 0] = 0.0
+    a = rng.uniform(2.0, 60.0, size=(zmax + 1, 7))
+    c6 = np.sqrt(a[:, None, :, None] * a[None, :, None, :]) * (1.0 + 0.1 * rng.uniform(size=(zmax + 1, zmax + 1, 7, 7)))
+    c6 = 0.5 * (c6 + c6.transpose(1, 0, 3, 2))
+    r4r2 = rng.uniform(1.5, 9.0, size=zmax + 1)
+    return {"cn": cn, "c6": c6, "r4r2": r4r2}
+
+
+# --------------------------------------------------------------------------------------
 # second/third-order electrostatics
 # --------------------------------------------------------------------------------------
 def gamma_shell(m: Mol, pos: np.ndarray):
@@ -644,7 +714,7 @@ def _potential(m: Mol, q_orb, gam, g3):
 
 
 def singlepoint(numbers, positions, chrg: float = 0.0, opts: dict | None = None, grad: bool = False,
-                d3_energy=None) -> Result:
+                d3_energy=None, d3_table=None) -> Result:
     """One GFN1-xTB single point with dxtb's default path.  ``d3_energy``: optional callable
     (numbers, positions) -> atomwise dispersion energies (the D3 table is third-party data)."""
     par = params()
@@ -672,6 +742,13 @@ def singlepoint(numbers, positions, chrg: float = 0.0, opts: dict | None = None,
         ed = d3_energy(m.numbers, pos)
         e_at += ed
         res.e_disp = ed.sum()
+    d3_dedcn = None
+    if "disp" not in excl and d3_table is not None:
+        ed, gd, d3_dedcn = d3_dispersion(m.numbers, pos, d3_table, grad=grad)
+        e_at += ed
+        res.e_disp = ed.sum()
+        if grad:
+            g_tot += gd
 
     # integrals (energy.py:170-268)
     S, dS = overlap(m, pos, cutoff=o["int_cutoff"], grad=grad)
@@ -760,6 +837,8 @@ def singlepoint(numbers, positions, chrg: float = 0.0, opts: dict | None = None,
         W = (st["C"] * (focc * st["emo"])[None, :]) @ st["C"].T
         res.W = W
         g_tot += _electronic_gradient(m, pos, S, dS, st["P"], W, v_fin, cn, dcfdr, st["q_sh"], gam)
+        if d3_dedcn is not None:  # CN chain rule of the dispersion energy (same exp-count CN as H0)
+            g_tot += (dcfdr * (d3_dedcn[:, None] + d3_dedcn[None, :])[:, :, None]).sum(1)
         res.gradient = g_tot
     return res
 

@@ -293,3 +293,26 @@ def test_mixed_sizes_use_two_buckets(mols):
         assert abs(float(e[i]) - r.energy) < E_TOL
         assert int(calc.get_iterations()[i]) == r.iterations
         assert np.abs(g[i, :k].cpu().numpy() - r.gradient).max() < F_TOL
+
+
+def test_d3_dispersion_kernels_match_oracle_with_synthetic_table(mols):
+    """D3(BJ) arithmetic (weights, C6 interpolation, BJ damping, CN chain rule).  tad-dftd3's reference data is
+    third-party and unavailable offline, so the table is synthetic (same shape): this pins the kernels to the
+    oracle's restatement, not to the real D3 numbers (parity unpinned)."""
+    from dxtb_b200 import GFN1Calculator
+
+    dev = _dev()
+    tab = O.synthetic_d3_table()
+    names = ["H2O", "SiH4", "caffeine", "MB16_43_01"]
+    numbers, pos, chrg = _pack(mols, names, dev)
+    calc = GFN1Calculator(numbers, device=dev, dtype=torch.float64, d3_reference=tab)
+    p = pos.clone().requires_grad_(True)
+    e = calc.get_energy(p, chrg)
+    (g,) = torch.autograd.grad(e.sum(), p)
+    for i, n in enumerate(names):
+        m = mols[n]
+        r = O.singlepoint(m["numbers"], np.array(m["positions"]), m["charge"], grad=True, d3_table=tab)
+        k = len(m["numbers"])
+        assert abs(r.e_disp) > 1e-5
+        assert abs(float(e[i]) - r.energy) < E_TOL
+        assert np.abs(g[i, :k].cpu().numpy() - r.gradient).max() < F_TOL

@@ -117,3 +117,21 @@ def test_default_path_iterations_and_charges(mols):
     r = O.singlepoint(nums, pos, chrg, opts=dict(exclude=("disp",)))
     assert r.converged and r.iterations == 13
     assert abs(r.q_at.sum() - chrg) < 1e-10
+
+
+def test_d3_gradient_is_derivative_of_energy(mols):
+    """D3(BJ) restatement: analytic gradient (direct + CN chain) vs finite differences, synthetic table."""
+    tab = O.synthetic_d3_table()
+    nums, pos, _ = _geom(mols, "CH4")
+    m = O.make_mol(nums)
+    cn, dcf = O.cn_d3(m, pos, grad=True)
+    e, gd, dedcn = O.d3_dispersion(nums, pos, tab, cn=cn, grad=True)
+    g = gd + (dcf * (dedcn[:, None] + dedcn[None, :])[:, :, None]).sum(1)
+    h = 1e-5
+    for a, x in [(0, 0), (1, 2), (4, 1)]:
+        p = pos.copy(); p[a, x] += h
+        ep = O.d3_dispersion(nums, p, tab)[0].sum()
+        p = pos.copy(); p[a, x] -= h
+        em = O.d3_dispersion(nums, p, tab)[0].sum()
+        assert abs((ep - em) / (2 * h) - g[a, x]) < 1e-9
+    assert e.sum() < 0
