@@ -118,7 +118,7 @@ __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, in
   const int grp = warp >> 2, gt = threadIdx.x & 127;
   double* Qs = c.jq;  // [nbp][16][QLD]
   double* Ms = c.jm;  // [nbp][16][MLD]
-  double* Rs = c.jr;  // [nbp][32] rotation parameters of the current inner round
+  double* Rs = c.jr;  // [nbp][48] rotation parameters (double buffered)
   int* bij = c.pp;    // [nbp][2] blocks of the pairs of this round
   XTB_ASSUME_SHARED(bij);
   if (SM) { XTB_ASSUME_SHARED(A); XTB_ASSUME_SHARED(V); XTB_ASSUME_SHARED(Qs); XTB_ASSUME_SHARED(Ms); XTB_ASSUME_SHARED(Rs); }
@@ -148,8 +148,8 @@ __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, in
         if (I > J) { const int t = I; I = J; J = t; }
         double* M = Ms + w * (JB2 * MLD);
         double* Q = Qs + w * (JB2 * QLD);
-        double2* rcs = reinterpret_cast<double2*>(Rs + w * 32);   // [8] (c, s)
-        int2* rpq = reinterpret_cast<int2*>(Rs + w * 32 + 16);    // [8] (p, q)
+        double2* rcs = reinterpret_cast<double2*>(Rs + w * 48);   // [2][8] (c, s), double buffered
+        int2* rpq = reinterpret_cast<int2*>(Rs + w * 48 + 32);    // [2][8] (p, q)
         if (gt == 0) { bij[2 * w] = I; bij[2 * w + 1] = J; }
         for (int e = gt; e < JB2 * JB2; e += 128) {
           const int rr = e >> 4, cc = e & 15;
@@ -158,7 +158,22 @@ __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, in
         }
         group_bar(grp);
         const int nin = (r < 0) ? JB2 - 1 : JB;
+        // Software pipeline: between the two group barriers of inner round t, warp 0 computes the 8 rotations of
+        // round t while warps 1..3 apply the rotations of round t-1 to Q (Q is off the critical path
+        // rot(t) -> M(t) -> rot(t+1)); rotation parameters are double buffered.
+        auto q_update = [&](int buf) {
+          // 128 items (16 rows x 8 pairs) on 96 threads; every half-warp covers 4 rows x 4 pairs (conflict-free)
+          for (int it = gt - 32; it < 128; it += 96) {
+            const int qk = (it & 3) + 4 * ((it >> 4) & 1), qi = ((it >> 2) & 3) + 4 * (it >> 5);
+            const int2 pqq = rpq[8 * buf + qk];
+            const double2 csq = rcs[8 * buf + qk];
+            const double vp = Q[qi * QLD + pqq.x], vq = Q[qi * QLD + pqq.y];
+            Q[qi * QLD + pqq.x] = csq.x * vp - csq.y * vq;
+            Q[qi * QLD + pqq.y] = csq.y * vp + csq.x * vq;
+          }
+        };
         for (int t = 0; t < nin; ++t) {
+          const int buf = t & 1;
           if (gt < 8) {
             // the 8 disjoint index pairs of this inner round
             const int l = gt;
@@ -183,37 +198,30 @@ __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, in
               cs_ = rsqrt(1.0 + tt * tt);
               sn = tt * cs_;
             }
-            rcs[l] = make_double2(cs_, sn);
-            rpq[l] = make_int2(p, q);
+            rcs[8 * buf + l] = make_double2(cs_, sn);
+            rpq[8 * buf + l] = make_int2(p, q);
+          } else if (gt >= 32 && t > 0) {
+            q_update(buf ^ 1);
           }
           group_bar(grp);
-          {
-            // M <- J^T M J on the 8x8 grid of 2x2 blocks (threads 0..63) and Q <- Q J (16 rows x 8 pairs, all 128
-            // threads); every load is issued before the first dependent store
-            // M blocks: thread -> (kp, kq) = (gt >> 3, gt & 7); Q items: every half-warp covers 4 rows x 4 pairs
-            // (conflict-free for QLD == 4 mod 16): pair qk, row qi
-            const int kp = (gt >> 3) & 7, kq = gt & 7;
-            const int qk = (gt & 3) + 4 * ((gt >> 4) & 1), qi = ((gt >> 2) & 3) + 4 * (gt >> 5);
-            const int2 pq1 = rpq[kp], pq2 = rpq[kq], pqq = rpq[qk];
-            const double2 cs1 = rcs[kp], cs2 = rcs[kq], csq = rcs[qk];
+          if (gt < 64) {
+            // M <- J^T M J on the 8x8 grid of 2x2 blocks: thread -> (kp, kq) = (gt >> 3, gt & 7)
+            const int kp = gt >> 3, kq = gt & 7;
+            const int2 pq1 = rpq[8 * buf + kp], pq2 = rpq[8 * buf + kq];
+            const double2 cs1 = rcs[8 * buf + kp], cs2 = rcs[8 * buf + kq];
             const int p1 = pq1.x, q1 = pq1.y, p2 = pq2.x, q2 = pq2.y;
             const double c1 = cs1.x, s1 = cs1.y, c2 = cs2.x, s2 = cs2.y;
-            const double vp = Q[qi * QLD + pqq.x], vq = Q[qi * QLD + pqq.y];
-            double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
-            if (gt < 64) { a00 = M[p1 * MLD + p2]; a01 = M[p1 * MLD + q2]; a10 = M[q1 * MLD + p2]; a11 = M[q1 * MLD + q2]; }
-            Q[qi * QLD + pqq.x] = csq.x * vp - csq.y * vq;
-            Q[qi * QLD + pqq.y] = csq.y * vp + csq.x * vq;
-            if (gt < 64) {
-              const double x00 = c1 * a00 - s1 * a10, x01 = c1 * a01 - s1 * a11;
-              const double x10 = s1 * a00 + c1 * a10, x11 = s1 * a01 + c1 * a11;
-              double y00 = c2 * x00 - s2 * x01, y01 = s2 * x00 + c2 * x01;
-              double y10 = c2 * x10 - s2 * x11, y11 = s2 * x10 + c2 * x11;
-              if (kp == kq) { y01 = 0.0; y10 = 0.0; }
-              M[p1 * MLD + p2] = y00; M[p1 * MLD + q2] = y01; M[q1 * MLD + p2] = y10; M[q1 * MLD + q2] = y11;
-            }
+            const double a00 = M[p1 * MLD + p2], a01 = M[p1 * MLD + q2], a10 = M[q1 * MLD + p2], a11 = M[q1 * MLD + q2];
+            const double x00 = c1 * a00 - s1 * a10, x01 = c1 * a01 - s1 * a11;
+            const double x10 = s1 * a00 + c1 * a10, x11 = s1 * a01 + c1 * a11;
+            double y00 = c2 * x00 - s2 * x01, y01 = s2 * x00 + c2 * x01;
+            double y10 = c2 * x10 - s2 * x11, y11 = s2 * x10 + c2 * x11;
+            if (kp == kq) { y01 = 0.0; y10 = 0.0; }
+            M[p1 * MLD + p2] = y00; M[p1 * MLD + q2] = y01; M[q1 * MLD + p2] = y10; M[q1 * MLD + q2] = y11;
           }
           group_bar(grp);
         }
+        if (gt >= 32) q_update((nin - 1) & 1);  // rotations of the last inner round
       }
       __syncthreads();
       // ---- 2a. column passes: A[:, idx] <- A[:, idx] Q and V[:, idx] <- V[:, idx] Q (m8 n16 k16 per unit) ----
@@ -688,7 +696,7 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
     const int nbpx = (lnao + 15) / 16;
     c.jq = p; p += nbpx * JB2 * QLD;
     c.jm = p; p += nbpx * JB2 * MLD;
-    c.jr = p; p += nbpx * 32;
+    c.jr = p; p += nbpx * 48;
   }
   p += ((p - sm) & 1);
   c.smem = SM;
@@ -700,9 +708,9 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
   } else {
     double* wm = work + (size_t)(o.generations + 1) * 2 * b.nao_tot + 3 * ((size_t)b.mat_off[m] + 34 * (size_t)c.o0 + 285 * (size_t)m);  // sum of (n+15)(n+19) bounds ne*ld
     c.C = wm; c.A = wm + msz; c.X = wm + 2 * msz;
-    // block-Jacobi scratch of this molecule: nbp * (16 * (QLD + MLD) + 32) <= 46 n + 736 doubles (+2 for 16-byte alignment)
+    // block-Jacobi scratch of this molecule: nbp * (16 * (QLD + MLD) + 32) <= 47 n + 752 doubles (+2 for 16-byte alignment)
     double* ws = work + (size_t)(o.generations + 1) * 2 * b.nao_tot + 3 * ((size_t)b.mat_total + 34 * (size_t)b.nao_tot + 285 * (size_t)b.nb) +
-                 46 * (size_t)c.o0 + 738 * (size_t)m;
+                 47 * (size_t)c.o0 + 754 * (size_t)m;
     ws = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(ws) + 15) & ~(uintptr_t)15);
     c.jq = ws; c.jm = ws + (size_t)(ne / 16) * JB2 * QLD; c.jr = c.jm + (size_t)(ne / 16) * JB2 * MLD;
   }
@@ -826,7 +834,7 @@ int64_t vec_smem_bytes(int64_t nao_max, int64_t nsx, int64_t nax) {
 
 extern "C" int64_t xtb_scf_smem_bytes_for(int32_t nao_max, int32_t nsh_max, int32_t nat_max) {
   const int64_t nex = (nao_max + 15) & ~15;
-  return vec_smem_bytes(nao_max, nsh_max, nat_max) + (3 * nex * (nex + 4) + (nex / 16) * (JB2 * (QLD + MLD) + 32)) * 8;
+  return vec_smem_bytes(nao_max, nsh_max, nat_max) + (3 * nex * (nex + 4) + (nex / 16) * (JB2 * (QLD + MLD) + 48)) * 8;
 }
 
 extern "C" int64_t xtb_scf_smem_bytes(const xtb_batch* b) {
@@ -840,7 +848,7 @@ extern "C" int64_t xtb_scf_workspace_bytes(const xtb_batch* b, const xtb_scf_opt
   if (!o->use_smem) {
     // 3 matrices of (n+1)(n+2) per molecule: 3 (sum n^2 + 3 sum n + 2 nb)
     d += 3 * (b->mat_total + 34 * (int64_t)b->nao_tot + 285 * (int64_t)b->nb);
-    d += 46 * (int64_t)b->nao_tot + 738 * (int64_t)b->nb;
+    d += 47 * (int64_t)b->nao_tot + 754 * (int64_t)b->nb;
   }
   return d * 8 + 256;
 }
