@@ -39,52 +39,53 @@ struct Ctx {
 // Address-space hint: lets the compiler emit LDS/STS (32-bit addressing) instead of generic LD/ST.
 #define XTB_ASSUME_SHARED(ptr) __builtin_assume(__isShared(ptr))
 
-// Out[i][j] = sum_{k<K} L[k*ld+i] * R[k*ld+j], i,j < ne.  4x4 register tiles whose rows/columns are
-// INTERLEAVED (row ti + r*nt4, column tj + c*nt4): lanes of a warp read consecutive fp64 words of R (no bank
-// conflicts) and broadcast the words of L.
-template <bool SM>
-__device__ void gemm_tn(int ne, int K, const double* __restrict__ L, const double* __restrict__ R, int ld, double* __restrict__ Out,
-                        int ldo, int nout) {
-  if (SM) { XTB_ASSUME_SHARED(L); XTB_ASSUME_SHARED(R); }
-  const int nt4 = (ne + 3) >> 2;
-  for (int t = threadIdx.x; t < nt4 * nt4; t += NT) {
-    const int ti = t / nt4, tj = t - ti * nt4;
-    double acc[4][4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
-    bool vi[4], vj[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) { vi[r] = ti + r * nt4 < ne; vj[r] = tj + r * nt4 < ne; }
-    for (int k = 0; k < K; ++k) {
-      const double* lr = L + (size_t)k * ld + ti;
-      const double* rr = R + (size_t)k * ld + tj;
-      double a[4], bv[4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) a[r] = vi[r] ? lr[r * nt4] : 0.0;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) bv[c] = vj[c] ? rr[c * nt4] : 0.0;
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc[r][c] = fma(a[r], bv[c], acc[r][c]);
-    }
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int i = ti + r * nt4, j = tj + c * nt4;
-        if (i < nout && j < nout) Out[(size_t)i * ldo + j] = acc[r][c];
-      }
-  }
-  __syncthreads();
-}
-
 // fp64 tensor-core MMA, D(8x8) += A(8x4, row) * B(4x8, col).  Lane l holds A[l/4][l%4], B[l%4][l/4],
 // D[l/4][2*(l%4) + {0,1}].  SASS: DMMA.8x8x4.
 XTB_DEV void dmma884(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// Out[i][j] = sum_{k<K} L[k*ld+i] * R[k*ld+j], i,j < ne (ne % 16 == 0), on the fp64 tensor cores:
+// one warp per 16x16 output tile (2x2 DMMA tiles), K consumed 4 at a time.  With ld == 4 (mod 16) both
+// fragment loads (4 consecutive k rows x 8 consecutive columns per half-warp) are bank-conflict free.
+template <bool SM>
+__device__ void gemm_tn(int ne, int K, const double* __restrict__ L, const double* __restrict__ R, int ld, double* __restrict__ Out,
+                        int ldo, int nout) {
+  if (SM) { XTB_ASSUME_SHARED(L); XTB_ASSUME_SHARED(R); }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, tg = lane & 3;
+  const int nt = ne >> 4;
+  for (int t = warp; t < nt * nt; t += NT / 32) {
+    const int ti = t / nt, tj = t - ti * nt;
+    const int i0 = ti << 4, j0 = tj << 4;
+    double d[2][2][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) d[a][b][0] = d[a][b][1] = 0.0;
+    for (int k0 = 0; k0 < K; k0 += 4) {
+      const bool kv = k0 + tg < K;
+      const double* lr = L + (size_t)(k0 + tg) * ld + i0 + g;
+      const double* rr = R + (size_t)(k0 + tg) * ld + j0 + g;
+      const double a0 = kv ? lr[0] : 0.0, a1 = kv ? lr[8] : 0.0;
+      const double b0 = kv ? rr[0] : 0.0, b1 = kv ? rr[8] : 0.0;
+      dmma884(d[0][0][0], d[0][0][1], a0, b0);
+      dmma884(d[0][1][0], d[0][1][1], a0, b1);
+      dmma884(d[1][0][0], d[1][0][1], a1, b0);
+      dmma884(d[1][1][0], d[1][1][1], a1, b1);
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int i = i0 + 8 * a + g, j = j0 + 8 * b + 2 * tg;
+        if (i < nout) {
+          if (j < nout) Out[(size_t)i * ldo + j] = d[a][b][0];
+          if (j + 1 < nout) Out[(size_t)i * ldo + j + 1] = d[a][b][1];
+        }
+      }
+  }
+  __syncthreads();
 }
 
 // named barrier for a group of 4 warps (ids 1..8; id 0 is __syncthreads)
