@@ -117,6 +117,10 @@ __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, in
   constexpr int NW = NT / 32;
   constexpr int NG = NW / 4;  // thread groups of 4 warps for the sub-problems
   const int grp = warp >> 2, gt = threadIdx.x & 127;
+  // Role rotation: the warp that computes the rotations (and the two that update M) is a different one in each
+  // group, so that the fp64-heavy chains of the concurrently running groups land on different SM sub-partitions
+  // (warp % 4) instead of all on sub-partition 0.
+  const int vt = ((((gt >> 5) - (grp & 3)) & 3) << 5) | lane;
   double* Qs = c.jq;  // [nbp][16][QLD]
   double* Ms = c.jm;  // [nbp][16][MLD]
   double* Rs = c.jr;  // [nbp][48] rotation parameters (double buffered)
@@ -164,7 +168,7 @@ __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, in
         // rot(t) -> M(t) -> rot(t+1)); rotation parameters are double buffered.
         auto q_update = [&](int buf) {
           // 128 items (16 rows x 8 pairs) on 96 threads; every half-warp covers 4 rows x 4 pairs (conflict-free)
-          for (int it = gt - 32; it < 128; it += 96) {
+          for (int it = vt - 32; it < 128; it += 96) {
             const int qk = (it & 3) + 4 * ((it >> 4) & 1), qi = ((it >> 2) & 3) + 4 * (it >> 5);
             const int2 pqq = rpq[8 * buf + qk];
             const double2 csq = rcs[8 * buf + qk];
@@ -175,9 +179,9 @@ __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, in
         };
         for (int t = 0; t < nin; ++t) {
           const int buf = t & 1;
-          if (gt < 8) {
+          if (vt < 8) {
             // the 8 disjoint index pairs of this inner round
-            const int l = gt;
+            const int l = vt;
             int p, q;
             if (r < 0) {
               if (l == 0) { p = t; q = JB2 - 1; }
@@ -188,26 +192,29 @@ __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, in
             }
             const double app = M[p * MLD + p], aqq = M[q * MLD + q], apq = M[p * MLD + q];
             double cs_ = 1.0, sn = 0.0;
-            // t = 2 apq / (d + sign(d) sqrt(d^2 + 4 apq^2)),  c = 1/sqrt(1 + t^2),  s = t c.  Reciprocals via rsqrt
-            // (62-cycle chain on sm_100a, tools/microbench): only c^2 + s^2 = 1 has to hold to round-off, the angle
-            // itself may carry a few ulp (the next digit-doubling sweep removes any residual).
+            // Small-angle Jacobi rotation from the double-angle identities (two dependent rsqrt instead of three
+            // divisions/square roots; rsqrt is a 62-cycle chain on sm_100a, tools/microbench/lat.cu):
+            //   r = sqrt(d^2 + 4 apq^2), cos 2t = |d| / r, sin 2t = sign(d) 2 apq / r,
+            //   c^2 = (1 + cos 2t) / 2,  c = c^2 rsqrt(c^2),  s = sin 2t / (2 c).
+            // s has no cancellation for small angles; c^2 + s^2 = 1 holds to a few ulp.
             const double d = aqq - app;
             const double x = d * d + 4.0 * apq * apq;
             if (x > 1e-280) {
-              const double y = d + copysign(x * rsqrt(x), d);  // |y| >= sqrt(x) > 0
-              const double tt = 2.0 * apq * copysign(rsqrt(y * y), y);
-              cs_ = rsqrt(1.0 + tt * tt);
-              sn = tt * cs_;
+              const double ir = rsqrt(x);
+              const double c2 = 0.5 + 0.5 * fabs(d) * ir;
+              const double ic = rsqrt(c2);
+              cs_ = c2 * ic;
+              sn = copysign(apq * ir, d * apq) * ic;
             }
             rcs[8 * buf + l] = make_double2(cs_, sn);
             rpq[8 * buf + l] = make_int2(p, q);
-          } else if (gt >= 32 && t > 0) {
+          } else if (vt >= 32 && t > 0) {
             q_update(buf ^ 1);
           }
           group_bar(grp);
-          if (gt < 64) {
-            // M <- J^T M J on the 8x8 grid of 2x2 blocks: thread -> (kp, kq) = (gt >> 3, gt & 7)
-            const int kp = gt >> 3, kq = gt & 7;
+          if (vt < 64) {
+            // M <- J^T M J on the 8x8 grid of 2x2 blocks: thread -> (kp, kq) = (vt >> 3, vt & 7)
+            const int kp = vt >> 3, kq = vt & 7;
             const int2 pq1 = rpq[8 * buf + kp], pq2 = rpq[8 * buf + kq];
             const double2 cs1 = rcs[8 * buf + kp], cs2 = rcs[8 * buf + kq];
             const int p1 = pq1.x, q1 = pq1.y, p2 = pq2.x, q2 = pq2.y;
@@ -222,7 +229,7 @@ __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, in
           }
           group_bar(grp);
         }
-        if (gt >= 32) q_update((nin - 1) & 1);  // rotations of the last inner round
+        if (vt >= 32) q_update((nin - 1) & 1);  // rotations of the last inner round
       }
       __syncthreads();
       // ---- 2a. column passes: A[:, idx] <- A[:, idx] Q and V[:, idx] <- V[:, idx] Q (m8 n16 k16 per unit) ----
