@@ -130,33 +130,59 @@ def run_reference(args) -> None:
 
 # --------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
+    """SM clock / throttle-reason sampler (NVML in-process; falls back to nvidia-smi)."""
+
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self._halt = index, [], set(), threading.Event()
         self.max_mhz = None
+        self._nvml = None
+        try:
+            import pynvml
 
-    def run(self):
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        nv = self._nvml
+        self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        for name, bit in (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown),
+                          ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                          ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown),
+                          ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                             capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+        self.samples.append(float(out[0]))
+        self.max_mhz = float(out[1])
+        for n, v in zip(names, out[2:]):
+            if v.strip().lower().startswith("active"):
+                self.reasons.add(n)
+
+    def run(self):
         while not self._halt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append(float(out[0]))
-                self.max_mhz = float(out[1])
-                for n, v in zip(names, out[2:]):
-                    if v.strip().lower().startswith("active"):
-                        self.reasons.add(n)
+                self._sample_nvml() if self._nvml is not None else self._sample_smi()
             except Exception:
                 pass
-            self._halt.wait(0.5)
+            self._halt.wait(0.1 if self._nvml is not None else 0.5)
 
     def stop(self):
         self._halt.set()
         self.join(timeout=3)
         med = float(np.median(self.samples)) if self.samples else None
-        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
 def measure_fp64_peak(dev) -> float:
@@ -276,7 +302,9 @@ def run_ours(args) -> None:
                        "sigma_bohr": SIGMA, "l2": "a new conformer batch every step; per-step working set (S,H0,P,W ~190 MB) exceeds L2",
                        "opts": "dxtb defaults (EEQ guess, Anderson, x_atol 1e-4/1e-5, 300 K, D3(BJ) with synthetic table)", "note": NODISP_NOTE},
             "roofline": {"bound": "tensor", "pipe": "fp64 (DFMA/DMMA)", "kernel": "k_scf", "achieved": achieved, "peak": peak,
-                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": 17.906944e6 / 148 * nb,  # DRAM bytes of k_scf per molecule from profiles/r1_scf_r4_ncu_full.csv
+
                          "peak_source": "cuBLAS DGEMM 4096^3 best-of-6 measured in this run (MEASURED_PEAKS.json has no fp64 entry)",
                          "scf_kernel_ms": scf_avg_ms, "scf_share_of_step": scf_avg_ms / (ms / args.steps),
                          "hbm_equiv_gbs": bytes_per_launch / (scf_avg_ms * 1e-3) / 1e9, "hbm_peak_gbs": peaks.get("hbm_gbs")},
