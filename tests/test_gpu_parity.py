@@ -316,3 +316,57 @@ def test_d3_dispersion_kernels_match_oracle_with_synthetic_table(mols):
         assert abs(r.e_disp) > 1e-5
         assert abs(float(e[i]) - r.energy) < E_TOL
         assert np.abs(g[i, :k].cpu().numpy() - r.gradient).max() < F_TOL
+
+
+def test_drug_like_conformer_batch_spot_checks(mols):
+    """BASELINE config 3 recipe at reduced size: capsaicin (49 atoms, nao 142) conformers, energy + forces."""
+    from dxtb_b200 import GFN1Calculator
+
+    dev = _dev()
+    nb = 64
+    numbers, pos = _conformers(mols, "capsaicin", nb, 0.05, 1, dev)
+    chrg = torch.zeros(nb, dtype=torch.float64, device=dev)
+    calc = GFN1Calculator(numbers, opts=NODISP, device=dev, dtype=torch.float64)
+    p = pos.clone().requires_grad_(True)
+    e = calc.get_energy(p, chrg)
+    (g,) = torch.autograd.grad(e.sum(), p)
+    assert g.sum(1).abs().max() < 1e-8
+    for i in (0, 31, 63):
+        r = O.singlepoint(mols["capsaicin"]["numbers"], pos[i].cpu().numpy(), 0.0, opts={"exclude": ("disp",)}, grad=True)
+        assert abs(float(e[i]) - r.energy) < E_TOL
+        assert int(calc.get_iterations()[i]) == r.iterations
+        assert np.abs(g[i].cpu().numpy() - r.gradient).max() < F_TOL
+
+
+def test_ragged_jittered_batch(mols):
+    """BASELINE config 5 recipe at reduced size: zero-padded batch of molecules of very different sizes with
+    jittered geometries (seed 2); every molecule is checked against the oracle."""
+    from dxtb_b200 import GFN1Calculator
+
+    dev = _dev()
+    rng = np.random.default_rng(2)
+    names = ["H2O", "capsaicin", "CH4", "nicotine", "NO2", "AD7en+", "caffeine", "LYS_xao", "SiH4", "MB16_43_01"]
+    items = []
+    for name in names:
+        m = mols[name]
+        xyz = np.array(m["positions"]) + 0.03 * rng.normal(size=(len(m["numbers"]), 3))
+        items.append((np.array(m["numbers"]), xyz, m["charge"]))
+    nat = max(len(z) for z, _, _ in items)
+    numbers = torch.zeros((len(items), nat), dtype=torch.long)
+    pos = torch.zeros((len(items), nat, 3), dtype=torch.float64)
+    chrg = torch.zeros(len(items), dtype=torch.float64)
+    for i, (z, xyz, q) in enumerate(items):
+        numbers[i, : len(z)] = torch.from_numpy(z)
+        pos[i, : len(z)] = torch.from_numpy(xyz)
+        chrg[i] = q
+    calc = GFN1Calculator(numbers.to(dev), opts=NODISP, device=dev, dtype=torch.float64)
+    assert len(calc._buckets) == 2
+    p = pos.to(dev).requires_grad_(True)
+    e = calc.get_energy(p, chrg.to(dev))
+    (g,) = torch.autograd.grad(e.sum(), p)
+    for i, (z, xyz, q) in enumerate(items):
+        r = O.singlepoint(z, xyz, q, opts={"exclude": ("disp",)}, grad=True)
+        assert r.converged
+        assert abs(float(e[i]) - r.energy) < E_TOL
+        assert int(calc.get_iterations()[i]) == r.iterations
+        assert np.abs(g[i, : len(z)].cpu().numpy() - r.gradient).max() < F_TOL
