@@ -105,8 +105,8 @@ XTB_DEV int bp_index(int I, int J, int l) { return (l < JB ? I * JB : J * JB - J
 //   1. one warp per block pair copies its 16x16 sub-matrix, runs the scalar rotations of the pair on the
 //      copy (warp-synchronous, no CTA barrier) and accumulates them into a 16x16 orthogonal Q;
 //   2. all warps apply the Q's with fp64 tensor-core MMAs: A <- A Q (columns), V <- V Q, then A <- Q^T A (rows).
-//   A sweep = one "self" round (pairs (0,1),(2,3),.. with all 120 index pairs of the 16) followed by the
-//   nblk-1 round-robin rounds in which only the 64 cross pairs of a block pair are rotated.
+//   A sweep = one "self" round (block pairs (0,1),(2,3),..: the 2 x 28 in-block index pairs) followed by the
+//   nblk-1 round-robin rounds in which the 64 cross pairs of a block pair are rotated: every index pair once.
 // Compared with rotating the full matrix after every scalar rotation round this moves A and V through
 // shared memory ~10x instead of ~80x per sweep.  Returns the number of sweeps, or -sweeps if not converged.
 template <bool SM>
@@ -162,7 +162,7 @@ __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, in
           Q[rr * QLD + cc] = (rr == cc) ? 1.0 : 0.0;
         }
         group_bar(grp);
-        const int nin = (r < 0) ? JB2 - 1 : JB;
+        const int nin = (r < 0) ? JB - 1 : JB;
         // Software pipeline: between the two group barriers of inner round t, warp 0 computes the 8 rotations of
         // round t while warps 1..3 apply the rotations of round t-1 to Q (Q is off the critical path
         // rot(t) -> M(t) -> rot(t+1)); rotation parameters are double buffered.
@@ -184,9 +184,12 @@ __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, in
             const int l = vt;
             int p, q;
             if (r < 0) {
-              if (l == 0) { p = t; q = JB2 - 1; }
-              else { p = t + l; if (p >= JB2 - 1) p -= JB2 - 1; q = t - l; if (q < 0) q += JB2 - 1; }
+              // self round: the 28 in-block pairs of block I (l < 4) and of block J (l >= 4), round-robin on 8
+              const int k = l & 3, h = (l >> 2) * JB;
+              if (k == 0) { p = t; q = JB - 1; }
+              else { p = t + k; if (p >= JB - 1) p -= JB - 1; q = t - k; if (q < 0) q += JB - 1; }
               if (p > q) { const int x = p; p = q; q = x; }
+              p += h; q += h;
             } else {
               p = l; q = JB + ((l + t) & (JB - 1));
             }
