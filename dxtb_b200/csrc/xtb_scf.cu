@@ -88,8 +88,10 @@ __device__ void gemm_tn(int ne, int K, const double* __restrict__ L, const doubl
   __syncthreads();
 }
 
-// named barrier for a group of 4 warps (ids 1..8; id 0 is __syncthreads)
-XTB_DEV void group_bar(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
+// named barrier for a thread group of 3 warps (ids 1..10; id 0 is __syncthreads)
+constexpr int GS = 96;            // threads per sub-problem group
+constexpr int NGRP = NT / GS;     // 10 groups (the last two warps of the CTA idle during the sub-problems)
+XTB_DEV void group_bar(int grp) { asm volatile("bar.sync %0, 96;" ::"r"(grp + 1) : "memory"); }
 
 constexpr int JB = 8;        // Jacobi block size
 constexpr int JB2 = 2 * JB;  // indices of a block pair
@@ -102,7 +104,7 @@ XTB_DEV int bp_index(int I, int J, int l) { return (l < JB ? I * JB : J * JB - J
 // BLOCKED two-sided Jacobi (block size 8) on the symmetric ne x ne matrix A (ne % 16 == 0), accumulating
 // the transformation into the columns of V (ne rows).
 //   Per block round (round-robin over the ne/8 blocks, ne/16 disjoint block pairs):
-//   1. one warp per block pair copies its 16x16 sub-matrix, runs the scalar rotations of the pair on the
+//   1. one thread group (3 warps) per block pair copies its 16x16 sub-matrix, runs the scalar rotations of the pair on the
 //      copy (warp-synchronous, no CTA barrier) and accumulates them into a 16x16 orthogonal Q;
 //   2. all warps apply the Q's with fp64 tensor-core MMAs: A <- A Q (columns), V <- V Q, then A <- Q^T A (rows).
 //   A sweep = one "self" round (block pairs (0,1),(2,3),..: the 2 x 28 in-block index pairs) followed by the
@@ -115,18 +117,19 @@ __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, in
   const int nblk = ne / JB, nbp = nblk / 2, ntile = ne / 8;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int NW = NT / 32;
-  constexpr int NG = NW / 4;  // thread groups of 4 warps for the sub-problems
-  const int grp = warp >> 2, gt = threadIdx.x & 127;
-  // Role rotation: the warp that computes the rotations (and the two that update M) is a different one in each
-  // group, so that the fp64-heavy chains of the concurrently running groups land on different SM sub-partitions
-  // (warp % 4) instead of all on sub-partition 0.
-  const int vt = ((((gt >> 5) - (grp & 3)) & 3) << 5) | lane;
+  constexpr int NG = NGRP;  // thread groups of 3 warps for the sub-problems
+  // group g = warps 3g..3g+2: warp 0 of a group computes the rotations (8 lanes) and, with warp 1, updates the
+  // sub-matrix; warps 1 and 2 accumulate Q.  Since 3g mod 4 cycles through the SM sub-partitions, the fp64-heavy
+  // rotation chains of concurrently running groups do not pile up on one sub-partition.
+  const int grp = warp / 3, gt = (int)threadIdx.x - GS * grp;
+  const int vt = gt;
   double* Qs = c.jq;  // [nbp][16][QLD]
-  double* Ms = c.jm;  // [nbp][16][MLD]
-  double* Rs = c.jr;  // [nbp][48] rotation parameters (double buffered)
+  double* Ms = c.jm;  // [NG][16][MLD]  sub-problem copy of the group
+  double* Rs = c.jr;  // [NG][48] rotation parameters (double buffered)
   int* bij = c.pp;    // [nbp][2] blocks of the pairs of this round
   XTB_ASSUME_SHARED(bij);
-  if (SM) { XTB_ASSUME_SHARED(A); XTB_ASSUME_SHARED(V); XTB_ASSUME_SHARED(Qs); XTB_ASSUME_SHARED(Ms); XTB_ASSUME_SHARED(Rs); }
+  XTB_ASSUME_SHARED(Qs); XTB_ASSUME_SHARED(Ms); XTB_ASSUME_SHARED(Rs);
+  if (SM) { XTB_ASSUME_SHARED(A); XTB_ASSUME_SHARED(V); }
   (void)nrow;
   int sweep = 0;
   for (;;) {
@@ -142,7 +145,7 @@ __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, in
     ++sweep;
     for (int r = -1; r < nblk - 1; ++r) {
       // ---- 1. sub-problems: a group of 4 warps (128 threads, named barrier) owns a block pair ----------
-      for (int w = grp; w < nbp; w += NG) {
+      for (int w = grp; w < nbp && grp < NG; w += NG) {
         int I, J;
         if (r < 0) { I = 2 * w; J = 2 * w + 1; }
         else if (w == 0) { I = r; J = nblk - 1; }
@@ -151,12 +154,12 @@ __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, in
           J = (r - w + 2 * (nblk - 1)) % (nblk - 1);
         }
         if (I > J) { const int t = I; I = J; J = t; }
-        double* M = Ms + w * (JB2 * MLD);
+        double* M = Ms + grp * (JB2 * MLD);
         double* Q = Qs + w * (JB2 * QLD);
-        double2* rcs = reinterpret_cast<double2*>(Rs + w * 48);   // [2][8] (c, s), double buffered
-        int2* rpq = reinterpret_cast<int2*>(Rs + w * 48 + 32);    // [2][8] (p, q)
+        double2* rcs = reinterpret_cast<double2*>(Rs + grp * 48);   // [2][8] (c, s), double buffered
+        int2* rpq = reinterpret_cast<int2*>(Rs + grp * 48 + 32);    // [2][8] (p, q)
         if (gt == 0) { bij[2 * w] = I; bij[2 * w + 1] = J; }
-        for (int e = gt; e < JB2 * JB2; e += 128) {
+        for (int e = gt; e < JB2 * JB2; e += GS) {
           const int rr = e >> 4, cc = e & 15;
           M[rr * MLD + cc] = A[(size_t)bp_index(I, J, rr) * ld + bp_index(I, J, cc)];
           Q[rr * QLD + cc] = (rr == cc) ? 1.0 : 0.0;
@@ -167,8 +170,8 @@ __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, in
         // round t while warps 1..3 apply the rotations of round t-1 to Q (Q is off the critical path
         // rot(t) -> M(t) -> rot(t+1)); rotation parameters are double buffered.
         auto q_update = [&](int buf) {
-          // 128 items (16 rows x 8 pairs) on 96 threads; every half-warp covers 4 rows x 4 pairs (conflict-free)
-          for (int it = vt - 32; it < 128; it += 96) {
+          // 128 items (16 rows x 8 pairs) on 64 threads; every half-warp covers 4 rows x 4 pairs (conflict-free)
+          for (int it = vt - 32; it < 128; it += GS - 32) {
             const int qk = (it & 3) + 4 * ((it >> 4) & 1), qi = ((it >> 2) & 3) + 4 * (it >> 5);
             const int2 pqq = rpq[8 * buf + qk];
             const double2 csq = rcs[8 * buf + qk];
@@ -703,11 +706,13 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
   double* sm_theta = p; p += 36;
   c.occl = (int*)p; p += (nmx + 2) / 2 + 1;
   p += ((p - sm) & 1);  // 16-byte alignment for the double2 / int2 scratch and the matrices
-  if (SM) {
+  {
+    // block-Jacobi scratch, always in shared memory: accumulated rotations Q per block pair, sub-problem copy and
+    // rotation parameters per concurrently working thread group
     const int nbpx = (lnao + 15) / 16;
     c.jq = p; p += nbpx * JB2 * QLD;
-    c.jm = p; p += nbpx * JB2 * MLD;
-    c.jr = p; p += nbpx * 48;
+    c.jm = p; p += NGRP * JB2 * MLD;
+    c.jr = p; p += NGRP * 48;
   }
   p += ((p - sm) & 1);
   c.smem = SM;
@@ -719,11 +724,6 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
   } else {
     double* wm = work + (size_t)(o.generations + 1) * 2 * b.nao_tot + 3 * ((size_t)b.mat_off[m] + 34 * (size_t)c.o0 + 285 * (size_t)m);  // sum of (n+15)(n+19) bounds ne*ld
     c.C = wm; c.A = wm + msz; c.X = wm + 2 * msz;
-    // block-Jacobi scratch of this molecule: nbp * (16 * (QLD + MLD) + 32) <= 47 n + 752 doubles (+2 for 16-byte alignment)
-    double* ws = work + (size_t)(o.generations + 1) * 2 * b.nao_tot + 3 * ((size_t)b.mat_total + 34 * (size_t)b.nao_tot + 285 * (size_t)b.nb) +
-                 47 * (size_t)c.o0 + 754 * (size_t)m;
-    ws = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(ws) + 15) & ~(uintptr_t)15);
-    c.jq = ws; c.jm = ws + (size_t)(ne / 16) * JB2 * QLD; c.jr = c.jm + (size_t)(ne / 16) * JB2 * MLD;
   }
   c.xh = work + (size_t)(o.generations + 1) * 2 * c.o0;
   c.fh = c.xh + (size_t)(o.generations + 1) * n;
@@ -838,6 +838,8 @@ int64_t vec_smem_bytes(int64_t nao_max, int64_t nsx, int64_t nax) {
   const int64_t nmx = nao_max + 2;
   int64_t d = 2 * (nmx + (nmx & 1)) + 8 * nmx + 2 * nsx + nax + 32 + 36 + (nmx + 2) / 2 + 1;
   d += d & 1;
+  d += ((nao_max + 15) / 16) * JB2 * QLD + NGRP * (JB2 * MLD + 48);  // block-Jacobi scratch
+  d += d & 1;
   return d * 8;
 }
 
@@ -845,7 +847,7 @@ int64_t vec_smem_bytes(int64_t nao_max, int64_t nsx, int64_t nax) {
 
 extern "C" int64_t xtb_scf_smem_bytes_for(int32_t nao_max, int32_t nsh_max, int32_t nat_max) {
   const int64_t nex = (nao_max + 15) & ~15;
-  return vec_smem_bytes(nao_max, nsh_max, nat_max) + (3 * nex * (nex + 4) + (nex / 16) * (JB2 * (QLD + MLD) + 48)) * 8;
+  return vec_smem_bytes(nao_max, nsh_max, nat_max) + 3 * nex * (nex + 4) * 8;
 }
 
 extern "C" int64_t xtb_scf_smem_bytes(const xtb_batch* b) {
@@ -859,7 +861,6 @@ extern "C" int64_t xtb_scf_workspace_bytes(const xtb_batch* b, const xtb_scf_opt
   if (!o->use_smem) {
     // 3 matrices of (n+1)(n+2) per molecule: 3 (sum n^2 + 3 sum n + 2 nb)
     d += 3 * (b->mat_total + 34 * (int64_t)b->nao_tot + 285 * (int64_t)b->nb);
-    d += 47 * (int64_t)b->nao_tot + 754 * (int64_t)b->nb;
   }
   return d * 8 + 256;
 }
