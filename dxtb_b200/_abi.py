@@ -67,7 +67,7 @@ EXPORTS = {
     "xtb_scf_smem_bytes": (C.c_int64, [_vp]),
     "xtb_scf_smem_bytes_for": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     "xtb_scf_run": (C.c_int, [_vp] * 21),
-    "xtb_grad_bwd": (C.c_int, [_vp] * 14),
+    "xtb_grad_bwd": (C.c_int, [_vp] * 15),
     "xtb_d3_fwd": (C.c_int, [_vp] * 6),
 }
 

@@ -164,12 +164,14 @@ class _SinglePoint(torch.autograd.Function):
             ge = ge.expand(d.nb).contiguous()
         grad = torch.empty((d.nat_tot, 3), dtype=torch.float64, device=d.device)
         dedcn = torch.empty(d.nat_tot, dtype=torch.float64, device=d.device)
+        pairbuf = torch.empty(4 * int(d.struct.gam_total), dtype=torch.float64, device=d.device)
         if ctx.excl_rep:
             raise NotImplementedError("analytic gradient with exclude=['rep'] is not implemented")
         _abi.check(
             _abi.lib().xtb_grad_bwd(d.ptr, pos.data_ptr(), cn.data_ptr(), S.data_ptr(), P.data_ptr(), W.data_ptr(), v_orb.data_ptr(),
                                     q_sh.data_ptr(), gamma.data_ptr(), ge.data_ptr(),
-                                    ctx.d3w.data_ptr() if ctx.d3w is not None else None, dedcn.data_ptr(), grad.data_ptr(),
+                                    ctx.d3w.data_ptr() if ctx.d3w is not None else None, pairbuf.data_ptr(), dedcn.data_ptr(),
+                                    grad.data_ptr(),
                                     _stream_ptr(d.device)),
             "xtb_grad_bwd",
         )
@@ -266,6 +268,13 @@ class GFN1Calculator:
         if fits is None:  # vectorised bound for very large batches: the layout grows monotonically with nao
             nao_cap = max([n for n in range(1, 200) if lib.xtb_scf_smem_bytes_for(n, 3 * n, n) <= _SMEM_LIMIT] or [0])
             fits = d.nao <= nao_cap
+        big = int(d.nao.max())
+        if lib.xtb_scf_smem_bytes_for(big, int(d.nsh.max()), int(d.nat.max())) - 3 * ((big + 15) // 16 * 16) * ((big + 15) // 16 * 16 + 4) * 8 > _SMEM_LIMIT:
+            raise NotImplementedError(
+                f"a molecule with {big} atomic orbitals exceeds the one-CTA-per-molecule SCF kernel (its per-orbital "
+                "vectors and Jacobi scratch no longer fit in shared memory); the multi-CTA eigensolver for such systems "
+                "(BASELINE config 4) is not built yet"
+            )
         buckets = []
         for use_smem, sel in ((0, ~fits), (1, fits)):
             idx = np.flatnonzero(sel)

@@ -205,19 +205,57 @@ __global__ void k_eeq(const xtb_batch b, const double* __restrict__ pos, const d
 // electrostatics with fixed charges (secondorder.py:873-926) and the CN chain rule
 // (ncoord/utils.py:30-52 with the exp-count derivative).  One CTA per molecule.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_grad_atoms(const xtb_batch b, const double* __restrict__ pos, const double* __restrict__ q_sh,
-                             const double* __restrict__ gamma, const double* __restrict__ dedcn,
-                             const double* __restrict__ ge, double* __restrict__ grad) {
+__global__ void k_grad_atoms(const xtb_batch b, const double* __restrict__ pos, const double* __restrict__ P,
+                             const double* __restrict__ q_sh, const double* __restrict__ gamma,
+                             const double* __restrict__ pairbuf, double* __restrict__ dedcn, const double* __restrict__ ge,
+                             double* __restrict__ grad) {
   const int m = blockIdx.x;
   const int a0 = b.at_off[m], na = b.at_off[m + 1] - a0;
   const int s0 = b.sh_off[m], ns = b.sh_off[m + 1] - s0;
+  const int o0 = b.ao_off[m], n = b.ao_off[m + 1] - o0;
   const double* p = pos + 3 * (size_t)a0;
   const double* g = gamma + b.gam_off[m];
+  const double* slots = pairbuf + 4 * (size_t)b.gam_off[m];
+  const double* Pm = P + b.mat_off[m];
   const double scale = ge[m];
+  // ---- phase A: dE/dCN of every atom (fixed summation order; dedcn may already hold the dispersion part) ----
+  for (int a = threadIdx.x; a < na; a += blockDim.x) {
+    const int sa0 = b.at_sh0[a0 + a], nsa = b.at_nsh[a0 + a];
+    double d = dedcn[a0 + a];
+    for (int k = 0; k < nsa; ++k) {
+      const int I = sa0 + k;
+      const double kcn = b.sh_par[(size_t)(s0 + I) * XTB_SHPAR + XTB_SH_KCN];
+      double acc = 0.0;
+      const int mu0 = b.sh_ao[s0 + I], nmu = 2 * b.sh_l[s0 + I] + 1;
+      for (int mu = mu0; mu < mu0 + nmu; ++mu) acc += Pm[(size_t)mu * n + mu];  // same-shell part (S = 1)
+      for (int J = 0; J < ns; ++J) {
+        if (J == I) continue;
+        acc += (I > J) ? slots[4 * ((size_t)I * ns + J) + 3] : slots[4 * ((size_t)J * ns + I) + 3];
+      }
+      d -= kcn * acc;
+    }
+    dedcn[a0 + a] = d;
+  }
+  __syncthreads();
+  // ---- phase B: gradient of atom a ----------------------------------------------------------------------
   for (int a = threadIdx.x; a < na; a += blockDim.x) {
     const double* pa = b.at_par + (size_t)(a0 + a) * XTB_ATPAR;
     const int sa0 = b.at_sh0[a0 + a], nsa = b.at_nsh[a0 + a];
     double gx = 0.0, gy = 0.0, gz = 0.0;
+    // shell-pair terms (overlap derivative + dPi/dR), ordered by (shell of a, other shell)
+    for (int k = 0; k < nsa; ++k) {
+      const int I = sa0 + k;
+      for (int J = 0; J < ns; ++J) {
+        if (J == I) continue;
+        if (I > J) {
+          const double* sl = slots + 4 * ((size_t)I * ns + J);
+          gx += sl[0]; gy += sl[1]; gz += sl[2];
+        } else {
+          const double* sl = slots + 4 * ((size_t)J * ns + I);
+          gx -= sl[0]; gy -= sl[1]; gz -= sl[2];
+        }
+      }
+    }
     for (int c = 0; c < na; ++c) {
       if (c == a) continue;
       const double* pc = b.at_par + (size_t)(a0 + c) * XTB_ATPAR;
@@ -247,9 +285,10 @@ __global__ void k_grad_atoms(const xtb_batch b, const double* __restrict__ pos, 
       f += es;
       gx += f * dx; gy += f * dy; gz += f * dz;
     }
-    atomicAdd(&grad[3 * (size_t)(a0 + a)], scale * gx);
-    atomicAdd(&grad[3 * (size_t)(a0 + a) + 1], scale * gy);
-    atomicAdd(&grad[3 * (size_t)(a0 + a) + 2], scale * gz);
+    // single writer per address: deterministic (grad may already hold the direct dispersion part)
+    grad[3 * (size_t)(a0 + a)] += scale * gx;
+    grad[3 * (size_t)(a0 + a) + 1] += scale * gy;
+    grad[3 * (size_t)(a0 + a) + 2] += scale * gz;
   }
 }
 
@@ -326,10 +365,10 @@ __global__ void k_d3_pairs(const xtb_batch b, const double* __restrict__ pos, co
       edisp[a0 + a] = e;
     } else {
       const double sc = ge[m];
-      atomicAdd(&grad[3 * (size_t)(a0 + a)], sc * gx);
-      atomicAdd(&grad[3 * (size_t)(a0 + a) + 1], sc * gy);
-      atomicAdd(&grad[3 * (size_t)(a0 + a) + 2], sc * gz);
-      atomicAdd(&dedcn[a0 + a], dcn);
+      grad[3 * (size_t)(a0 + a)] += sc * gx;  // single writer per address
+      grad[3 * (size_t)(a0 + a) + 1] += sc * gy;
+      grad[3 * (size_t)(a0 + a) + 2] += sc * gz;
+      dedcn[a0 + a] += dcn;
     }
   }
 }
@@ -386,8 +425,8 @@ int xtb_launch_d3_grad(const xtb_batch* b, const double* pos, const double* d3w,
 }
 
 // used by xtb_grad_bwd (xtb_integrals.cu)
-int xtb_launch_grad_atoms(const xtb_batch* b, const double* pos, const double* q_sh, const double* gamma,
-                          const double* dedcn, const double* ge, double* grad, cudaStream_t st) {
-  k_grad_atoms<<<b->nb, 128, 0, st>>>(*b, pos, q_sh, gamma, dedcn, ge, grad);
+int xtb_launch_grad_atoms(const xtb_batch* b, const double* pos, const double* P, const double* q_sh, const double* gamma,
+                          const double* pairbuf, double* dedcn, const double* ge, double* grad, cudaStream_t st) {
+  k_grad_atoms<<<b->nb, 128, 0, st>>>(*b, pos, P, q_sh, gamma, pairbuf, dedcn, ge, grad);
   return launch_status();
 }

@@ -285,8 +285,7 @@ __global__ void k_diag(const xtb_batch b, const double* __restrict__ cn, double*
 template <int LI, int LJ>
 __global__ void __launch_bounds__(128) k_grad_pair(const xtb_batch b, const double* __restrict__ pos, const double* __restrict__ cn,
                                                    const double* __restrict__ P, const double* __restrict__ W,
-                                                   const double* __restrict__ v_orb, const double* __restrict__ ge,
-                                                   double* __restrict__ dedcn, double* __restrict__ grad) {
+                                                   const double* __restrict__ v_orb, double* __restrict__ pairbuf) {
   const int m = blockIdx.y;
   const PairInfo pi = pair_setup<LI, LJ>(b, m, pos);
   if (!pi.valid) return;
@@ -320,27 +319,18 @@ __global__ void __launch_bounds__(128) k_grad_pair(const xtb_batch b, const doub
   gx += dpi * (-pi.vx);
   gy += dpi * (-pi.vy);
   gz += dpi * (-pi.vz);
-  const double sc = ge[m];
-  double* ga = grad + 3 * (size_t)(a0 + pi.A);
-  double* gb = grad + 3 * (size_t)(a0 + pi.B);
-  atomicAdd(ga + 0, sc * gx); atomicAdd(ga + 1, sc * gy); atomicAdd(ga + 2, sc * gz);
-  atomicAdd(gb + 0, -sc * gx); atomicAdd(gb + 1, -sc * gy); atomicAdd(gb + 2, -sc * gz);
-  // dE/dCN: -kcn * Pi*K * (P.S)_sh to the atom owning each shell
-  const double pk = ps * f.var_pi * f.var_k;
-  atomicAdd(&dedcn[a0 + pi.A], -f.kcn_a * pk);
-  atomicAdd(&dedcn[a0 + pi.B], -f.kcn_b * pk);
-}
-
-// same-shell part of dE/dCN: -kcn * sum_{mu in shell} P_mumu
-__global__ void k_dedcn_diag(const xtb_batch b, const double* __restrict__ P, double* __restrict__ dedcn) {
-  const int m = blockIdx.y;
-  const int o0 = b.ao_off[m], n = b.ao_off[m + 1] - o0;
-  const int s0 = b.sh_off[m], a0 = b.at_off[m];
-  for (int mu = blockIdx.x * blockDim.x + threadIdx.x; mu < n; mu += gridDim.x * blockDim.x) {
-    const int sh = b.ao_sh[o0 + mu];
-    const double kcn = b.sh_par[(size_t)(s0 + sh) * XTB_SHPAR + XTB_SH_KCN];
-    atomicAdd(&dedcn[a0 + b.sh_atom[s0 + sh]], -kcn * P[b.mat_off[m] + (size_t)mu * n + mu]);
-  }
+  // Deterministic accumulation: every shell pair owns the slot (hi, lo) = (max(I,J), min(I,J)) of an nsh x nsh
+  // table; k_grad_atoms sums the slots of an atom in a fixed order (no atomics, bit-reproducible forces).
+  // Stored: derivative w.r.t. the atom of shell `hi`, and Pi*K*(P.S)_sh for dE/dCN.
+  const int ns = b.sh_off[m + 1] - s0;
+  const double sg = pi.I > pi.J ? 1.0 : -1.0;
+  const int hi = pi.I > pi.J ? pi.I : pi.J, lo = pi.I > pi.J ? pi.J : pi.I;
+  double* slot = pairbuf + 4 * ((size_t)b.gam_off[m] + (size_t)hi * ns + lo);
+  slot[0] = sg * gx;
+  slot[1] = sg * gy;
+  slot[2] = sg * gz;
+  slot[3] = ps * f.var_pi * f.var_k;
+  (void)a0;
 }
 
 template <int LI, int LJ> int launch_overlap(const xtb_batch* b, const double* pos, const double* cn, double* S, double* H0, cudaStream_t st) {
@@ -352,18 +342,18 @@ template <int LI, int LJ> int launch_overlap(const xtb_batch* b, const double* p
 }
 template <int LI, int LJ>
 int launch_grad_pair(const xtb_batch* b, const double* pos, const double* cn, const double* P, const double* W, const double* v,
-                     const double* ge, double* dedcn, double* grad, cudaStream_t st) {
+                     double* pairbuf, cudaStream_t st) {
   const int nt = 128;
   const int npair = b->nsh_max * b->nsh_max;
   dim3 grid((npair + nt - 1) / nt, b->nb);
-  k_grad_pair<LI, LJ><<<grid, nt, 0, st>>>(*b, pos, cn, P, W, v, ge, dedcn, grad);
+  k_grad_pair<LI, LJ><<<grid, nt, 0, st>>>(*b, pos, cn, P, W, v, pairbuf);
   return launch_status();
 }
 
 }  // namespace
 
-int xtb_launch_grad_atoms(const xtb_batch* b, const double* pos, const double* q_sh, const double* gamma,
-                          const double* dedcn, const double* ge, double* grad, cudaStream_t st);
+int xtb_launch_grad_atoms(const xtb_batch* b, const double* pos, const double* P, const double* q_sh, const double* gamma,
+                          const double* pairbuf, double* dedcn, const double* ge, double* grad, cudaStream_t st);
 int xtb_launch_d3_grad(const xtb_batch* b, const double* pos, const double* d3w, const double* ge, double* dedcn, double* grad,
                        cudaStream_t st);
 
@@ -388,24 +378,22 @@ extern "C" int xtb_overlap_h0_fwd(const xtb_batch* b, const double* pos, const d
 
 extern "C" int xtb_grad_bwd(const xtb_batch* b, const double* pos, const double* cn, const double* S, const double* P,
                             const double* W, const double* v_orb, const double* q_sh, const double* gamma, const double* ge,
-                            const double* d3w, double* dedcn, double* grad, void* stream) {
+                            const double* d3w, double* pairbuf, double* dedcn, double* grad, void* stream) {
   (void)S;
-  if (!b || !pos || !cn || !P || !W || !v_orb || !q_sh || !gamma || !ge || !dedcn || !grad) return -1;
+  if (!b || !pos || !cn || !P || !W || !v_orb || !q_sh || !gamma || !ge || !pairbuf || !dedcn || !grad) return -1;
   if (b->nb == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(dedcn, 0, sizeof(double) * (size_t)b->nat_tot, st);
   cudaMemsetAsync(grad, 0, sizeof(double) * 3 * (size_t)b->nat_tot, st);
+  cudaMemsetAsync(pairbuf, 0, sizeof(double) * 4 * (size_t)b->gam_total, st);
   int rc;
-  if ((rc = launch_grad_pair<0, 0>(b, pos, cn, P, W, v_orb, ge, dedcn, grad, st))) return rc;
-  if ((rc = launch_grad_pair<1, 0>(b, pos, cn, P, W, v_orb, ge, dedcn, grad, st))) return rc;
-  if ((rc = launch_grad_pair<1, 1>(b, pos, cn, P, W, v_orb, ge, dedcn, grad, st))) return rc;
-  if ((rc = launch_grad_pair<2, 0>(b, pos, cn, P, W, v_orb, ge, dedcn, grad, st))) return rc;
-  if ((rc = launch_grad_pair<2, 1>(b, pos, cn, P, W, v_orb, ge, dedcn, grad, st))) return rc;
-  if ((rc = launch_grad_pair<2, 2>(b, pos, cn, P, W, v_orb, ge, dedcn, grad, st))) return rc;
-  int gx = (b->nao_max + 127) / 128;
-  k_dedcn_diag<<<dim3(gx, b->nb), 128, 0, st>>>(*b, P, dedcn);
-  if ((rc = launch_status())) return rc;
-  // dispersion: direct part into grad, dE/dCN into dedcn (the exp-count CN is shared with H0)
+  if ((rc = launch_grad_pair<0, 0>(b, pos, cn, P, W, v_orb, pairbuf, st))) return rc;
+  if ((rc = launch_grad_pair<1, 0>(b, pos, cn, P, W, v_orb, pairbuf, st))) return rc;
+  if ((rc = launch_grad_pair<1, 1>(b, pos, cn, P, W, v_orb, pairbuf, st))) return rc;
+  if ((rc = launch_grad_pair<2, 0>(b, pos, cn, P, W, v_orb, pairbuf, st))) return rc;
+  if ((rc = launch_grad_pair<2, 1>(b, pos, cn, P, W, v_orb, pairbuf, st))) return rc;
+  if ((rc = launch_grad_pair<2, 2>(b, pos, cn, P, W, v_orb, pairbuf, st))) return rc;
+  // dispersion: direct part into grad, dE/dCN into dedcn (the exp-count CN is shared with H0); one writer per atom
   if (d3w && (rc = xtb_launch_d3_grad(b, pos, d3w, ge, dedcn, grad, st))) return rc;
-  return xtb_launch_grad_atoms(b, pos, q_sh, gamma, dedcn, ge, grad, st);
+  return xtb_launch_grad_atoms(b, pos, P, q_sh, gamma, pairbuf, dedcn, ge, grad, st);
 }

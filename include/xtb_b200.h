@@ -155,10 +155,11 @@ int xtb_scf_run(const xtb_batch* b, const xtb_scf_opts* o, const double* S, cons
 /* Analytic nuclear gradient of the converged single point (calculators/types/analytical.py:63-222,
  * xtb/gfn1.py:185-408, secondorder.py:873-926, repulsion/base.py:337-406, ncoord/utils.py:30-52):
  * grad[a] = ge[m] * dE_m/dR_a, ge [nb] being the upstream gradient of the molecular energies.
- * dedcn [nat_tot] is scratch; d3w = weights of xtb_d3_fwd, or NULL when dispersion is excluded. */
+ * dedcn [nat_tot] and pairbuf [4 * gam_off[nb]] are scratch; d3w = weights of xtb_d3_fwd, or NULL when
+ * dispersion is excluded.  No atomics: the result is bit-reproducible. */
 int xtb_grad_bwd(const xtb_batch* b, const double* pos, const double* cn, const double* S, const double* P,
                  const double* W, const double* v_orb, const double* q_sh, const double* gamma, const double* ge,
-                 const double* d3w, double* dedcn, double* grad, void* stream);
+                 const double* d3w, double* pairbuf, double* dedcn, double* grad, void* stream);
 
 /* D3(BJ) two-body dispersion energy (tad-dftd3 dftd3: weight_references, atomic_c6, dispersion with
  * rational_damping; s9 = 0 for GFN1).  cn is the exp-count CN of xtb_geometry_fwd; d3w [nat_tot][14] receives

@@ -126,7 +126,7 @@ def test_readme_example_forces_equal_minus_gradient(mols):
     calc.reset()
     forces = calc.get_forces(positions)
     assert energy.shape == () and forces.shape == (2, 3)
-    assert torch.allclose(forces, -g, rtol=0, atol=1e-14)
+    assert torch.equal(forces, -g)  # README.md:108-122: bit-equal (the gradient kernels use no atomics)
     r = _oracle(mols, "LiH_readme", grad=True)
     assert abs(float(energy) - r.energy) < E_TOL
     assert np.abs(-forces.cpu().numpy() - r.gradient).max() < F_TOL
@@ -242,6 +242,11 @@ def test_full_size_conformer_batch_properties(mols):
     (g,) = torch.autograd.grad(e.sum(), p)
     it = calc.get_iterations()
     assert torch.isfinite(e).all() and torch.isfinite(g).all()
+    # bit-reproducible: no atomics anywhere on the path
+    p2 = pos.clone().requires_grad_(True)
+    e_again = calc.get_energy(p2, chrg)
+    (g_again,) = torch.autograd.grad(e_again.sum(), p2)
+    assert torch.equal(e_again, e) and torch.equal(g_again, g)
     # total charge conserved, forces sum to zero (translational invariance)
     assert calc.get_mulliken_charges().sum(-1).abs().max() < 1e-9
     assert g.sum(1).abs().max() < 1e-8
