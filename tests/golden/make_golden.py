@@ -84,6 +84,13 @@ def read_xyz(p, first=True):
     return nums, pos
 
 
+def atom_refs():
+    txt = open(REF / "test/test_scf/test_elements_gfn1.py").read()
+    a = txt.index("ref = torch.tensor(")
+    blk = txt[a : txt.index("ref_cation", a)]
+    return [float(x) for x in re.findall(r"-?\d+\.\d+(?:e[-+]?\d+)?", blk)]
+
+
 def main():
     mols = {}
     base = REF / "test/test_singlepoint/mols"
@@ -141,6 +148,8 @@ def main():
         "scf_gfn1_tblite": {k: v for k, v in literals(REF / "test/test_scf/samples.py", "egfn1").items() if k in mols},
         "total_gfn1_tblite": literals(REF / "test/test_singlepoint/samples.py", "egfn1"),
         "eeq_guess_CH": [-0.11593066900969, -0.03864355757833, -0.03864355757833, -0.03864355757833, 0.11593066900969, 0.11593066900969],
+        "scf_gfn1_tblite_atoms": atom_refs(),
+        "scf_gfn1_tblite_atoms_source": "test/test_scf/test_elements_gfn1.py:45-132 (tblite 0.2.1, neutral atoms Z=1..86, no repulsion/dispersion)",
         "note": "tblite values (fp64 literals of the reference tests); tblite uses 1 Eh = 27.21138505 eV",
     }
     (OUT / "energies.json").write_text(json.dumps(energies, indent=1))

@@ -375,3 +375,24 @@ def test_ragged_jittered_batch(mols):
         assert abs(float(e[i]) - r.energy) < E_TOL
         assert int(calc.get_iterations()[i]) == r.iterations
         assert np.abs(g[i, : len(z)].cpu().numpy() - r.gradient).max() < F_TOL
+
+
+def test_atomic_scf_energies_all_elements_gpu(energies):
+    """All 86 neutral atoms in one padded batch (nao 1..9; open shells, s/p/d shells, 6s/6p STO-6G special case)
+    against tblite's atomic SCF energies (test/test_scf/test_elements_gfn1.py; Mn excluded, see the oracle test)."""
+    from dxtb_b200 import GFN1Calculator
+    from dxtb_b200.param import gfn1_param
+
+    dev = _dev()
+    zs = [z for z in range(1, 87) if z != 25]
+    numbers = torch.tensor(zs, device=dev)[:, None]
+    pos = torch.zeros((len(zs), 1, 3), dtype=torch.float64, device=dev)
+    chrg = torch.zeros(len(zs), dtype=torch.float64, device=dev)
+    par = gfn1_param().with_ev2au(1.0 / 27.21138505)
+    opts = {"exclude": ["disp", "rep", "hal"], "x_atol": 1e-9, "x_atol_max": 1e-9, "maxiter": 300, "guess": "sad"}
+    calc = GFN1Calculator(numbers, par, opts=opts, device=dev, dtype=torch.float64)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        e = calc.get_energy(pos, chrg).cpu().numpy()
+    ref = np.array([energies["scf_gfn1_tblite_atoms"][z - 1] for z in zs])
+    assert np.abs(e - ref).max() < 1e-7
