@@ -13,7 +13,8 @@ ROOT = Path(__file__).resolve().parent
 CSRC = ROOT / "csrc"
 INCLUDE = ROOT.parent / "include"
 SO_PATH = ROOT / "_C.so"
-SOURCES = ["xtb_geometry.cu", "xtb_integrals.cu", "xtb_scf.cu"]
+# (source, object suffix, extra flags): xtb_scf.cu is built twice, see the comment at its top
+SOURCES = [("xtb_geometry.cu", "", []), ("xtb_integrals.cu", "", []), ("xtb_scf.cu", "", []), ("xtb_scf.cu", ".nt512", ["-DXTB_NT=512"])]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "-diag-suppress", "177",
@@ -31,7 +32,7 @@ def needs_build() -> bool:
     if not SO_PATH.exists():
         return True
     t = SO_PATH.stat().st_mtime
-    deps = [CSRC / s for s in SOURCES] + list(CSRC.glob("*.cuh")) + list(INCLUDE.glob("*.h"))
+    deps = [CSRC / s[0] for s in SOURCES] + list(CSRC.glob("*.cuh")) + list(INCLUDE.glob("*.h"))
     return any(d.stat().st_mtime > t for d in deps)
 
 
@@ -44,12 +45,12 @@ def build_extension(force: bool = False, verbose: bool = False) -> Path:
     objdir.mkdir(exist_ok=True)
     objs = []
     procs = []
-    for s in SOURCES:
-        obj = objdir / (s + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, f"-I{INCLUDE}", f"-I{CSRC}", "-c", str(CSRC / s), "-o", str(obj)]
+    for s, suffix, extra in SOURCES:
+        obj = objdir / (s + suffix + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, *extra, f"-I{INCLUDE}", f"-I{CSRC}", "-c", str(CSRC / s), "-o", str(obj)]
         if verbose:
             print(" ".join(cmd))
-        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        procs.append((s + suffix, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(str(obj))
     for s, p in procs:
         out, _ = p.communicate()

@@ -18,7 +18,14 @@ using namespace xtb;
 
 namespace {
 
-constexpr int NT = 1024;  // threads per CTA (64 registers per thread)
+// This translation unit is compiled twice (dxtb_b200/build.py):
+//   XTB_NT = 1024 (default): the shared-memory variant (1 CTA/SM) + the C entry points;
+//   XTB_NT = 512 : the global-memory variant, 2 CTAs/SM, so that one molecule's latency-bound sub-problem phase
+//                  overlaps the other's L2-bound tensor-core passes.  Exports only xtb_scf_launch_global_512().
+#ifndef XTB_NT
+#define XTB_NT 1024
+#endif
+constexpr int NT = XTB_NT;  // threads per CTA (64 registers per thread in both builds)
 
 struct Ctx {
   int n, ne, ld, ns, na, np;
@@ -672,7 +679,7 @@ __device__ bool mix(Ctx& c, Mixer& mx, const xtb_scf_opts& o, double* sm_theta) 
 }
 
 template <bool SM>
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __launch_bounds__(NT, 1024 / NT)
 k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, const double* __restrict__ H0,
       const double* __restrict__ gamma, const double* __restrict__ nel_ab, const double* __restrict__ q0_at, double* __restrict__ work,
       double* __restrict__ q_orb, double* __restrict__ q_sh, double* __restrict__ q_at, double* __restrict__ v_orb,
@@ -845,6 +852,29 @@ int64_t vec_smem_bytes(int64_t nao_max, int64_t nsx, int64_t nax) {
 
 }  // namespace
 
+#if XTB_NT == 512
+// secondary build: launcher of the 2-CTA/SM global-memory variant
+int xtb_scf_launch_global_512(const xtb_batch* b, const xtb_scf_opts* o, int nblocks, int lnao, int lnsh, int lnat, const double* S,
+                              const double* H0, const double* gamma, const double* nel_ab, const double* q0_at, double* work,
+                              double* q_orb, double* q_sh, double* q_at, double* v_orb, double* e_atom, double* fenergy, double* emo,
+                              double* occ, int32_t* iterations, int32_t* status, double* P, double* W, cudaStream_t st) {
+  const int64_t smem = vec_smem_bytes(lnao, lnsh, lnat);
+  static int64_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_scf<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = smem;
+  }
+  k_scf<false><<<nblocks, NT, (size_t)smem, st>>>(*b, *o, S, H0, gamma, nel_ab, q0_at, work, q_orb, q_sh, q_at, v_orb, e_atom, fenergy,
+                                                   emo, occ, iterations, status, P, W);
+  return launch_status();
+}
+#else
+int xtb_scf_launch_global_512(const xtb_batch* b, const xtb_scf_opts* o, int nblocks, int lnao, int lnsh, int lnat, const double* S,
+                              const double* H0, const double* gamma, const double* nel_ab, const double* q0_at, double* work,
+                              double* q_orb, double* q_sh, double* q_at, double* v_orb, double* e_atom, double* fenergy, double* emo,
+                              double* occ, int32_t* iterations, int32_t* status, double* P, double* W, cudaStream_t st);
+
 extern "C" int64_t xtb_scf_smem_bytes_for(int32_t nao_max, int32_t nsh_max, int32_t nat_max) {
   const int64_t nex = (nao_max + 15) & ~15;
   return vec_smem_bytes(nao_max, nsh_max, nat_max) + 3 * nex * (nex + 4) * 8;
@@ -879,15 +909,38 @@ extern "C" int xtb_scf_run(const xtb_batch* b, const xtb_scf_opts* o, const doub
   if (nblocks <= 0) return 0;
   const int lnao = o->mol_list ? o->list_nao_max : b->nao_max, lnsh = o->mol_list ? o->list_nsh_max : b->nsh_max,
             lnat = o->mol_list ? o->list_nat_max : b->nat_max;
-  int64_t smem = o->use_smem ? xtb_scf_smem_bytes_for(lnao, lnsh, lnat) : vec_smem_bytes(lnao, lnsh, lnat);
-  static int64_t configured[2] = {0, 0};
-  auto kern = o->use_smem ? k_scf<true> : k_scf<false>;
-  if (smem > configured[o->use_smem ? 1 : 0]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    configured[o->use_smem ? 1 : 0] = smem;
+  if (!o->use_smem) {
+    // global-memory variant: with at least ~1.5 molecules per SM two 512-thread CTAs per SM overlap one molecule's
+    // latency-bound sub-problems with the other's L2-bound passes; below that one 1024-thread CTA per SM is faster
+    static int n_sm = 0;
+    if (n_sm == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    }
+    if (2 * nblocks >= 3 * n_sm)
+      return xtb_scf_launch_global_512(b, o, nblocks, lnao, lnsh, lnat, S, H0, gamma, nel_ab, q0_at, (double*)work, q_orb, q_sh, q_at,
+                                       v_orb, e_atom, fenergy, emo, occ, iterations, status, P, W, (cudaStream_t)stream);
+    const int64_t smem = vec_smem_bytes(lnao, lnsh, lnat);
+    static int64_t configured_g = 0;
+    if (smem > configured_g) {
+      cudaError_t e = cudaFuncSetAttribute(k_scf<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      configured_g = smem;
+    }
+    k_scf<false><<<nblocks, NT, (size_t)smem, (cudaStream_t)stream>>>(*b, *o, S, H0, gamma, nel_ab, q0_at, (double*)work, q_orb, q_sh,
+                                                                      q_at, v_orb, e_atom, fenergy, emo, occ, iterations, status, P, W);
+    return launch_status();
   }
-  kern<<<nblocks, NT, (size_t)smem, (cudaStream_t)stream>>>(*b, *o, S, H0, gamma, nel_ab, q0_at, (double*)work, q_orb, q_sh, q_at,
-                                                           v_orb, e_atom, fenergy, emo, occ, iterations, status, P, W);
+  const int64_t smem = xtb_scf_smem_bytes_for(lnao, lnsh, lnat);
+  static int64_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_scf<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = smem;
+  }
+  k_scf<true><<<nblocks, NT, (size_t)smem, (cudaStream_t)stream>>>(*b, *o, S, H0, gamma, nel_ab, q0_at, (double*)work, q_orb, q_sh, q_at,
+                                                                   v_orb, e_atom, fenergy, emo, occ, iterations, status, P, W);
   return launch_status();
 }
+#endif  // XTB_NT
