@@ -32,8 +32,11 @@ NODISP_NOTE = ("D3(BJ) dispersion is computed on both arms with a SYNTHETIC refe
                "C6 data is third-party and unavailable offline): its cost is included, its energy is not physical")
 
 
+MOLECULE = "caffeine"
+
+
 def load_caffeine():
-    m = json.load(open(ROOT / "tests" / "golden" / "molecules.json"))["caffeine"]
+    m = json.load(open(ROOT / "tests" / "golden" / "molecules.json"))[MOLECULE]
     return np.array(m["numbers"]), np.array(m["positions"])
 
 
@@ -285,7 +288,7 @@ def run_ours(args) -> None:
     e2e = world * nb * args.steps / (ms_e2e * 1e-3)
 
     if rank == 0:
-        n = 76
+        n = int(calc.desc.nao[0])
         flops_per_launch = 10.0 * n**3 * iters_total / args.steps  # W_iter = 10 n^3 per SCF map evaluation
         scf_avg_ms = float(np.mean(scf_ms))
         peak = measure_fp64_peak(dev)
@@ -295,18 +298,18 @@ def run_ours(args) -> None:
             peaks = json.load(open(ROOT / "MEASURED_PEAKS.json"))
         except Exception:
             pass
-        bytes_per_launch = (48.0 * n * n + 8.0 * 48 * 48) * iters_total / args.steps
+        bytes_per_launch = (48.0 * n * n + 8.0 * float(calc.desc.nsh[0]) ** 2) * iters_total / args.steps
         cpu_v, cpu_dt = cpu_rate(6, 1)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"caffeine x{nb} conformers per GPU (C8H10N4O2, 24 atoms, nao 76), energy+forces (BASELINE config 2 geometry recipe)",
+            "config": {"workload": f"{MOLECULE} x{nb} conformers per GPU ({len(numbers_np)} atoms, nao {n}), energy+forces (BASELINE config 2 geometry recipe)",
                        "sigma_bohr": SIGMA, "l2": "a new conformer batch every step; per-step working set (S,H0,P,W ~190 MB) exceeds L2",
                        "opts": "dxtb defaults (EEQ guess, Anderson, x_atol 1e-4/1e-5, 300 K, D3(BJ) with synthetic table)", "note": NODISP_NOTE},
             "roofline": {"bound": "tensor", "pipe": "fp64 (DFMA/DMMA)", "kernel": "k_scf", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": 18.189056e6 / 148 * nb,  # DRAM bytes (read+write) of k_scf per molecule, profiles/r1_scf_r5_ncu_full.csv
+                         "traffic": 18.189056e6 / 148 * nb if MOLECULE == "caffeine" else None,  # DRAM bytes of k_scf per molecule, profiles/r1_scf_r5_ncu_full.csv
 
                          "peak_source": "cuBLAS DGEMM 4096^3 best-of-6 measured in this run (MEASURED_PEAKS.json has no fp64 entry)",
                          "scf_kernel_ms": scf_avg_ms, "scf_share_of_step": scf_avg_ms / (ms / args.steps),
@@ -330,7 +333,10 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nb", type=int, default=NB)
+    ap.add_argument("--molecule", default="caffeine", help="fixture geometry to make conformers of (default: BASELINE config 2)")
     args = ap.parse_args()
+    global MOLECULE
+    MOLECULE = args.molecule
     if args.impl == "reference":
         run_reference(args)
     else:
