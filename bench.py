@@ -300,6 +300,21 @@ def run_ours(args) -> None:
             pass
         bytes_per_launch = (48.0 * n * n + 8.0 * float(calc.desc.nsh[0]) ** 2) * iters_total / args.steps
         cpu_v, cpu_dt = cpu_rate(6, 1)
+        # parity gate beside the throughput number: a few molecules of the last batch against the oracle
+        from oracle import gfn1_oracle as O
+
+        p_last = devpos[nstep - 1].detach().requires_grad_(True)
+        e_last = calc.get_energy(p_last, chrg)
+        (g_last,) = torch.autograd.grad(e_last.sum(), p_last)
+        it_last = calc.get_iterations()
+        de = dg = 0.0
+        it_equal = True
+        idx = [0, nb // 3, nb - 1]
+        for i in idx:
+            r = O.singlepoint(numbers_np, host[nstep - 1][i].numpy(), 0.0, grad=True, d3_table=_d3_table())
+            de = max(de, abs(float(e_last[i]) - r.energy))
+            dg = max(dg, float(np.abs(g_last[i].cpu().numpy() - r.gradient).max()))
+            it_equal = it_equal and int(it_last[i]) == r.iterations
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -320,6 +335,8 @@ def run_ours(args) -> None:
             "gpu_launches": 22 * args.steps,
             "clocks": clocks,
             "scf_iterations_mean": (iters_total / args.steps - 2 * nb) / nb,
+            "parity": {"checked": len(idx), "max_abs_dE_Eh": de, "max_abs_dF_Eh_per_bohr": dg, "scf_iterations_equal": it_equal,
+                       "against": "oracle/gfn1_oracle.py (tolerances: 1e-9 Eh, 1e-7 Eh/bohr)"},
         }
         print(json.dumps(line), flush=True)
     if world > 1:
