@@ -157,6 +157,7 @@ class BatchDescriptor:
         ao_local = np.arange(nao_tot) - ao_off[ao_mol]
         self.nao_pad = int(nao.max())
         self.ao_index = dev(ao_mol * self.nao_pad + ao_local, i64)
+        self._ao_atom_local = (sh_atom[ao_sh_g]).astype(np.int64)  # molecule-local atom of every AO (ragged order)
 
         s = _abi.XtbBatch()
         s.nb, s.nat_tot, s.nsh_tot, s.nao_tot = self.nb, self.nat_tot, nsh_tot, nao_tot
@@ -189,6 +190,19 @@ class BatchDescriptor:
         out = ragged.new_zeros((self.nb * self.nat_pad, *ragged.shape[1:]))
         out.index_copy_(0, self.atom_index, ragged)
         out = out.reshape(self.nb, self.nat_pad, *ragged.shape[1:])
+        return out[0] if self.single else out
+
+    def scatter_matrices(self, ragged: torch.Tensor) -> torch.Tensor:
+        """(mat_total,) ragged nao x nao blocks -> (nb, nao_pad, nao_pad) zero padded (built lazily; not on the hot path)."""
+        if not hasattr(self, "_mat_index"):
+            nao = torch.from_numpy(self.nao).to(self.device)
+            mol = torch.repeat_interleave(torch.arange(self.nb, device=self.device), nao * nao)
+            local = torch.arange(int(self.mat_off[-1]), device=self.device) - torch.from_numpy(self.mat_off[:-1]).to(self.device)[mol]
+            n = nao[mol]
+            self._mat_index = mol * self.nao_pad * self.nao_pad + (local // n) * self.nao_pad + local % n
+        out = ragged.new_zeros((self.nb * self.nao_pad * self.nao_pad,))
+        out.index_copy_(0, self._mat_index, ragged)
+        out = out.reshape(self.nb, self.nao_pad, self.nao_pad)
         return out[0] if self.single else out
 
     def scatter_orbitals(self, ragged: torch.Tensor) -> torch.Tensor:

@@ -396,8 +396,12 @@ class GFN1Calculator:
         """Orbital-resolved Mulliken partial charges (calculators/types/abc.py:429-486)."""
         return self.desc.scatter_orbitals(self._ensure(positions, chrg, spin).q_orb)
 
-    def get_mulliken_charges(self, positions: torch.Tensor | None = None, chrg: Any = 0, spin: Any = None, **_: Any) -> torch.Tensor:
-        """Atom-resolved Mulliken charges (ihelp.reduce_orbital_to_atom of ``get_charges``)."""
+    def get_mulliken_charges(self, positions: torch.Tensor | None = None, chrg: Any = 0, spin: Any = None, **kw: Any) -> torch.Tensor:
+        """Same as ``get_charges`` (orbital-resolved), exactly like the reference (calculators/types/abc.py:488-495)."""
+        return self.get_charges(positions, chrg, spin, **kw)
+
+    def get_atomic_charges(self, positions: torch.Tensor | None = None, chrg: Any = 0, spin: Any = None, **_: Any) -> torch.Tensor:
+        """Atom-resolved Mulliken charges (``ihelp.reduce_orbital_to_atom`` of ``get_charges`` in the reference)."""
         return self.desc.scatter_atoms(self._ensure(positions, chrg, spin).q_at)
 
     def get_iterations(self, positions: torch.Tensor | None = None, chrg: Any = 0, spin: Any = None, **_: Any) -> torch.Tensor:
@@ -409,6 +413,44 @@ class GFN1Calculator:
 
     def get_occupation(self, positions: torch.Tensor | None = None, chrg: Any = 0, spin: Any = None, **_: Any) -> torch.Tensor:
         return self.desc.scatter_orbitals(self._ensure(positions, chrg, spin).occ)
+
+    def get_potential(self, positions: torch.Tensor | None = None, chrg: Any = 0, spin: Any = None, **_: Any) -> torch.Tensor:
+        """Orbital-resolved monopole potential of the final charges (calculators/types/abc.py:536-553)."""
+        return self.desc.scatter_orbitals(self._ensure(positions, chrg, spin).v_orb)
+
+    def get_overlap(self, positions: torch.Tensor | None = None, chrg: Any = 0, spin: Any = None, **_: Any) -> torch.Tensor:
+        """Overlap matrix, zero padded to (nb, nao, nao)."""
+        return self.desc.scatter_matrices(self._ensure(positions, chrg, spin).S)
+
+    def get_hcore(self, positions: torch.Tensor | None = None, chrg: Any = 0, spin: Any = None, **_: Any) -> torch.Tensor:
+        """Core Hamiltonian H0, zero padded to (nb, nao, nao)."""
+        return self.desc.scatter_matrices(self._ensure(positions, chrg, spin).H0)
+
+    def get_density(self, positions: torch.Tensor, chrg: Any = 0, spin: Any = None, **_: Any) -> torch.Tensor:
+        """Density matrix P = C diag(f) C^T of the final solve (calculators/types/abc.py:416-427)."""
+        p = positions.detach().clone().requires_grad_(True)  # the kernel writes P, W only when a gradient may follow
+        self.energy(p, chrg, spin)
+        return self.desc.scatter_matrices(self.cache["ws"].P)
+
+    def get_bond_orders(self, positions: torch.Tensor, chrg: Any = 0, spin: Any = None, **_: Any) -> torch.Tensor:
+        """Wiberg bond orders (wavefunction/wiberg.py:33-60): atom-reduced (PS) o (PS)^T with a zero diagonal."""
+        pmat = self.get_density(positions, chrg, spin)
+        smat = self.desc.scatter_matrices(self.cache["ws"].S)
+        ps = pmat @ smat
+        t = ps * ps.mT
+        d = self.desc
+        nb, nat = d.nb, d.nat_pad
+        ao_atom = torch.zeros(nb * d.nao_pad, dtype=torch.long, device=self.device)
+        at_local = torch.from_numpy(d._ao_atom_local).to(self.device)
+        ao_atom.index_copy_(0, d.ao_index, at_local)
+        onehot = torch.zeros((nb, d.nao_pad, nat), dtype=t.dtype, device=self.device)
+        valid = torch.zeros(nb * d.nao_pad, dtype=torch.bool, device=self.device)
+        valid[d.ao_index] = True
+        onehot.view(-1, nat)[torch.arange(nb * d.nao_pad, device=self.device)[valid], ao_atom[valid]] = 1.0
+        t = t if t.ndim == 3 else t[None]
+        wbo = onehot.mT @ t @ onehot
+        wbo.diagonal(dim1=-2, dim2=-1).fill_(0.0)
+        return wbo[0] if d.single else wbo
 
     def reset(self) -> None:
         self.cache = {}

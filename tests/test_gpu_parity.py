@@ -75,7 +75,7 @@ def test_padded_mixed_batch_matches_oracle(mols, mixed_run, i):
     assert abs(e[i] - r.energy) < E_TOL
     q = calc.get_charges()[i, :nao].cpu().numpy()
     assert np.abs(q - r.q_orb).max() < Q_TOL
-    qa = calc.get_mulliken_charges()[i, :nat].cpu().numpy()
+    qa = calc.get_atomic_charges()[i, :nat].cpu().numpy()
     assert np.abs(qa - r.q_at).max() < Q_TOL
     assert int(calc.get_iterations()[i]) == r.iterations
     assert np.abs(g[i, :nat] - r.gradient).max() < F_TOL
@@ -248,7 +248,7 @@ def test_full_size_conformer_batch_properties(mols):
     (g_again,) = torch.autograd.grad(e_again.sum(), p2)
     assert torch.equal(e_again, e) and torch.equal(g_again, g)
     # total charge conserved, forces sum to zero (translational invariance)
-    assert calc.get_mulliken_charges().sum(-1).abs().max() < 1e-9
+    assert calc.get_atomic_charges().sum(-1).abs().max() < 1e-9
     assert g.sum(1).abs().max() < 1e-8
     # rigid rotation + translation + permutation of the batch leave energies (and iteration counts) unchanged
     th = 0.7
@@ -273,7 +273,8 @@ def test_single_molecule_unbatched_shapes(mols):
     e = calc.get_energy(pos[0])
     assert e.shape == ()
     assert calc.get_charges().shape == (12,)
-    assert calc.get_mulliken_charges().shape == (5,)
+    assert calc.get_atomic_charges().shape == (5,)
+    assert calc.get_mulliken_charges().shape == (12,)  # orbital-resolved, as in the reference
     r = _oracle(mols, "CH4")
     assert abs(float(e) - r.energy) < E_TOL
 
@@ -397,3 +398,33 @@ def test_atomic_scf_energies_all_elements_gpu(energies):
         e = calc.get_energy(pos, chrg).cpu().numpy()
     ref = np.array([energies["scf_gfn1_tblite_atoms"][z - 1] for z in zs])
     assert np.abs(e - ref).max() < 1e-7
+
+
+def test_property_getters_match_oracle(mols):
+    """Result plumbing next to the path: density, overlap, hcore, potential, Wiberg bond orders."""
+    from dxtb_b200 import GFN1Calculator
+
+    dev = _dev()
+    names = ["H2O", "caffeine"]
+    numbers, pos, chrg = _pack(mols, names, dev)
+    calc = GFN1Calculator(numbers, opts=NODISP, device=dev, dtype=torch.float64)
+    P = calc.get_density(pos, chrg)
+    S, H0, v = calc.get_overlap(), calc.get_hcore(), calc.get_potential()
+    wbo = calc.get_bond_orders(pos, chrg)
+    for i, n in enumerate(names):
+        r = _oracle(mols, n, grad=True)
+        m = O.make_mol(mols[n]["numbers"])
+        k, nat = m.nao, m.nat
+        assert np.abs(P[i, :k, :k].cpu().numpy() - r.P).max() < 1e-8
+        assert np.abs(S[i, :k, :k].cpu().numpy() - r.S).max() < 1e-12
+        assert np.abs(H0[i, :k, :k].cpu().numpy() - r.H0).max() < 1e-12
+        assert np.abs(v[i, :k].cpu().numpy() - r.v_orb).max() < 1e-8
+        ps = r.P @ r.S
+        t = ps * ps.T
+        ref = np.zeros((nat, nat))
+        np.add.at(ref, (m.ao_atom[:, None], m.ao_atom[None, :]), t)
+        np.fill_diagonal(ref, 0.0)
+        assert np.abs(wbo[i, :nat, :nat].cpu().numpy() - ref).max() < 1e-7
+        assert float(P[i, k:, :].abs().max()) == 0.0 if P.shape[1] > k else True
+    # a C-H bond of caffeine has a Wiberg bond order close to one
+    assert 0.8 < float(wbo[1].max()) < 2.2
