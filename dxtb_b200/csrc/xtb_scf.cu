@@ -113,7 +113,7 @@ XTB_DEV int bp_index(int I, int J, int l) { return (l < JB ? I * JB : J * JB - J
 //   Per block round (round-robin over the ne/8 blocks, ne/16 disjoint block pairs):
 //   1. one thread group (3 warps) per block pair copies its 16x16 sub-matrix, runs the scalar rotations of the pair on the
 //      copy (warp-synchronous, no CTA barrier) and accumulates them into a 16x16 orthogonal Q;
-//   2. all warps apply the Q's with fp64 tensor-core MMAs: A <- A Q (columns), V <- V Q, then A <- Q^T A (rows).
+//   2. all warps apply the Q's with fp64 tensor-core MMAs: every 16x16 block of A two-sided (Q_P^T B Q_R), V <- V Q.
 //   A sweep = one "self" round (block pairs (0,1),(2,3),..: the 2 x 28 in-block index pairs) followed by the
 //   nblk-1 round-robin rounds in which the 64 cross pairs of a block pair are rotated: every index pair once.
 // Compared with rotating the full matrix after every scalar rotation round this moves A and V through
@@ -245,58 +245,92 @@ __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, in
         if (vt >= 32) q_update((nin - 1) & 1);  // rotations of the last inner round
       }
       __syncthreads();
-      // ---- 2a. column passes: A[:, idx] <- A[:, idx] Q and V[:, idx] <- V[:, idx] Q (m8 n16 k16 per unit) ----
+      // ---- 2. apply the rotations with fp64 tensor-core MMAs, one phase ---------------------------------------
+      //   A: every 16x16 block (pair P, pair R) is transformed on BOTH sides in registers, B' = Q_P^T (B Q_R): A is
+      //      read and written once per block round (the intermediate T = B Q_R is re-laid out from the accumulator
+      //      to the B-operand fragment layout with warp shuffles);
+      //   V: V[:, idx] <- V[:, idx] Q  (m8 n16 k16 units).
       {
-        const int nunit = 2 * ntile * nbp;
         const int g = lane >> 2, tg = lane & 3;
+        const int nfused = nbp * nbp, nunit = nfused + ntile * nbp;
         for (int u = warp; u < nunit; u += NW) {
-          const int which = u >= ntile * nbp;
-          const int rem = u - which * (ntile * nbp);
-          const int k = (int)__fdividef((float)rem + 0.5f, (float)ntile), rt = rem - k * ntile;
-          double* Mx = which ? V : A;
-          const int I = bij[2 * k], J = bij[2 * k + 1];
-          const double* Q = Qs + k * (JB2 * QLD);
-          double* row = Mx + (size_t)(rt * 8 + g) * ld;
-          double af[4];
+          if (u < nfused) {
+            const int P = (int)__fdividef((float)u + 0.5f, (float)nbp), R = u - P * nbp;
+            const int IP = bij[2 * P], JP = bij[2 * P + 1], IR = bij[2 * R], JR = bij[2 * R + 1];
+            const double* QP = Qs + P * (JB2 * QLD);
+            const double* QR = Qs + R * (JB2 * QLD);
+            // T = B Q_R
+            double t[2][2][2];
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) af[kk] = row[bp_index(I, J, 4 * kk + tg)];
-          double d[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+            for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
+              for (int nt = 0; nt < 2; ++nt) t[mt][nt][0] = t[mt][nt][1] = 0.0;
+            const double* r0 = A + (size_t)bp_index(IP, JP, g) * ld;
+            const double* r1 = A + (size_t)bp_index(IP, JP, 8 + g) * ld;
 #pragma unroll
-            for (int nt = 0; nt < 2; ++nt) dmma884(d[nt][0], d[nt][1], af[kk], Q[(4 * kk + tg) * QLD + 8 * nt + g]);
-          }
+            for (int kk = 0; kk < 4; ++kk) {
+              const int col = bp_index(IR, JR, 4 * kk + tg);
+              const double a0 = r0[col], a1 = r1[col];
+              const double b0 = QR[(4 * kk + tg) * QLD + g], b1 = QR[(4 * kk + tg) * QLD + 8 + g];
+              dmma884(t[0][0][0], t[0][0][1], a0, b0);
+              dmma884(t[0][1][0], t[0][1][1], a0, b1);
+              dmma884(t[1][0][0], t[1][0][1], a1, b0);
+              dmma884(t[1][1][0], t[1][1][1], a1, b1);
+            }
+            // B' = Q_P^T T:  A-operand [m][k] = Q_P[k][m];  B-operand [k][n] = T[k][n] fetched from the accumulator
+            // layout (row g', cols 2 tg', 2 tg' + 1) of lane 4 g' + tg' with g' = 4 (kk & 1) + tg, tg' = g >> 1.
+            double d[2][2][2];
 #pragma unroll
-          for (int nt = 0; nt < 2; ++nt) {
-            const int col = bp_index(I, J, 8 * nt + 2 * tg);  // 2*tg and 2*tg+1 are in the same 8-block: contiguous
-            row[col] = d[nt][0];
-            row[col + 1] = d[nt][1];
-          }
-        }
-      }
-      __syncthreads();
-      // ---- 2b. row pass: A[idx, :] <- Q^T A[idx, :] (m16 n8 k16 per unit) ------------------------------
-      {
-        const int nunit = ntile * nbp;
-        const int g = lane >> 2, tg = lane & 3;
-        for (int u = warp; u < nunit; u += NW) {
-          const int k = (int)__fdividef((float)u + 0.5f, (float)ntile), ct = u - k * ntile;
-          const int I = bij[2 * k], J = bij[2 * k + 1];
-          const double* Q = Qs + k * (JB2 * QLD);
-          double bf[4];
+            for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) bf[kk] = A[(size_t)bp_index(I, J, 4 * kk + tg) * ld + ct * 8 + g];
-          double d[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+              for (int nt = 0; nt < 2; ++nt) d[mt][nt][0] = d[mt][nt][1] = 0.0;
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
+            for (int kk = 0; kk < 4; ++kk) {
+              const int src = ((4 * (kk & 1) + tg) << 2) | (g >> 1);
+              double bfr[2];
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt) dmma884(d[mt][0], d[mt][1], Q[(4 * kk + tg) * QLD + 8 * mt + g], bf[kk]);
-          }
+              for (int nt = 0; nt < 2; ++nt) {
+                const double v0 = __shfl_sync(0xffffffffu, t[kk >> 1][nt][0], src);
+                const double v1 = __shfl_sync(0xffffffffu, t[kk >> 1][nt][1], src);
+                bfr[nt] = (g & 1) ? v1 : v0;
+              }
+              const double a0 = QP[(4 * kk + tg) * QLD + g], a1 = QP[(4 * kk + tg) * QLD + 8 + g];
+              dmma884(d[0][0][0], d[0][0][1], a0, bfr[0]);
+              dmma884(d[0][1][0], d[0][1][1], a0, bfr[1]);
+              dmma884(d[1][0][0], d[1][0][1], a1, bfr[0]);
+              dmma884(d[1][1][0], d[1][1][1], a1, bfr[1]);
+            }
 #pragma unroll
-          for (int mt = 0; mt < 2; ++mt) {
-            double* row = A + (size_t)bp_index(I, J, 8 * mt + g) * ld + ct * 8 + 2 * tg;
-            row[0] = d[mt][0];
-            row[1] = d[mt][1];
+            for (int mt = 0; mt < 2; ++mt) {
+              double* row = A + (size_t)bp_index(IP, JP, 8 * mt + g) * ld;
+#pragma unroll
+              for (int nt = 0; nt < 2; ++nt) {
+                const int col = bp_index(IR, JR, 8 * nt + 2 * tg);
+                row[col] = d[mt][nt][0];
+                row[col + 1] = d[mt][nt][1];
+              }
+            }
+          } else {
+            const int rem = u - nfused;
+            const int k = (int)__fdividef((float)rem + 0.5f, (float)ntile), rt = rem - k * ntile;
+            const int I = bij[2 * k], J = bij[2 * k + 1];
+            const double* Q = Qs + k * (JB2 * QLD);
+            double* row = V + (size_t)(rt * 8 + g) * ld;
+            double af[4];
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) af[kk] = row[bp_index(I, J, 4 * kk + tg)];
+            double d[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+              for (int nt = 0; nt < 2; ++nt) dmma884(d[nt][0], d[nt][1], af[kk], Q[(4 * kk + tg) * QLD + 8 * nt + g]);
+            }
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+              const int col = bp_index(I, J, 8 * nt + 2 * tg);  // 2*tg and 2*tg+1 are in the same 8-block: contiguous
+              row[col] = d[nt][0];
+              row[col + 1] = d[nt][1];
+            }
           }
         }
       }
