@@ -246,16 +246,20 @@ __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, in
       }
       __syncthreads();
       // ---- 2. apply the rotations with fp64 tensor-core MMAs, one phase ---------------------------------------
-      //   A: every 16x16 block (pair P, pair R) is transformed on BOTH sides in registers, B' = Q_P^T (B Q_R): A is
-      //      read and written once per block round (the intermediate T = B Q_R is re-laid out from the accumulator
+      //   A: every 16x16 block (pair P, pair R), P >= R, is transformed on BOTH sides in registers, B' = Q_P^T (B Q_R),
+      //      and mirrored into (R, P): A is read (half) and written once per block round (the intermediate T = B Q_R is re-laid out from the accumulator
       //      to the B-operand fragment layout with warp shuffles);
       //   V: V[:, idx] <- V[:, idx] Q  (m8 n16 k16 units).
       {
         const int g = lane >> 2, tg = lane & 3;
-        const int nfused = nbp * nbp, nunit = nfused + ntile * nbp;
+        // A is symmetric: only the blocks P >= R are computed, P > R blocks are mirrored into (R, P)
+        const int nfused = nbp * (nbp + 1) / 2, nunit = nfused + ntile * nbp;
         for (int u = warp; u < nunit; u += NW) {
           if (u < nfused) {
-            const int P = (int)__fdividef((float)u + 0.5f, (float)nbp), R = u - P * nbp;
+            int P = (int)((sqrtf(8.0f * (float)u + 1.0f) - 1.0f) * 0.5f);
+            while ((P + 1) * (P + 2) / 2 <= u) ++P;
+            while (P * (P + 1) / 2 > u) --P;
+            const int R = u - P * (P + 1) / 2;
             const int IP = bij[2 * P], JP = bij[2 * P + 1], IR = bij[2 * R], JR = bij[2 * R + 1];
             const double* QP = Qs + P * (JB2 * QLD);
             const double* QR = Qs + R * (JB2 * QLD);
@@ -308,6 +312,10 @@ __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, in
                 const int col = bp_index(IR, JR, 8 * nt + 2 * tg);
                 row[col] = d[mt][nt][0];
                 row[col + 1] = d[mt][nt][1];
+                if (P != R) {  // mirror: A[col][row]
+                  A[(size_t)col * ld + bp_index(IP, JP, 8 * mt + g)] = d[mt][nt][0];
+                  A[(size_t)(col + 1) * ld + bp_index(IP, JP, 8 * mt + g)] = d[mt][nt][1];
+                }
               }
             }
           } else {
