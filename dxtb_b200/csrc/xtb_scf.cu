@@ -18,14 +18,20 @@ using namespace xtb;
 
 namespace {
 
-// This translation unit is compiled twice (dxtb_b200/build.py):
-//   XTB_NT = 1024 (default): the shared-memory variant (1 CTA/SM) + the C entry points;
-//   XTB_NT = 512 : the global-memory variant, 2 CTAs/SM, so that one molecule's latency-bound sub-problem phase
-//                  overlaps the other's L2-bound tensor-core passes.  Exports only xtb_scf_launch_global_512().
+// This translation unit is compiled twice (dxtb_b200/build.py), both with 512 threads per CTA:
+//   primary   (XTB_MINB = 1): 1 CTA/SM, up to 128 registers per thread (no spills; measured 8 % faster than 1024
+//                             threads x 64 registers) -- the shared-memory variant, the global-memory variant for
+//                             small buckets, and the C entry points;
+//   secondary (-DXTB_SECONDARY -DXTB_MINB=2): the global-memory variant at 2 CTAs/SM (64 registers), so that one
+//                             molecule's latency-bound sub-problem phase overlaps the other's L2-bound tensor-core
+//                             passes.  Exports only xtb_scf_launch_global_512().
 #ifndef XTB_NT
-#define XTB_NT 1024
+#define XTB_NT 512
 #endif
-constexpr int NT = XTB_NT;  // threads per CTA (64 registers per thread in both builds)
+#ifndef XTB_MINB
+#define XTB_MINB 1
+#endif
+constexpr int NT = XTB_NT;  // threads per CTA
 
 struct Ctx {
   int n, ne, ld, ns, na, np;
@@ -95,9 +101,9 @@ __device__ void gemm_tn(int ne, int K, const double* __restrict__ L, const doubl
   __syncthreads();
 }
 
-// named barrier for a thread group of 3 warps (ids 1..10; id 0 is __syncthreads)
+// named barrier for a thread group of 3 warps (ids 1..NGRP; id 0 is __syncthreads)
 constexpr int GS = 96;            // threads per sub-problem group
-constexpr int NGRP = NT / GS;     // 10 groups (the last two warps of the CTA idle during the sub-problems)
+constexpr int NGRP = NT / GS;     // 5 groups of 3 warps (the 16th warp idles during the sub-problems)
 XTB_DEV void group_bar(int grp) { asm volatile("bar.sync %0, 96;" ::"r"(grp + 1) : "memory"); }
 
 constexpr int JB = 8;        // Jacobi block size
@@ -721,7 +727,7 @@ __device__ bool mix(Ctx& c, Mixer& mx, const xtb_scf_opts& o, double* sm_theta) 
 }
 
 template <bool SM>
-__global__ void __launch_bounds__(NT, 1024 / NT)
+__global__ void __launch_bounds__(NT, XTB_MINB)
 k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, const double* __restrict__ H0,
       const double* __restrict__ gamma, const double* __restrict__ nel_ab, const double* __restrict__ q0_at, double* __restrict__ work,
       double* __restrict__ q_orb, double* __restrict__ q_sh, double* __restrict__ q_at, double* __restrict__ v_orb,
@@ -894,7 +900,7 @@ int64_t vec_smem_bytes(int64_t nao_max, int64_t nsx, int64_t nax) {
 
 }  // namespace
 
-#if XTB_NT == 512
+#ifdef XTB_SECONDARY
 // secondary build: launcher of the 2-CTA/SM global-memory variant
 int xtb_scf_launch_global_512(const xtb_batch* b, const xtb_scf_opts* o, int nblocks, int lnao, int lnsh, int lnat, const double* S,
                               const double* H0, const double* gamma, const double* nel_ab, const double* q0_at, double* work,
