@@ -135,12 +135,13 @@ def run_reference(args) -> None:
 
 
 # --------------------------------------------------------------------------------------------------
-class ClockSampler(threading.Thread):
-    """SM clock / throttle-reason sampler (NVML in-process; falls back to nvidia-smi)."""
+class ClockSampler:
+    """SM clock / throttle-reason sampler.  Sampled from the timing loop itself (NVML, ~20 us per call) right after
+    a step has been enqueued, i.e. while the GPU is still executing it: a polling thread would fight the timing
+    loop for the GIL and distort the measurement."""
 
     def __init__(self, index: int):
-        super().__init__(daemon=True)
-        self.index, self.samples, self.reasons, self._halt = index, [], set(), threading.Event()
+        self.index, self.samples, self.reasons = index, [], set()
         self.max_mhz = None
         self._nvml = None
         try:
@@ -153,42 +154,38 @@ class ClockSampler(threading.Thread):
         except Exception:
             self._nvml = None
 
-    def _sample_nvml(self):
-        nv = self._nvml
-        self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
-        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
-        for name, bit in (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown),
-                          ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
-                          ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown),
-                          ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap)):
-            if r & bit:
-                self.reasons.add(name)
-
-    def _sample_smi(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                             capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-        self.samples.append(float(out[0]))
-        self.max_mhz = float(out[1])
-        for n, v in zip(names, out[2:]):
-            if v.strip().lower().startswith("active"):
-                self.reasons.add(n)
-
-    def run(self):
-        while not self._halt.is_set():
-            try:
-                self._sample_nvml() if self._nvml is not None else self._sample_smi()
-            except Exception:
-                pass
-            self._halt.wait(0.1 if self._nvml is not None else 0.5)
+    def sample(self):
+        t0 = time.perf_counter()
+        try:
+            if self._nvml is not None:
+                nv = self._nvml
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for name, bit in (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown),
+                                  ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                                  ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown),
+                                  ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap)):
+                    if r & bit:
+                        self.reasons.add(name)
+            else:
+                q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                     "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+        except Exception:
+            pass
+        self.cost_ms = getattr(self, "cost_ms", 0.0) + 1e3 * (time.perf_counter() - t0)
 
     def stop(self):
-        self._halt.set()
-        self.join(timeout=3)
         med = float(np.median(self.samples)) if self.samples else None
-        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples),
+                "query_ms_total": round(getattr(self, "cost_ms", 0.0), 2)}
 
 
 def measure_fp64_peak(dev) -> float:
@@ -249,17 +246,20 @@ def run_ours(args) -> None:
         step(devpos[s])
     calc.scf_events = []
     sampler = ClockSampler(local)
-    sampler.start()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    iters_total = 0
+    iter_tensors = []
     for s in range(args.warmup, nstep):
         step(devpos[s])
-        iters_total += int(calc.get_iterations().sum()) + 2 * nb  # + final solve + S orthonormaliser
+        if s == args.warmup + args.steps // 2:
+            sampler.sample()  # one NVML query inside the timed region (each costs milliseconds of driver time)
+        iter_tensors.append(calc.get_iterations())
     e1.record()
+    sampler.sample()  # the backward kernels of the last step are still running
     barrier()
     clocks = sampler.stop()
+    iters_total = sum(int(t.sum()) for t in iter_tensors) + 2 * nb * args.steps  # + final solve + start basis per molecule
     ms = e0.elapsed_time(e1)
     scf_ms = [a.elapsed_time(b) for a, b in calc.scf_events]
     calc.scf_events = None
@@ -324,7 +324,7 @@ def run_ours(args) -> None:
                        "opts": "dxtb defaults (EEQ guess, Anderson, x_atol 1e-4/1e-5, 300 K, D3(BJ) with synthetic table)", "note": NODISP_NOTE},
             "roofline": {"bound": "tensor", "pipe": "fp64 (DFMA/DMMA)", "kernel": "k_scf", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": 18.189056e6 / 148 * nb if MOLECULE == "caffeine" else None,  # DRAM bytes of k_scf per molecule, profiles/r1_scf_r5_ncu_full.csv
+                         "traffic": 17.853184e6 / 148 * nb if MOLECULE == "caffeine" else None,  # DRAM bytes of k_scf per molecule, profiles/r1_scf_r6_ncu_full.csv
 
                          "peak_source": "cuBLAS DGEMM 4096^3 best-of-6 measured in this run (MEASURED_PEAKS.json has no fp64 entry)",
                          "scf_kernel_ms": scf_avg_ms, "scf_share_of_step": scf_avg_ms / (ms / args.steps),
