@@ -58,6 +58,11 @@ _IGNORED_OPTS = {"cache_enabled", "cache_charges", "cache_iterations", "cache_de
                  "verbosity", "batch_mode", "damp_dynamic", "damp_dynamic_factor", "log_level", "json"}
 
 _SMEM_LIMIT = 227 * 1024  # per-CTA opt-in shared memory on sm_100
+_SMEM_2CTA = 113 * 1024   # two CTAs per SM (228 KB per SM, 1 KB reserved per CTA); XTB_SMEM_2CTA in include/xtb_b200.h
+
+
+def _sm_count(device: torch.device) -> int:
+    return int(torch.cuda.get_device_properties(device).multi_processor_count)
 
 
 def _stream_ptr(device: torch.device) -> int:
@@ -80,7 +85,7 @@ class _Workspace:
         self.q_sh, self.q_at, self.e_atom = z(d.nsh_tot), z(d.nat_tot), z(d.nat_tot)
         self.fenergy = z(d.nb)
         self.iterations, self.status = z(d.nb, torch.int32), z(d.nb, torch.int32)
-        scf_opts.use_smem = 0 if need_global else 1
+        scf_opts.use_smem = 0 if need_global else 1  # sizes the matrix workspace of variants 0 and 2
         nbytes = _abi.lib().xtb_scf_workspace_bytes(d.ptr, _abi.C.addressof(scf_opts))
         self.work = torch.empty(int(nbytes) // 8 + 1, dtype=f64, device=dev)
         if want_density:
@@ -101,7 +106,7 @@ class _SinglePoint(torch.autograd.Function):
         need_grad = bool(ctx.needs_input_grad[0])
         pos = d.gather_atoms(positions.detach())
         o = calc._scf_struct(want_density=need_grad)
-        need_global = calc._use_smem_override == 0 or any(not bk["use_smem"] for bk in calc._buckets)
+        need_global = calc._use_smem_override in (0, 2) or any(bk["use_smem"] in (0, 2) for bk in calc._buckets)
         ws = _Workspace(d, need_grad, o, need_global)
         excl = calc._exclude
 
@@ -121,6 +126,9 @@ class _SinglePoint(torch.autograd.Function):
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record(torch.cuda.current_stream(d.device))
         for bk in calc._buckets:
+            if bk["use_smem"] == 3:
+                calc._run_large(bk, o, ws, nel_ab, need_grad, st)
+                continue
             o.use_smem = bk["use_smem"] if calc._use_smem_override is None else calc._use_smem_override
             o.mol_list, o.list_len = bk["list"].data_ptr(), bk["len"]
             o.list_nao_max, o.list_nsh_max, o.list_nat_max = bk["nao"], bk["nsh"], bk["nat"]
@@ -252,8 +260,9 @@ class GFN1Calculator:
         self.cache: dict[str, Any] = {}
         self.scf_events: list | None = None
         self._use_smem_override: int | None = None  # tests: force the global-memory variant
+        self._prefer_hybrid = os.environ.get("DXTB_B200_PREFER_HYBRID", "0") != "0"
+        self._large_min_nao = int(os.environ.get("DXTB_B200_LARGE_MIN_NAO", "1000000"))
         self._buckets = self._make_buckets()
-        self._use_smem = 1 if all(bk["use_smem"] for bk in self._buckets) else 0
 
     # ------------------------------------------------------------------------------------------
     def _make_buckets(self) -> list[dict[str, Any]]:
@@ -263,21 +272,28 @@ class GFN1Calculator:
         import numpy as np
 
         d, lib = self.desc, _abi.lib()
-        fits = np.array([lib.xtb_scf_smem_bytes_for(int(n), int(s), int(a)) <= _SMEM_LIMIT
-                         for n, s, a in zip(d.nao, d.nsh, d.nat)]) if d.nb <= 4096 else None
-        if fits is None:  # vectorised bound for very large batches: the layout grows monotonically with nao
-            nao_cap = max([n for n in range(1, 200) if lib.xtb_scf_smem_bytes_for(n, 3 * n, n) <= _SMEM_LIMIT] or [0])
-            fits = d.nao <= nao_cap
-        big = int(d.nao.max())
-        if lib.xtb_scf_smem_bytes_for(big, int(d.nsh.max()), int(d.nat.max())) - 3 * ((big + 15) // 16 * 16) * ((big + 15) // 16 * 16 + 4) * 8 > _SMEM_LIMIT:
-            raise NotImplementedError(
-                f"a molecule with {big} atomic orbitals exceeds the one-CTA-per-molecule SCF kernel (its per-orbital "
-                "vectors and Jacobi scratch no longer fit in shared memory); the multi-CTA eigensolver for such systems "
-                "(BASELINE config 4) is not built yet"
-            )
+        if d.nb <= 4096:
+            need = np.array([[lib.xtb_scf_smem_bytes_mode(mode, int(n), int(s), int(a)) for mode in (0, 1, 2)]
+                             for n, s, a in zip(d.nao, d.nsh, d.nat)], dtype=np.int64)
+        else:  # bound for very large batches: the layout grows monotonically with nao (at most 3 shells / AO per atom)
+            tab = np.array([[lib.xtb_scf_smem_bytes_mode(mode, n, 3 * n, n) for mode in (0, 1, 2)] for n in range(0, int(d.nao.max()) + 1)],
+                           dtype=np.int64)
+            need = tab[d.nao]
+        # kernel variant per molecule (use_smem field of xtb_scf_opts): 1 = all three matrices in shared memory, 2 = hybrid
+        # (only the Fock / A / density buffer in shared memory, C and the GEMM temporary in the L2-resident workspace),
+        # 0 = everything in the workspace.  Molecules small enough for two hybrid CTAs per SM prefer that to variant 1
+        # when the batch is large enough to fill the device twice (the C side picks 1 or 2 CTAs per SM).
+        # 3 = large-system path: the molecule runs alone on the whole device (xtb_scf_run_large) when the per-orbital vectors of
+        # the one-CTA kernel no longer fit in shared memory, or from `large_min_nao` atomic orbitals on
+        mode = np.where(need[:, 1] <= _SMEM_LIMIT, 1, np.where(need[:, 2] <= _SMEM_LIMIT, 2, 0))
+        mode[(need[:, 0] > _SMEM_LIMIT) | (d.nao >= self._large_min_nao)] = 3
+        if self._prefer_hybrid:
+            two = (need[:, 2] <= _SMEM_2CTA) & (mode == 1)
+            if 2 * int(two.sum()) >= 3 * _sm_count(self.device):
+                mode[two] = 2
         buckets = []
-        for use_smem, sel in ((0, ~fits), (1, fits)):
-            idx = np.flatnonzero(sel)
+        for use_smem in (3, 0, 2, 1):
+            idx = np.flatnonzero(mode == use_smem)
             if idx.size == 0:
                 continue
             idx = idx[np.argsort(-d.nao[idx], kind="stable")]
@@ -285,8 +301,33 @@ class GFN1Calculator:
                 "use_smem": use_smem,
                 "list": torch.from_numpy(idx.astype(np.int32)).to(self.device),
                 "len": int(idx.size), "nao": int(d.nao[idx].max()), "nsh": int(d.nsh[idx].max()), "nat": int(d.nat[idx].max()),
+                "mols": [int(i) for i in idx] if use_smem == 3 else None,
             })
         return buckets
+
+    def _run_large(self, bk, o, ws, nel_ab, need_grad: bool, st: int) -> None:
+        """Molecules of the large-system bucket, one after the other on the whole device (xtb_scf_run_large)."""
+        d, lib = self.desc, _abi.lib()
+        nbytes = max(int(lib.xtb_scf_large_workspace_bytes(int(d.nao[m]), int(d.nsh[m]), int(d.nat[m]), int(o.generations)))
+                     for m in bk["mols"])
+        work = torch.empty(nbytes // 8 + 1, dtype=torch.float64, device=d.device)
+        o.mol_list, o.list_len = None, 0
+        for m in bk["mols"]:
+            _abi.check(
+                lib.xtb_scf_run_large(
+                    d.ptr, _abi.C.addressof(o), int(m), int(d.nao[m]), int(d.nsh[m]), int(d.nat[m]), ws.S.data_ptr(), ws.H0.data_ptr(),
+                    ws.gamma.data_ptr(), nel_ab.data_ptr(), ws.q0_at.data_ptr(), work.data_ptr(), ws.q_orb.data_ptr(),
+                    ws.q_sh.data_ptr(), ws.q_at.data_ptr(), ws.v_orb.data_ptr(), ws.e_atom.data_ptr(), ws.fenergy.data_ptr(),
+                    ws.emo.data_ptr(), ws.occ.data_ptr(), ws.iterations.data_ptr(), ws.status.data_ptr(),
+                    ws.P.data_ptr() if need_grad else None, ws.W.data_ptr() if need_grad else None, int(d.mat_off[m]), st,
+                ),
+                "xtb_scf_run_large",
+            )
+
+    @property
+    def _variants(self) -> list[int]:
+        """SCF kernel variants (xtb_scf_opts.use_smem values) this batch launches."""
+        return sorted({bk["use_smem"] for bk in self._buckets})
 
     def _scf_struct(self, want_density: bool) -> _abi.XtbScfOpts:
         o, s = self.opts, _abi.XtbScfOpts()

@@ -12,535 +12,47 @@
 // Matrices (C, A/F, X/P) live in shared memory when 3*ne*ld*8 B fit (nao <= ~96), otherwise in a global
 // workspace (L2-resident for the active CTAs).  Leading dimension ld is odd so that both row and column
 // accesses of fp64 data are bank-conflict free.
-#include "xtb_common.cuh"
-
-using namespace xtb;
+#include "xtb_scf_core.cuh"
 
 namespace {
 
-// This translation unit is compiled twice (dxtb_b200/build.py), both with 512 threads per CTA:
-//   primary   (XTB_MINB = 1): 1 CTA/SM, up to 128 registers per thread (no spills; measured 8 % faster than 1024
-//                             threads x 64 registers) -- the shared-memory variant, the global-memory variant for
-//                             small buckets, and the C entry points;
-//   secondary (-DXTB_SECONDARY -DXTB_MINB=2): the global-memory variant at 2 CTAs/SM (64 registers), so that one
-//                             molecule's latency-bound sub-problem phase overlaps the other's L2-bound tensor-core
-//                             passes.  Exports only xtb_scf_launch_global_512().
-#ifndef XTB_NT
-#define XTB_NT 512
-#endif
-#ifndef XTB_MINB
-#define XTB_MINB 1
-#endif
-constexpr int NT = XTB_NT;  // threads per CTA
-
-struct Ctx {
-  int n, ne, ld, ns, na, np;
-  int o0, s0, a0;
-  double *C, *A, *X;             // ne x ld matrices (shared or global)
-  const double *S, *H0, *gam;    // global, n x n / ns x ns
-  double *eps, *srt, *focc, *v, *vnew, *q, *n0, *eorb, *qsh, *vsh, *qat, *red, *cs;
-  int *pp, *qq, *occl;
-  double *jq, *jm, *jr;          // block-Jacobi scratch: accumulated rotations / sub-problem copies / rotation params
-  bool smem;                     // matrices live in shared memory
-  const int *ao_sh, *sh_atom, *at_sh0, *at_nsh, *sh_ao, *sh_l;
-  const double* gam3;            // at_par base (stride XTB_ATPAR)
-  double *xh, *fh;               // Anderson history [gen+1][n] (global)
-  int status;
-  int sweeps;                    // diagnostic: total Jacobi sweeps of this molecule
-};
-
-// Address-space hint: lets the compiler emit LDS/STS (32-bit addressing) instead of generic LD/ST.
-#define XTB_ASSUME_SHARED(ptr) __builtin_assume(__isShared(ptr))
-
-// fp64 tensor-core MMA, D(8x8) += A(8x4, row) * B(4x8, col).  Lane l holds A[l/4][l%4], B[l%4][l/4],
-// D[l/4][2*(l%4) + {0,1}].  SASS: DMMA.8x8x4.
-XTB_DEV void dmma884(double& d0, double& d1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
-}
-
-// Out[i][j] = sum_{k<K} L[k*ld+i] * R[k*ld+j], i,j < ne (ne % 16 == 0), on the fp64 tensor cores:
-// one warp per 16x16 output tile (2x2 DMMA tiles), K consumed 4 at a time.  With ld == 4 (mod 16) both
-// fragment loads (4 consecutive k rows x 8 consecutive columns per half-warp) are bank-conflict free.
-template <bool SM>
-__device__ void gemm_tn(int ne, int K, const double* __restrict__ L, const double* __restrict__ R, int ld, double* __restrict__ Out,
-                        int ldo, int nout) {
-  if (SM) { XTB_ASSUME_SHARED(L); XTB_ASSUME_SHARED(R); }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int g = lane >> 2, tg = lane & 3;
-  const int nt = ne >> 4;
-  for (int t = warp; t < nt * nt; t += NT / 32) {
-    const int ti = t / nt, tj = t - ti * nt;
-    const int i0 = ti << 4, j0 = tj << 4;
-    double d[2][2][2];
-#pragma unroll
-    for (int a = 0; a < 2; ++a)
-#pragma unroll
-      for (int b = 0; b < 2; ++b) d[a][b][0] = d[a][b][1] = 0.0;
-    for (int k0 = 0; k0 < K; k0 += 4) {
-      const bool kv = k0 + tg < K;
-      const double* lr = L + (size_t)(k0 + tg) * ld + i0 + g;
-      const double* rr = R + (size_t)(k0 + tg) * ld + j0 + g;
-      const double a0 = kv ? lr[0] : 0.0, a1 = kv ? lr[8] : 0.0;
-      const double b0 = kv ? rr[0] : 0.0, b1 = kv ? rr[8] : 0.0;
-      dmma884(d[0][0][0], d[0][0][1], a0, b0);
-      dmma884(d[0][1][0], d[0][1][1], a0, b1);
-      dmma884(d[1][0][0], d[1][0][1], a1, b0);
-      dmma884(d[1][1][0], d[1][1][1], a1, b1);
-    }
-#pragma unroll
-    for (int a = 0; a < 2; ++a)
-#pragma unroll
-      for (int b = 0; b < 2; ++b) {
-        const int i = i0 + 8 * a + g, j = j0 + 8 * b + 2 * tg;
-        if (i < nout) {
-          if (j < nout) Out[(size_t)i * ldo + j] = d[a][b][0];
-          if (j + 1 < nout) Out[(size_t)i * ldo + j + 1] = d[a][b][1];
-        }
-      }
-  }
-  __syncthreads();
-}
-
-// named barrier for a thread group of 3 warps (ids 1..NGRP; id 0 is __syncthreads)
-constexpr int GS = 96;            // threads per sub-problem group
-constexpr int NGRP = NT / GS;     // 5 groups of 3 warps (the 16th warp idles during the sub-problems)
-XTB_DEV void group_bar(int grp) { asm volatile("bar.sync %0, 96;" ::"r"(grp + 1) : "memory"); }
-
-constexpr int JB = 8;        // Jacobi block size
-constexpr int JB2 = 2 * JB;  // indices of a block pair
-constexpr int MLD = 24;      // leading dimension of the 16x16 sub-problem copy (== 8 mod 16: conflict-free 2x2-block updates)
-constexpr int QLD = 20;      // leading dimension of the accumulated 16x16 rotation (== 4 mod 16: conflict-free DMMA fragments)
-
-// Global index of local index l (0..15) of block pair (I, J).
-XTB_DEV int bp_index(int I, int J, int l) { return (l < JB ? I * JB : J * JB - JB) + l; }
-
-// BLOCKED two-sided Jacobi (block size 8) on the symmetric ne x ne matrix A (ne % 16 == 0), accumulating
-// the transformation into the columns of V (ne rows).
-//   Per block round (round-robin over the ne/8 blocks, ne/16 disjoint block pairs):
-//   1. one thread group (3 warps) per block pair copies its 16x16 sub-matrix, runs the scalar rotations of the pair on the
-//      copy (warp-synchronous, no CTA barrier) and accumulates them into a 16x16 orthogonal Q;
-//   2. all warps apply the Q's with fp64 tensor-core MMAs: every 16x16 block of A two-sided (Q_P^T B Q_R), V <- V Q.
-//   A sweep = one "self" round (block pairs (0,1),(2,3),..: the 2 x 28 in-block index pairs) followed by the
-//   nblk-1 round-robin rounds in which the 64 cross pairs of a block pair are rotated: every index pair once.
-// Compared with rotating the full matrix after every scalar rotation round this moves A and V through
-// shared memory ~10x instead of ~80x per sweep.  Returns the number of sweeps, or -sweeps if not converged.
-template <bool SM>
-__device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, int nrow, double tol, int maxsweeps) {
-  const int ne = c.ne, ld = c.ld;
-  const int nblk = ne / JB, nbp = nblk / 2, ntile = ne / 8;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int NW = NT / 32;
-  constexpr int NG = NGRP;  // thread groups of 3 warps for the sub-problems
-  // group g = warps 3g..3g+2: warp 0 of a group computes the rotations (8 lanes) and, with warp 1, updates the
-  // sub-matrix; warps 1 and 2 accumulate Q.  Since 3g mod 4 cycles through the SM sub-partitions, the fp64-heavy
-  // rotation chains of concurrently running groups do not pile up on one sub-partition.
-  const int grp = warp / 3, gt = (int)threadIdx.x - GS * grp;
-  const int vt = gt;
-  double* Qs = c.jq;  // [nbp][16][QLD]
-  double* Ms = c.jm;  // [NG][16][MLD]  sub-problem copy of the group
-  double* Rs = c.jr;  // [NG][48] rotation parameters (double buffered)
-  int* bij = c.pp;    // [nbp][2] blocks of the pairs of this round
-  XTB_ASSUME_SHARED(bij);
-  XTB_ASSUME_SHARED(Qs); XTB_ASSUME_SHARED(Ms); XTB_ASSUME_SHARED(Rs);
-  if (SM) { XTB_ASSUME_SHARED(A); XTB_ASSUME_SHARED(V); }
-  (void)nrow;
-  int sweep = 0;
-  for (;;) {
-    double off = 0.0;
-    for (int i = warp; i < ne; i += NW) {
-      const double* row = A + (size_t)i * ld;
-      for (int j = lane; j < ne; j += 32)
-        if (i != j) off = fmax(off, fabs(row[j]));
-    }
-    off = block_max(off, c.red);
-    if (off <= tol) return sweep;
-    if (sweep >= maxsweeps) return -sweep;
-    ++sweep;
-    for (int r = -1; r < nblk - 1; ++r) {
-      // ---- 1. sub-problems: a group of 4 warps (128 threads, named barrier) owns a block pair ----------
-      for (int w = grp; w < nbp && grp < NG; w += NG) {
-        int I, J;
-        if (r < 0) { I = 2 * w; J = 2 * w + 1; }
-        else if (w == 0) { I = r; J = nblk - 1; }
-        else {
-          I = (r + w) % (nblk - 1);
-          J = (r - w + 2 * (nblk - 1)) % (nblk - 1);
-        }
-        if (I > J) { const int t = I; I = J; J = t; }
-        double* M = Ms + grp * (JB2 * MLD);
-        double* Q = Qs + w * (JB2 * QLD);
-        double2* rcs = reinterpret_cast<double2*>(Rs + grp * 48);   // [2][8] (c, s), double buffered
-        int2* rpq = reinterpret_cast<int2*>(Rs + grp * 48 + 32);    // [2][8] (p, q)
-        if (gt == 0) { bij[2 * w] = I; bij[2 * w + 1] = J; }
-        for (int e = gt; e < JB2 * JB2; e += GS) {
-          const int rr = e >> 4, cc = e & 15;
-          M[rr * MLD + cc] = A[(size_t)bp_index(I, J, rr) * ld + bp_index(I, J, cc)];
-          Q[rr * QLD + cc] = (rr == cc) ? 1.0 : 0.0;
-        }
-        group_bar(grp);
-        const int nin = (r < 0) ? JB - 1 : JB;
-        // Software pipeline: between the two group barriers of inner round t, warp 0 computes the 8 rotations of
-        // round t while warps 1..3 apply the rotations of round t-1 to Q (Q is off the critical path
-        // rot(t) -> M(t) -> rot(t+1)); rotation parameters are double buffered.
-        auto q_update = [&](int buf) {
-          // 128 items (16 rows x 8 pairs) on 64 threads; every half-warp covers 4 rows x 4 pairs (conflict-free)
-          for (int it = vt - 32; it < 128; it += GS - 32) {
-            const int qk = (it & 3) + 4 * ((it >> 4) & 1), qi = ((it >> 2) & 3) + 4 * (it >> 5);
-            const int2 pqq = rpq[8 * buf + qk];
-            const double2 csq = rcs[8 * buf + qk];
-            const double vp = Q[qi * QLD + pqq.x], vq = Q[qi * QLD + pqq.y];
-            Q[qi * QLD + pqq.x] = csq.x * vp - csq.y * vq;
-            Q[qi * QLD + pqq.y] = csq.y * vp + csq.x * vq;
-          }
-        };
-        for (int t = 0; t < nin; ++t) {
-          const int buf = t & 1;
-          if (vt < 8) {
-            // the 8 disjoint index pairs of this inner round
-            const int l = vt;
-            int p, q;
-            if (r < 0) {
-              // self round: the 28 in-block pairs of block I (l < 4) and of block J (l >= 4), round-robin on 8
-              const int k = l & 3, h = (l >> 2) * JB;
-              if (k == 0) { p = t; q = JB - 1; }
-              else { p = t + k; if (p >= JB - 1) p -= JB - 1; q = t - k; if (q < 0) q += JB - 1; }
-              if (p > q) { const int x = p; p = q; q = x; }
-              p += h; q += h;
-            } else {
-              p = l; q = JB + ((l + t) & (JB - 1));
-            }
-            const double app = M[p * MLD + p], aqq = M[q * MLD + q], apq = M[p * MLD + q];
-            double cs_ = 1.0, sn = 0.0;
-            // Small-angle Jacobi rotation from the double-angle identities (two dependent rsqrt instead of three
-            // divisions/square roots; rsqrt is a 62-cycle chain on sm_100a, tools/microbench/lat.cu):
-            //   r = sqrt(d^2 + 4 apq^2), cos 2t = |d| / r, sin 2t = sign(d) 2 apq / r,
-            //   c^2 = (1 + cos 2t) / 2,  c = c^2 rsqrt(c^2),  s = sin 2t / (2 c).
-            // s has no cancellation for small angles; c^2 + s^2 = 1 holds to a few ulp.
-            const double d = aqq - app;
-            const double x = d * d + 4.0 * apq * apq;
-            if (x > 1e-280) {
-              const double ir = rsqrt(x);
-              const double c2 = 0.5 + 0.5 * fabs(d) * ir;
-              const double ic = rsqrt(c2);
-              cs_ = c2 * ic;
-              sn = copysign(apq * ir, d * apq) * ic;
-            }
-            rcs[8 * buf + l] = make_double2(cs_, sn);
-            rpq[8 * buf + l] = make_int2(p, q);
-          } else if (vt >= 32 && t > 0) {
-            q_update(buf ^ 1);
-          }
-          group_bar(grp);
-          if (vt < 64) {
-            // M <- J^T M J on the 8x8 grid of 2x2 blocks: thread -> (kp, kq) = (vt >> 3, vt & 7)
-            const int kp = vt >> 3, kq = vt & 7;
-            const int2 pq1 = rpq[8 * buf + kp], pq2 = rpq[8 * buf + kq];
-            const double2 cs1 = rcs[8 * buf + kp], cs2 = rcs[8 * buf + kq];
-            const int p1 = pq1.x, q1 = pq1.y, p2 = pq2.x, q2 = pq2.y;
-            const double c1 = cs1.x, s1 = cs1.y, c2 = cs2.x, s2 = cs2.y;
-            const double a00 = M[p1 * MLD + p2], a01 = M[p1 * MLD + q2], a10 = M[q1 * MLD + p2], a11 = M[q1 * MLD + q2];
-            const double x00 = c1 * a00 - s1 * a10, x01 = c1 * a01 - s1 * a11;
-            const double x10 = s1 * a00 + c1 * a10, x11 = s1 * a01 + c1 * a11;
-            double y00 = c2 * x00 - s2 * x01, y01 = s2 * x00 + c2 * x01;
-            double y10 = c2 * x10 - s2 * x11, y11 = s2 * x10 + c2 * x11;
-            if (kp == kq) { y01 = 0.0; y10 = 0.0; }
-            M[p1 * MLD + p2] = y00; M[p1 * MLD + q2] = y01; M[q1 * MLD + p2] = y10; M[q1 * MLD + q2] = y11;
-          }
-          group_bar(grp);
-        }
-        if (vt >= 32) q_update((nin - 1) & 1);  // rotations of the last inner round
-      }
-      __syncthreads();
-      // ---- 2. apply the rotations with fp64 tensor-core MMAs, one phase ---------------------------------------
-      //   A: every 16x16 block (pair P, pair R), P >= R, is transformed on BOTH sides in registers, B' = Q_P^T (B Q_R),
-      //      and mirrored into (R, P): A is read (half) and written once per block round (the intermediate T = B Q_R is re-laid out from the accumulator
-      //      to the B-operand fragment layout with warp shuffles);
-      //   V: V[:, idx] <- V[:, idx] Q  (m8 n16 k16 units).
-      {
-        const int g = lane >> 2, tg = lane & 3;
-        // A is symmetric: only the blocks P >= R are computed, P > R blocks are mirrored into (R, P)
-        const int nfused = nbp * (nbp + 1) / 2, nunit = nfused + ntile * nbp;
-        for (int u = warp; u < nunit; u += NW) {
-          if (u < nfused) {
-            int P = (int)((sqrtf(8.0f * (float)u + 1.0f) - 1.0f) * 0.5f);
-            while ((P + 1) * (P + 2) / 2 <= u) ++P;
-            while (P * (P + 1) / 2 > u) --P;
-            const int R = u - P * (P + 1) / 2;
-            const int IP = bij[2 * P], JP = bij[2 * P + 1], IR = bij[2 * R], JR = bij[2 * R + 1];
-            const double* QP = Qs + P * (JB2 * QLD);
-            const double* QR = Qs + R * (JB2 * QLD);
-            // T = B Q_R
-            double t[2][2][2];
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-              for (int nt = 0; nt < 2; ++nt) t[mt][nt][0] = t[mt][nt][1] = 0.0;
-            const double* r0 = A + (size_t)bp_index(IP, JP, g) * ld;
-            const double* r1 = A + (size_t)bp_index(IP, JP, 8 + g) * ld;
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              const int col = bp_index(IR, JR, 4 * kk + tg);
-              const double a0 = r0[col], a1 = r1[col];
-              const double b0 = QR[(4 * kk + tg) * QLD + g], b1 = QR[(4 * kk + tg) * QLD + 8 + g];
-              dmma884(t[0][0][0], t[0][0][1], a0, b0);
-              dmma884(t[0][1][0], t[0][1][1], a0, b1);
-              dmma884(t[1][0][0], t[1][0][1], a1, b0);
-              dmma884(t[1][1][0], t[1][1][1], a1, b1);
-            }
-            // B' = Q_P^T T:  A-operand [m][k] = Q_P[k][m];  B-operand [k][n] = T[k][n] fetched from the accumulator
-            // layout (row g', cols 2 tg', 2 tg' + 1) of lane 4 g' + tg' with g' = 4 (kk & 1) + tg, tg' = g >> 1.
-            double d[2][2][2];
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-              for (int nt = 0; nt < 2; ++nt) d[mt][nt][0] = d[mt][nt][1] = 0.0;
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              const int src = ((4 * (kk & 1) + tg) << 2) | (g >> 1);
-              double bfr[2];
-#pragma unroll
-              for (int nt = 0; nt < 2; ++nt) {
-                const double v0 = __shfl_sync(0xffffffffu, t[kk >> 1][nt][0], src);
-                const double v1 = __shfl_sync(0xffffffffu, t[kk >> 1][nt][1], src);
-                bfr[nt] = (g & 1) ? v1 : v0;
-              }
-              const double a0 = QP[(4 * kk + tg) * QLD + g], a1 = QP[(4 * kk + tg) * QLD + 8 + g];
-              dmma884(d[0][0][0], d[0][0][1], a0, bfr[0]);
-              dmma884(d[0][1][0], d[0][1][1], a0, bfr[1]);
-              dmma884(d[1][0][0], d[1][0][1], a1, bfr[0]);
-              dmma884(d[1][1][0], d[1][1][1], a1, bfr[1]);
-            }
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
-              double* row = A + (size_t)bp_index(IP, JP, 8 * mt + g) * ld;
-#pragma unroll
-              for (int nt = 0; nt < 2; ++nt) {
-                const int col = bp_index(IR, JR, 8 * nt + 2 * tg);
-                row[col] = d[mt][nt][0];
-                row[col + 1] = d[mt][nt][1];
-                if (P != R) {  // mirror: A[col][row]
-                  A[(size_t)col * ld + bp_index(IP, JP, 8 * mt + g)] = d[mt][nt][0];
-                  A[(size_t)(col + 1) * ld + bp_index(IP, JP, 8 * mt + g)] = d[mt][nt][1];
-                }
-              }
-            }
-          } else {
-            const int rem = u - nfused;
-            const int k = (int)__fdividef((float)rem + 0.5f, (float)ntile), rt = rem - k * ntile;
-            const int I = bij[2 * k], J = bij[2 * k + 1];
-            const double* Q = Qs + k * (JB2 * QLD);
-            double* row = V + (size_t)(rt * 8 + g) * ld;
-            double af[4];
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) af[kk] = row[bp_index(I, J, 4 * kk + tg)];
-            double d[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-#pragma unroll
-              for (int nt = 0; nt < 2; ++nt) dmma884(d[nt][0], d[nt][1], af[kk], Q[(4 * kk + tg) * QLD + 8 * nt + g]);
-            }
-#pragma unroll
-            for (int nt = 0; nt < 2; ++nt) {
-              const int col = bp_index(I, J, 8 * nt + 2 * tg);  // 2*tg and 2*tg+1 are in the same 8-block: contiguous
-              row[col] = d[nt][0];
-              row[col + 1] = d[nt][1];
-            }
-          }
-        }
-      }
-      __syncthreads();
-    }
-  }
-}
-
-// Fermi smearing, both spin channels in lockstep (wavefunction/filling.py:201-366).
-// focc[k] = f_alpha + f_beta; returns G = kT sum ln(f^f (1-f)^(1-f)) (scf/base.py:586-594).
-__device__ double fermi_fill(Ctx& c, double nel_a, double nel_b, const xtb_scf_opts& o) {
-  const int n = c.n;
-  // rank sort of the eigenvalues (ascending; ties broken by index)
-  for (int k = threadIdx.x; k < n; k += NT) {
-    const double e = c.eps[k];
-    int rk = 0;
-    for (int j = 0; j < n; ++j) {
-      const double ej = c.eps[j];
-      rk += (ej < e) || (ej == e && j < k);
-    }
-    c.srt[rk] = e;
-  }
-  __syncthreads();
-  double nel[2] = {nel_a, nel_b}, ef[2], ef_used[2], hom[2];
-  bool ne_[2];
-  if (fabs(nel_a + nel_b) < kEps) {
-    for (int k = threadIdx.x; k < n; k += NT) c.focc[k] = 0.0;
-    __syncthreads();
-    return 0.0;
-  }
-  if (o.kt < 3e-7) {  // aufbau (scf/base.py:889)
-    for (int k = threadIdx.x; k < n; k += NT) {
-      const double e = c.eps[k];
-      int rk = 0;
-      for (int j = 0; j < n; ++j) rk += (c.eps[j] < e) || (c.eps[j] == e && j < k);
-      c.focc[k] = (rk < nel_a ? 1.0 : 0.0) + (rk < nel_b ? 1.0 : 0.0);
-    }
-    __syncthreads();
-    return 0.0;
-  }
-#pragma unroll
-  for (int s = 0; s < 2; ++s) {
-    int h = (int)ceil(nel[s] - 5.0e-15) - 1;
-    if (h < 0) h = 0;
-    if (h > n - 1) h = 0;
-    const int l = (n - 1 <= h) ? h : h + 1;
-    hom[s] = (double)h;
-    ne_[s] = nel[s] != 0.0;
-    ef[s] = ne_[s] ? 0.5 * (c.srt[h] + c.srt[l]) : 0.0;
-    ef_used[s] = ef[s];
-  }
-  bool conv = false;
-  for (int it = 0; it < o.fermi_maxiter; ++it) {
-    double sf[2] = {0.0, 0.0}, sd[2] = {0.0, 0.0};
-    for (int k = threadIdx.x; k < n; k += NT) {
-#pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        const double e = ne_[s] ? c.eps[k] : 0.0;
-        const double ex = (e - ef[s]) / o.kt;
-        if (ex < 50.0) {
-          const double et = exp(ex);
-          sf[s] += 1.0 / (et + 1.0);
-          sd[s] += et / (o.kt * (et + 1.0) * (et + 1.0));
-        } else {
-          sd[s] += kEps;
-        }
-      }
-    }
-    const double f0 = block_sum(sf[0], c.red), f1 = block_sum(sf[1], c.red);
-    const double d0 = block_sum(sd[0], c.red), d1 = block_sum(sd[1], c.red);
-    const double r0 = hom[0] - f0 + 1.0, r1 = hom[1] - f1 + 1.0;
-    ef_used[0] = ef[0];
-    ef_used[1] = ef[1];
-    ef[0] += r0 / d0;
-    ef[1] += r1 / d1;
-    if (fabs(r0) <= o.fermi_thresh && fabs(r1) <= o.fermi_thresh) { conv = true; break; }
-  }
-  if (!conv) c.status |= XTB_STATUS_FERMI_FAILED;
-  double g = 0.0;
-  for (int k = threadIdx.x; k < n; k += NT) {
-    double ft = 0.0;
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      double f = 0.0;
-      if (ne_[s]) {
-        const double ex = (c.eps[k] - ef_used[s]) / o.kt;
-        if (ex < 50.0) f = 1.0 / (exp(ex) + 1.0);
-      }
-      ft += f;
-      const double o1 = fmax(f, kEps), o2 = fmax(1.0 - f, kEps);
-      g += o1 * log(o1) + o2 * log(o2);
-    }
-    c.focc[k] = ft;
-  }
-  g = block_sum(g, c.red);
-  __syncthreads();
-  return g * o.kt;
-}
-
-// q (orbital charges) -> shell/atom charges -> potential vout (scf/base.py:702-727, interactions/base.py:134-181)
-__device__ void potential(Ctx& c, const double* __restrict__ q, double* __restrict__ vout) {
-  for (int a = threadIdx.x; a < c.na; a += NT) {
-    const int s0 = c.at_sh0[a], nsa = c.at_nsh[a];
-    double qa = 0.0;
-    for (int k = 0; k < nsa; ++k) {
-      double qs = 0.0;
-      const int sh = s0 + k;
-      const int mu0 = c.sh_ao[sh], nmu = 2 * c.sh_l[sh] + 1;  // AOs of a shell are contiguous
-      for (int mu = mu0; mu < mu0 + nmu; ++mu) qs += q[mu];
-      c.qsh[sh] = qs;
-      qa += qs;
-    }
-    c.qat[a] = qa;
-  }
-  __syncthreads();
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int k = w; k < c.ns; k += NT / 32) {
-    const double* gr = c.gam + (size_t)k * c.ns;
-    double acc = 0.0;
-    for (int l = lane; l < c.ns; l += 32) acc += gr[l] * c.qsh[l];
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      const int a = c.sh_atom[k];
-      const double qa = c.qat[a];
-      c.vsh[k] = acc + c.gam3[(size_t)a * XTB_ATPAR + XTB_AT_GAM3] * qa * qa;
-    }
-  }
-  __syncthreads();
-  for (int mu = threadIdx.x; mu < c.n; mu += NT) vout[mu] = c.vsh[c.ao_sh[mu]];
-  __syncthreads();
-}
-
-// In-CTA right-looking Cholesky S = L L^T (lower triangle, in the A buffer), X = L^{-1} by forward substitution
-// (thread per column, X buffer), C = X^T.  Returns false if S is not positive definite.
-template <bool SM>
-__device__ bool cholesky_start_basis(Ctx& c) {
+// One Newton-Schulz step C <- C (3/2 I - 1/2 C^T S C): restores C^T S C = I to second order.  The Cholesky start basis
+// is S-orthonormal only to cond(S) eps and the Jacobi rotations accumulated over the SCF let it drift further; the defect
+// d enters the energy as sum_k f_k eps_k d_kk (3e-10 Eh for the 550-AO vancoh2, 1e-8 Eh for 3104 AOs).  Uses A and X.
+template <int MODE>
+__device__ void reorthonormalize(Ctx& c) {
   const int n = c.n, ne = c.ne, ld = c.ld;
-  double* A = c.A; double* X = c.X; double* C = c.C; double* lk = c.srt;
-  if (SM) { XTB_ASSUME_SHARED(A); XTB_ASSUME_SHARED(X); XTB_ASSUME_SHARED(C); }
-  XTB_ASSUME_SHARED(lk);
+  constexpr bool AS = MODE != 0, CS = MODE == 1;
   for (int t = threadIdx.x; t < ne * ld; t += NT) {
     const int i = t / ld, j = t - i * ld;
-    A[t] = (i < n && j < n) ? c.S[(size_t)i * n + j] : 0.0;
-    X[t] = 0.0;
-    C[t] = 0.0;
+    c.A[t] = (i < n && j < n) ? c.S[(size_t)i * n + j] : 0.0;
   }
   __syncthreads();
-  bool ok = true;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int k = 0; k < n; ++k) {
-    const double akk = A[(size_t)k * ld + k];
-    if (!(akk > 0.0)) ok = false;
-    const double inv = (akk > 0.0) ? rsqrt(akk) : 0.0;
-    // column k of L, also staged contiguously in lk[]
-    for (int i = k + threadIdx.x; i < n; i += NT) lk[i] = (i == k) ? akk * inv : A[(size_t)i * ld + k] * inv;
-    __syncthreads();
-    for (int i = k + threadIdx.x; i < n; i += NT) A[(size_t)i * ld + k] = lk[i];
-    // trailing update of the lower triangle: A[i][j] -= L[i][k] L[j][k], k < j <= i
-    for (int i = k + 1 + warp; i < n; i += NT / 32) {
-      const double li = lk[i];
-      double* row = A + (size_t)i * ld;
-      for (int j = k + 1 + lane; j <= i; j += 32) row[j] = fma(-li, lk[j], row[j]);
-    }
-    __syncthreads();
-  }
-  // X = L^{-1}: thread j owns column j (consecutive threads -> consecutive words: no bank conflicts)
-  for (int j = threadIdx.x; j < n; j += NT) {
-    for (int i = j; i < n; ++i) {
-      const double* lrow = A + (size_t)i * ld;
-      double s0 = (i == j) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-      int k = j;
-      for (; k + 3 < i; k += 4) {
-        s0 = fma(-lrow[k], X[(size_t)k * ld + j], s0);
-        s1 = fma(-lrow[k + 1], X[(size_t)(k + 1) * ld + j], s1);
-        s2 = fma(-lrow[k + 2], X[(size_t)(k + 2) * ld + j], s2);
-        s3 = fma(-lrow[k + 3], X[(size_t)(k + 3) * ld + j], s3);
-      }
-      for (; k < i; ++k) s0 = fma(-lrow[k], X[(size_t)k * ld + j], s0);
-      X[(size_t)i * ld + j] = ((s0 + s1) + (s2 + s3)) / lrow[i];
+  gemm_tn<AS, CS>(ne, ne, c.A, c.C, ld, c.X, ld, ne);  // X = S C
+  gemm_tn<CS, CS>(ne, ne, c.C, c.X, ld, c.A, ld, ne);  // A = C^T S C
+  for (int t = threadIdx.x; t < ne * ne; t += NT) {
+    const int i = t / ne, j = t - i * ne;
+    if (i <= j) {
+      const double g = 0.5 * (c.A[(size_t)i * ld + j] + c.A[(size_t)j * ld + i]);
+      const double m = (i == j ? 1.5 : 0.0) - 0.5 * g;
+      c.A[(size_t)i * ld + j] = m;
+      c.A[(size_t)j * ld + i] = m;
     }
   }
-  __syncthreads();
-  // C0 = X^T  (upper triangular): C0^T S C0 = L^{-1} L L^T L^{-T} = I
-  for (int t = threadIdx.x; t < n * n; t += NT) {
-    const int a = t / n, b = t - a * n;
-    C[(size_t)a * ld + b] = (b >= a) ? X[(size_t)b * ld + a] : 0.0;
+  for (int t = threadIdx.x; t < ne * ne; t += NT) {
+    const int k = t / ne, i = t - k * ne;
+    c.X[(size_t)k * ld + i] = c.C[(size_t)i * ld + k];  // X = C^T
   }
   __syncthreads();
-  return ok;
+  gemm_tn<CS, AS>(ne, ne, c.X, c.A, ld, c.C, ld, ne);  // C = C M
 }
 
 // One SCF map evaluation v -> q -> vnew (scf/base.py:651-675, 818-907, 765-792).
 // Returns the electronic free energy of this solve.
-template <bool SM>
+template <int MODE>
 __device__ double fcn(Ctx& c, const double* __restrict__ v, const xtb_scf_opts& o, double nel_a, double nel_b, double jtol) {
   const int n = c.n, ne = c.ne, ld = c.ld;
+  constexpr bool AS = MODE != 0, CS = MODE == 1;  // address space of the A buffer / of the C and X buffers
   // F = H0 - 1/2 S (v_i + v_j)   -> A buffer (symmetric, zero padded)
   for (int t = threadIdx.x; t < ne * ld; t += NT) {
     const int i = t / ld, j = t - i * ld;
@@ -552,8 +64,8 @@ __device__ double fcn(Ctx& c, const double* __restrict__ v, const xtb_scf_opts& 
     c.A[t] = f;
   }
   __syncthreads();
-  gemm_tn<SM>(ne, ne, c.A, c.C, ld, c.X, ld, ne);  // X = F C   (F symmetric)
-  gemm_tn<SM>(ne, ne, c.C, c.X, ld, c.A, ld, ne);  // A = C^T X
+  gemm_tn<AS, CS>(ne, ne, c.A, c.C, ld, c.X, ld, ne);  // X = F C   (F symmetric)
+  gemm_tn<CS, CS>(ne, ne, c.C, c.X, ld, c.A, ld, ne);  // A = C^T X
   // symmetrise (round-off) and keep the pad row/column exactly zero
   for (int t = threadIdx.x; t < ne * ne; t += NT) {
     const int i = t / ne, j = t - i * ne;
@@ -564,7 +76,7 @@ __device__ double fcn(Ctx& c, const double* __restrict__ v, const xtb_scf_opts& 
     }
   }
   __syncthreads();
-  const int sw = jacobi<SM>(c, c.A, c.C, ne, jtol, o.jacobi_max_sweeps);
+  const int sw = jacobi<AS, CS>(c, c.A, c.C, ne, jtol, o.jacobi_max_sweeps);
   if (sw < 0) c.status |= XTB_STATUS_JACOBI_NOT_CONVERGED;
   c.sweeps += sw < 0 ? -sw : sw;
   for (int k = threadIdx.x; k < n; k += NT) c.eps[k] = c.A[(size_t)k * ld + k];
@@ -586,7 +98,7 @@ __device__ double fcn(Ctx& c, const double* __restrict__ v, const xtb_scf_opts& 
     c.X[t] = (i < n) ? sqrt(c.focc[k]) * c.C[(size_t)i * ld + k] : 0.0;
   }
   __syncthreads();
-  gemm_tn<SM>(ne, nocc, c.X, c.X, ld, c.A, ld, ne);
+  gemm_tn<CS, CS>(ne, nocc, c.X, c.X, ld, c.A, ld, ne);
   // Mulliken populations and orbital-resolved H0 energies: one warp per row
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   for (int mu = w; mu < n; mu += NT / 32) {
@@ -611,122 +123,7 @@ __device__ double fcn(Ctx& c, const double* __restrict__ v, const xtb_scf_opts& 
   return g;
 }
 
-// 5x5 (or smaller) solve with partial pivoting, thread 0 only
-__device__ void small_solve(int n, double (*a)[5], double* b, double* x) {
-  for (int k = 0; k < n; ++k) {
-    int piv = k;
-    double best = fabs(a[k][k]);
-    for (int i = k + 1; i < n; ++i)
-      if (fabs(a[i][k]) > best) { best = fabs(a[i][k]); piv = i; }
-    if (piv != k) {
-      for (int j = 0; j < n; ++j) { const double t = a[k][j]; a[k][j] = a[piv][j]; a[piv][j] = t; }
-      const double t = b[k]; b[k] = b[piv]; b[piv] = t;
-    }
-    for (int i = k + 1; i < n; ++i) {
-      const double f = a[i][k] / a[k][k];
-      for (int j = k + 1; j < n; ++j) a[i][j] -= f * a[k][j];
-      b[i] -= f * b[k];
-    }
-  }
-  for (int i = n - 1; i >= 0; --i) {
-    double s = b[i];
-    for (int j = i + 1; j < n; ++j) s -= a[i][j] * x[j];
-    x[i] = s / a[i][i];
-  }
-}
-
-struct Mixer {
-  int step, head;  // head: physical slot of logical history index 0
-};
-
-// Anderson / simple mixing (mixer/anderson.py:163-317, mixer/simple.py:88-151).  x_old is in c.v, x_new in
-// c.vnew; the mixed vector is written to c.v.  Returns true if converged (mixer/base.py:229-256).
-__device__ bool mix(Ctx& c, Mixer& mx, const xtb_scf_opts& o, double* sm_theta) {
-  const int n = c.n, G1 = o.generations + 1;
-  auto slot = [&](int i) { return (mx.head + i) % G1; };
-  double* f0 = c.fh + (size_t)slot(0) * n;
-  double* x0 = c.xh + (size_t)slot(0) * n;
-  if (mx.step == 0)
-    for (int k = threadIdx.x; k < n; k += NT) x0[k] = c.v[k];
-  mx.step += 1;
-  double l2 = 0.0, li = 0.0;
-  for (int k = threadIdx.x; k < n; k += NT) {
-    const double d = c.vnew[k] - c.v[k];
-    f0[k] = d;
-    l2 += d * d;
-    li = fmax(li, fabs(d));
-  }
-  l2 = block_sum(l2, c.red);
-  li = block_max(li, c.red);
-  __syncthreads();
-  const bool conv = (sqrt(l2) < o.x_atol) && (li < o.x_atol_max);
-
-  const bool anderson = o.mixer == 0 && (mx.step > o.generations || (mx.step > 1 && !o.soft_start));
-  if (o.mixer == 1) {
-    for (int k = threadIdx.x; k < n; k += NT) c.v[k] = c.v[k] + o.damp * f0[k];
-  } else if (anderson) {
-    int nh = mx.step - 1;
-    if (nh > o.generations) nh = o.generations;
-    if (nh > 5) nh = 5;
-    // a_ij = <dF_i, dF_j>, b_i = <dF_i, F0>, dF_i = F0 - F_i   (20 dot products, one warp each)
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int ndot = nh * (nh + 1) / 2 + nh;
-    for (int d = w; d < ndot; d += NT / 32) {
-      int i, j;
-      if (d < nh) { i = d; j = -1; }
-      else {
-        int r = d - nh; i = 0;
-        while (r > i) { r -= i + 1; ++i; }
-        j = r;
-      }
-      const double* fi = c.fh + (size_t)slot(i + 1) * n;
-      const double* fj = (j >= 0) ? c.fh + (size_t)slot(j + 1) * n : nullptr;
-      double acc = 0.0;
-      for (int k = lane; k < n; k += 32) {
-        const double di = f0[k] - fi[k];
-        const double dj = (j >= 0) ? f0[k] - fj[k] : f0[k];
-        acc = fma(di, dj, acc);
-      }
-      acc = warp_sum(acc);
-      if (lane == 0) {
-        if (j < 0) sm_theta[25 + i] = acc;
-        else { sm_theta[i * 5 + j] = acc; sm_theta[j * 5 + i] = acc; }
-      }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double a[5][5], bb[5], th[5];
-      for (int i = 0; i < nh; ++i) {
-        for (int j = 0; j < nh; ++j) a[i][j] = sm_theta[i * 5 + j];
-        a[i][i] *= 1.0 + o.diag_offset * o.diag_offset;
-        bb[i] = sm_theta[25 + i];
-      }
-      small_solve(nh, a, bb, th);
-      for (int i = 0; i < nh; ++i) sm_theta[30 + i] = th[i];
-    }
-    __syncthreads();
-    for (int k = threadIdx.x; k < n; k += NT) {
-      double xb = x0[k], fb = f0[k];
-      for (int i = 0; i < nh; ++i) {
-        const double th = sm_theta[30 + i];
-        xb += th * (c.xh[(size_t)slot(i + 1) * n + k] - x0[k]);
-        fb -= th * (f0[k] - c.fh[(size_t)slot(i + 1) * n + k]);
-      }
-      c.v[k] = xb + o.damp * fb;
-    }
-  } else {
-    for (int k = threadIdx.x; k < n; k += NT) c.v[k] = x0[k] + o.damp_init * f0[k];
-  }
-  __syncthreads();
-  // roll histories and store the mixed vector as x_hist[0]
-  mx.head = (mx.head + G1 - 1) % G1;
-  double* xn = c.xh + (size_t)slot(0) * n;
-  for (int k = threadIdx.x; k < n; k += NT) xn[k] = c.v[k];
-  __syncthreads();
-  return conv;
-}
-
-template <bool SM>
+template <int MODE>
 __global__ void __launch_bounds__(NT, XTB_MINB)
 k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, const double* __restrict__ H0,
       const double* __restrict__ gamma, const double* __restrict__ nel_ab, const double* __restrict__ q0_at, double* __restrict__ work,
@@ -770,15 +167,16 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
     c.jr = p; p += NGRP * 48;
   }
   p += ((p - sm) & 1);
-  c.smem = SM;
+  c.smem = MODE == 1;
   const size_t msz = (size_t)ne * ld;
-  if (SM) {
+  if (MODE == 1) {
     const size_t nex = (size_t)((lnao + 15) & ~15);
     const size_t mszx = nex * (nex + 4);
     c.C = p; c.A = p + mszx; c.X = p + 2 * mszx;
   } else {
     double* wm = work + (size_t)(o.generations + 1) * 2 * b.nao_tot + 3 * ((size_t)b.mat_off[m] + 34 * (size_t)c.o0 + 285 * (size_t)m);  // sum of (n+15)(n+19) bounds ne*ld
     c.C = wm; c.A = wm + msz; c.X = wm + 2 * msz;
+    if (MODE == 2) c.A = p;  // hybrid: the Fock / A / density buffer (sub-problem gathers, two-sided updates) in shared memory
   }
   c.xh = work + (size_t)(o.generations + 1) * 2 * c.o0;
   c.fh = c.xh + (size_t)(o.generations + 1) * n;
@@ -801,7 +199,8 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
   }
   // S-orthonormal start basis C0 = L^{-T} from the Cholesky factor S = L L^T (done once; the reference
   // re-factorises S in every iteration inside storch.eighb, scf/unrolling/base.py:141-175)
-  if (!cholesky_start_basis<SM>(c)) c.status |= XTB_STATUS_S_NOT_POSDEF;
+  if (!cholesky_start_basis<MODE>(c)) c.status |= XTB_STATUS_S_NOT_POSDEF;
+  reorthonormalize<MODE>(c);
 
   // guess: atomic charges spread equally over shells, then over the AOs of a shell (scf/guess.py:122-182)
   for (int mu = threadIdx.x; mu < n; mu += NT) {
@@ -819,54 +218,24 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
   bool converged = true;
   // intermediate map evaluations only steer the SCF trajectory: a looser eigensolver tolerance saves the last
   // (verification) sweep; the final solve that defines charges / energies / P / W uses the tight one
-  double g = fcn<SM>(c, c.v, o, nel_a, nel_b, o.maxiter > 0 ? o.jacobi_tol_iter : o.jacobi_tol);  // outside the loop (unrolling/default.py:81)
+  double g = fcn<MODE>(c, c.v, o, nel_a, nel_b, o.maxiter > 0 ? o.jacobi_tol_iter : o.jacobi_tol);  // outside the loop (unrolling/default.py:81)
   if (o.maxiter > 0) {
     converged = false;
     mix(c, mx, o, sm_theta);  // mix_guess (unrolling/default.py:93-94); convergence is not tested here
     for (int it = 0; it < o.maxiter; ++it) {
-      g = fcn<SM>(c, c.v, o, nel_a, nel_b, o.jacobi_tol_iter);
+      g = fcn<MODE>(c, c.v, o, nel_a, nel_b, o.jacobi_tol_iter);
       ++iters;
       if (mix(c, mx, o, sm_theta)) { converged = true; break; }
     }
     // converged_to_charges: one more solve with the UN-MIXED potential (scf/base.py:497-501, default.py:111-114)
     for (int k = threadIdx.x; k < n; k += NT) c.v[k] = c.vnew[k];
     __syncthreads();
-    g = fcn<SM>(c, c.v, o, nel_a, nel_b, o.jacobi_tol);
+    reorthonormalize<MODE>(c);  // remove the drift of the accumulated rotations before the solve that defines the results
+    g = fcn<MODE>(c, c.v, o, nel_a, nel_b, o.jacobi_tol);
   }
   if (!converged) c.status |= XTB_STATUS_SCF_NOT_CONVERGED;
 
-  // ---- outputs -------------------------------------------------------------------------------
-  for (int mu = threadIdx.x; mu < n; mu += NT) {
-    q_orb[c.o0 + mu] = c.q[mu];
-    v_orb[c.o0 + mu] = c.vnew[mu];  // potential of the final charges (scf/base.py:468)
-    emo[c.o0 + mu] = c.eps[mu];
-    occ[c.o0 + mu] = c.focc[mu];
-  }
-  for (int k = threadIdx.x; k < c.ns; k += NT) q_sh[c.s0 + k] = c.qsh[k];
-  // atom-resolved energies (scf/base.py:514-534; interactions/base.py:305-360; secondorder.py:374-382; thirdorder.py:246-276)
-  for (int a = threadIdx.x; a < c.na; a += NT) {
-    double e = 0.0;
-    const int sh0 = c.at_sh0[a], nsa = c.at_nsh[a];
-    for (int k = 0; k < nsa; ++k) {
-      const int mu0 = c.sh_ao[sh0 + k], nmu = 2 * c.sh_l[sh0 + k] + 1;
-      for (int mu = mu0; mu < mu0 + nmu; ++mu) e += c.eorb[mu];
-    }
-    const double qa = c.qat[a];
-    const double g3 = c.gam3[(size_t)a * XTB_ATPAR + XTB_AT_GAM3];
-    for (int k = 0; k < nsa; ++k) {
-      const double ves2 = c.vsh[sh0 + k] - g3 * qa * qa;  // gamma.q_sh part of the shell potential
-      e += 0.5 * c.qsh[sh0 + k] * ves2;
-    }
-    e += g3 * qa * qa * qa / 3.0;
-    e += g / (double)c.na;
-    e_atom[c.a0 + a] = e;
-    q_at[c.a0 + a] = qa;
-  }
-  if (threadIdx.x == 0) {
-    fenergy[m] = g;
-    iterations[m] = iters;
-    status[m] = c.status | (c.sweeps << 8);  // bits 8..: total Jacobi sweeps (diagnostic)
-  }
+  emit_results(c, b, m, g, iters, q_orb, q_sh, q_at, v_orb, e_atom, fenergy, emo, occ, iterations, status);
   if (o.want_density) {
     double* Pm = Pout + b.mat_off[m];
     double* Wm = Wout + b.mat_off[m];
@@ -885,7 +254,7 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
       c.A[t] = cv;
     }
     __syncthreads();
-    gemm_tn<SM>(ne, nocc, c.X, c.A, ld, Wm, n, n);
+    gemm_tn<MODE == 1, MODE != 0>(ne, nocc, c.X, c.A, ld, Wm, n, n);
   }
 }
 
@@ -898,34 +267,54 @@ int64_t vec_smem_bytes(int64_t nao_max, int64_t nsx, int64_t nax) {
   return d * 8;
 }
 
-}  // namespace
+// dynamic shared memory of a launch: vectors + Jacobi scratch + the matrices the mode keeps in shared memory
+int64_t mode_smem_bytes(int mode, int64_t nao_max, int64_t nsx, int64_t nax) {
+  const int64_t nex = (nao_max + 15) & ~15;
+  const int64_t nmat = mode == 1 ? 3 : mode == 2 ? 1 : 0;
+  return vec_smem_bytes(nao_max, nsx, nax) + nmat * nex * (nex + 4) * 8;
+}
 
-#ifdef XTB_SECONDARY
-// secondary build: launcher of the 2-CTA/SM global-memory variant
-int xtb_scf_launch_global_512(const xtb_batch* b, const xtb_scf_opts* o, int nblocks, int lnao, int lnsh, int lnat, const double* S,
-                              const double* H0, const double* gamma, const double* nel_ab, const double* q0_at, double* work,
-                              double* q_orb, double* q_sh, double* q_at, double* v_orb, double* e_atom, double* fenergy, double* emo,
-                              double* occ, int32_t* iterations, int32_t* status, double* P, double* W, cudaStream_t st) {
-  const int64_t smem = vec_smem_bytes(lnao, lnsh, lnat);
+#define XTB_SCF_ARGS                                                                                                              \
+  const xtb_batch *b, const xtb_scf_opts *o, int nblocks, int lnao, int lnsh, int lnat, const double *S, const double *H0,       \
+      const double *gamma, const double *nel_ab, const double *q0_at, double *work, double *q_orb, double *q_sh, double *q_at,    \
+      double *v_orb, double *e_atom, double *fenergy, double *emo, double *occ, int32_t *iterations, int32_t *status, double *P, \
+      double *W, cudaStream_t st
+
+template <int MODE>
+int launch_mode(XTB_SCF_ARGS) {
+  const int64_t smem = mode_smem_bytes(MODE, lnao, lnsh, lnat);
   static int64_t configured = 0;
   if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_scf<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_scf<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     configured = smem;
   }
-  k_scf<false><<<nblocks, NT, (size_t)smem, st>>>(*b, *o, S, H0, gamma, nel_ab, q0_at, work, q_orb, q_sh, q_at, v_orb, e_atom, fenergy,
-                                                   emo, occ, iterations, status, P, W);
+  k_scf<MODE><<<nblocks, NT, (size_t)smem, st>>>(*b, *o, S, H0, gamma, nel_ab, q0_at, work, q_orb, q_sh, q_at, v_orb, e_atom, fenergy, emo,
+                                                  occ, iterations, status, P, W);
   return launch_status();
 }
+
+}  // namespace
+
+#ifdef XTB_SECONDARY
+// secondary build: launcher of the 2-CTA/SM variants (mode 0: global memory, mode 2: hybrid)
+int xtb_scf_launch_2cta(int mode, XTB_SCF_ARGS) {
+  if (mode == 2)
+    return launch_mode<2>(b, o, nblocks, lnao, lnsh, lnat, S, H0, gamma, nel_ab, q0_at, work, q_orb, q_sh, q_at, v_orb, e_atom, fenergy,
+                          emo, occ, iterations, status, P, W, st);
+  return launch_mode<0>(b, o, nblocks, lnao, lnsh, lnat, S, H0, gamma, nel_ab, q0_at, work, q_orb, q_sh, q_at, v_orb, e_atom, fenergy, emo,
+                        occ, iterations, status, P, W, st);
+}
 #else
-int xtb_scf_launch_global_512(const xtb_batch* b, const xtb_scf_opts* o, int nblocks, int lnao, int lnsh, int lnat, const double* S,
-                              const double* H0, const double* gamma, const double* nel_ab, const double* q0_at, double* work,
-                              double* q_orb, double* q_sh, double* q_at, double* v_orb, double* e_atom, double* fenergy, double* emo,
-                              double* occ, int32_t* iterations, int32_t* status, double* P, double* W, cudaStream_t st);
+int xtb_scf_launch_2cta(int mode, XTB_SCF_ARGS);
+
+extern "C" int64_t xtb_scf_smem_bytes_mode(int32_t mode, int32_t nao_max, int32_t nsh_max, int32_t nat_max) {
+  if (mode < 0 || mode > 2) return -1;
+  return mode_smem_bytes(mode, nao_max, nsh_max, nat_max);
+}
 
 extern "C" int64_t xtb_scf_smem_bytes_for(int32_t nao_max, int32_t nsh_max, int32_t nat_max) {
-  const int64_t nex = (nao_max + 15) & ~15;
-  return vec_smem_bytes(nao_max, nsh_max, nat_max) + 3 * nex * (nex + 4) * 8;
+  return mode_smem_bytes(1, nao_max, nsh_max, nat_max);
 }
 
 extern "C" int64_t xtb_scf_smem_bytes(const xtb_batch* b) {
@@ -936,8 +325,8 @@ extern "C" int64_t xtb_scf_smem_bytes(const xtb_batch* b) {
 extern "C" int64_t xtb_scf_workspace_bytes(const xtb_batch* b, const xtb_scf_opts* o) {
   if (!b || !o) return -1;
   int64_t d = (int64_t)(o->generations + 1) * 2 * b->nao_tot;
-  if (!o->use_smem) {
-    // 3 matrices of (n+1)(n+2) per molecule: 3 (sum n^2 + 3 sum n + 2 nb)
+  if (o->use_smem != 1) {
+    // 3 matrices of at most (n+15)(n+19) per molecule: 3 (sum n^2 + 34 sum n + 285 nb)
     d += 3 * (b->mat_total + 34 * (int64_t)b->nao_tot + 285 * (int64_t)b->nb);
   }
   return d * 8 + 256;
@@ -952,43 +341,34 @@ extern "C" int xtb_scf_run(const xtb_batch* b, const xtb_scf_opts* o, const doub
     return -1;
   if (o->want_density && (!P || !W)) return -1;
   if (o->generations > 5 || o->generations < 1) return -3;
+  if (o->use_smem < 0 || o->use_smem > 2) return -4;
   if (b->nb == 0) return 0;
   const int nblocks = o->mol_list ? o->list_len : b->nb;
   if (nblocks <= 0) return 0;
   const int lnao = o->mol_list ? o->list_nao_max : b->nao_max, lnsh = o->mol_list ? o->list_nsh_max : b->nsh_max,
             lnat = o->mol_list ? o->list_nat_max : b->nat_max;
-  if (!o->use_smem) {
-    // global-memory variant: with at least ~1.5 molecules per SM two 512-thread CTAs per SM overlap one molecule's
-    // latency-bound sub-problems with the other's L2-bound passes; below that one 1024-thread CTA per SM is faster
-    static int n_sm = 0;
-    if (n_sm == 0) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    }
-    if (2 * nblocks >= 3 * n_sm)
-      return xtb_scf_launch_global_512(b, o, nblocks, lnao, lnsh, lnat, S, H0, gamma, nel_ab, q0_at, (double*)work, q_orb, q_sh, q_at,
-                                       v_orb, e_atom, fenergy, emo, occ, iterations, status, P, W, (cudaStream_t)stream);
-    const int64_t smem = vec_smem_bytes(lnao, lnsh, lnat);
-    static int64_t configured_g = 0;
-    if (smem > configured_g) {
-      cudaError_t e = cudaFuncSetAttribute(k_scf<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return (int)e;
-      configured_g = smem;
-    }
-    k_scf<false><<<nblocks, NT, (size_t)smem, (cudaStream_t)stream>>>(*b, *o, S, H0, gamma, nel_ab, q0_at, (double*)work, q_orb, q_sh,
-                                                                      q_at, v_orb, e_atom, fenergy, emo, occ, iterations, status, P, W);
-    return launch_status();
+  cudaStream_t st = (cudaStream_t)stream;
+  double* wk = (double*)work;
+  const int mode = o->use_smem;
+  if (mode == 1)
+    return launch_mode<1>(b, o, nblocks, lnao, lnsh, lnat, S, H0, gamma, nel_ab, q0_at, wk, q_orb, q_sh, q_at, v_orb, e_atom, fenergy, emo,
+                          occ, iterations, status, P, W, st);
+  // global-memory and hybrid variants: with at least ~1.5 molecules per SM two CTAs per SM (secondary build, 64 registers)
+  // overlap one molecule's latency-bound sub-problems with the other's tensor-core passes, if their shared memory fits twice
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   }
-  const int64_t smem = xtb_scf_smem_bytes_for(lnao, lnsh, lnat);
-  static int64_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_scf<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    configured = smem;
-  }
-  k_scf<true><<<nblocks, NT, (size_t)smem, (cudaStream_t)stream>>>(*b, *o, S, H0, gamma, nel_ab, q0_at, (double*)work, q_orb, q_sh, q_at,
-                                                                   v_orb, e_atom, fenergy, emo, occ, iterations, status, P, W);
-  return launch_status();
+  const bool two = 2 * nblocks >= 3 * n_sm && mode_smem_bytes(mode, lnao, lnsh, lnat) <= XTB_SMEM_2CTA;
+  if (two)
+    return xtb_scf_launch_2cta(mode, b, o, nblocks, lnao, lnsh, lnat, S, H0, gamma, nel_ab, q0_at, wk, q_orb, q_sh, q_at, v_orb, e_atom,
+                               fenergy, emo, occ, iterations, status, P, W, st);
+  if (mode == 2)
+    return launch_mode<2>(b, o, nblocks, lnao, lnsh, lnat, S, H0, gamma, nel_ab, q0_at, wk, q_orb, q_sh, q_at, v_orb, e_atom, fenergy, emo,
+                          occ, iterations, status, P, W, st);
+  return launch_mode<0>(b, o, nblocks, lnao, lnsh, lnat, S, H0, gamma, nel_ab, q0_at, wk, q_orb, q_sh, q_at, v_orb, e_atom, fenergy, emo,
+                        occ, iterations, status, P, W, st);
 }
-#endif  // XTB_NT
+#endif  // XTB_SECONDARY

@@ -1,0 +1,656 @@
+// Multi-CTA self-consistent field path for ONE large molecule (BASELINE config 4: sh3, nao 3104).
+//
+// The one-CTA-per-molecule kernel (xtb_scf.cu) stops scaling when a single system should use the whole device, and its
+// per-orbital vectors no longer fit in shared memory beyond ~700 AOs.  Here every stage of the SCF map is a grid-wide
+// kernel over the padded ne x ne matrices (ne = n rounded up to 128, row-major, ld = ne) in a torch-owned workspace:
+//   Fock build -> A = C^T F C (two fp64 tensor-core GEMMs, 128x128 tiles) -> two-level block Jacobi (outer blocks of 32:
+//   one CTA per block pair solves the 64x64 sub-problem with the in-CTA blocked Jacobi of xtb_scf_core.cuh, then all
+//   CTAs apply the accumulated 64x64 rotations Q to A (two-sided, symmetric half + mirror) and C with 64^3 DMMA GEMMs)
+//   -> Fermi filling / potential / Anderson mixing (single-CTA kernels reusing the device functions of the batch path)
+//   -> density P = Y^T Y (GEMM) -> Mulliken populations.
+// The host drives the loop (one stream synchronisation per Jacobi sweep and per SCF iteration to read the convergence
+// scalars); same arithmetic conventions as the batch kernel (eigenvector basis of the previous iteration, final solve
+// with the un-mixed potential, scf/base.py:497-501).  The S-orthonormal start basis is U s^{-1/2} from the Jacobi
+// eigendecomposition S = U s U^T (any S-orthonormal basis gives the same SCF trajectory up to round-off).
+#include "xtb_scf_core.cuh"
+
+namespace {
+
+constexpr int OB = 32;       // outer Jacobi block
+constexpr int OP = 2 * OB;   // indices of an outer block pair = sub-problem dimension
+constexpr int SLD = OP + 4;  // shared-memory leading dimension (== 4 mod 16: conflict-free DMMA fragments)
+constexpr int LPAD = 128;    // ne is a multiple of the GEMM tile
+constexpr int GT = 128;      // GEMM CTA tile
+constexpr int GK = 16;       // GEMM K chunk
+constexpr int GLD = GT + 4;  // GEMM shared-memory leading dimension
+
+struct LargeState {  // device-resident scalars of one large-molecule SCF
+  double g;          // electronic free energy of the last solve
+  double off;        // max |off-diagonal| (Jacobi sweep test), compared as raw bits (non-negative doubles)
+  int mixer_step, mixer_head;
+  int status, sweeps, nocc, converged;
+  int pad[8];
+};
+
+struct Layout {  // workspace offsets in doubles
+  size_t C, A, X, Q, vec, hist, bij, state, total;
+  int ne, nbp;
+};
+
+__host__ __device__ inline Layout layout(int n, int ns, int na, int gen) {
+  Layout l;
+  l.ne = (n + LPAD - 1) / LPAD * LPAD;
+  l.nbp = l.ne / OP;
+  const size_t m = (size_t)l.ne * l.ne;
+  size_t p = 0;
+  l.C = p; p += m;
+  l.A = p; p += m;
+  l.X = p; p += m;
+  l.Q = p; p += (size_t)l.nbp * OP * OP;
+  l.vec = p; p += (size_t)8 * (n + 2) + 2 * ns + na + 32 + 36 + (n + 4) / 2 + 2;
+  p += p & 1;
+  l.hist = p; p += (size_t)2 * (gen + 1) * n;
+  p += p & 1;
+  l.bij = p; p += l.nbp + 1;
+  p += p & 1;
+  l.state = p; p += sizeof(LargeState) / 8 + 1;
+  l.total = p;
+  return l;
+}
+
+// Context of molecule m with all per-orbital vectors in the workspace (generic address space).
+__device__ void large_ctx(Ctx& c, const xtb_batch& b, int m, double* work, int gen, const double* S, const double* H0,
+                          const double* gamma) {
+  c.o0 = b.ao_off[m]; c.s0 = b.sh_off[m]; c.a0 = b.at_off[m];
+  c.n = b.ao_off[m + 1] - c.o0;
+  c.ns = b.sh_off[m + 1] - c.s0;
+  c.na = b.at_off[m + 1] - c.a0;
+  const Layout l = layout(c.n, c.ns, c.na, gen);
+  c.ne = l.ne; c.ld = l.ne; c.np = l.ne / 2;
+  c.status = 0; c.sweeps = 0; c.smem = false;
+  c.C = work + l.C; c.A = work + l.A; c.X = work + l.X;
+  const int nmx = c.n + 2;
+  double* p = work + l.vec;
+  c.eps = p; p += nmx; c.srt = p; p += nmx; c.focc = p; p += nmx; c.v = p; p += nmx; c.vnew = p; p += nmx;
+  c.q = p; p += nmx; c.n0 = p; p += nmx; c.eorb = p; p += nmx;
+  c.qsh = p; p += c.ns; c.vsh = p; p += c.ns; c.qat = p; p += c.na;
+  c.red = p; p += 32;
+  c.cs = p; p += 36;  // Anderson small system (sm_theta of the batch kernel)
+  c.occl = (int*)p;
+  c.pp = c.qq = nullptr; c.jq = c.jm = c.jr = nullptr;
+  c.xh = work + l.hist;
+  c.fh = c.xh + (size_t)(gen + 1) * c.n;
+  c.S = S + b.mat_off[m];
+  c.H0 = H0 + b.mat_off[m];
+  c.gam = gamma + b.gam_off[m];
+  c.ao_sh = b.ao_sh + c.o0;
+  c.sh_atom = b.sh_atom + c.s0;
+  c.sh_ao = b.sh_ao + c.s0;
+  c.sh_l = b.sh_l + c.s0;
+  c.at_sh0 = b.at_sh0 + c.a0;
+  c.at_nsh = b.at_nsh + c.a0;
+  c.gam3 = b.at_par + (size_t)c.a0 * XTB_ATPAR;
+}
+
+// ---- elementwise / reduction kernels over the padded matrices ----------------------------------------------------
+
+// dst (ne x ne) = src (n x n) zero padded; pad diagonal = dpad
+__global__ void kl_load(double* __restrict__ dst, const double* __restrict__ src, int n, int ne, double dpad) {
+  const size_t tot = (size_t)ne * ne;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(t / ne), j = (int)(t - (size_t)i * ne);
+    dst[t] = (i < n && j < n) ? src[(size_t)i * n + j] : (i == j ? dpad : 0.0);
+  }
+}
+
+__global__ void kl_pack(double* __restrict__ dst, const double* __restrict__ src, int n, int ne) {
+  const size_t tot = (size_t)n * n;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(t / n), j = (int)(t - (size_t)i * n);
+    dst[t] = src[(size_t)i * ne + j];
+  }
+}
+
+// F = H0 - 1/2 S (v_i + v_j), zero padded (scf/base.py:651-675)
+__global__ void kl_fock(double* __restrict__ A, const double* __restrict__ H0, const double* __restrict__ S, const double* __restrict__ v,
+                        int n, int ne) {
+  const size_t tot = (size_t)ne * ne;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(t / ne), j = (int)(t - (size_t)i * ne);
+    double f = 0.0;
+    if (i < n && j < n) {
+      const size_t ij = (size_t)i * n + j;
+      f = H0[ij] - 0.5 * S[ij] * (v[i] + v[j]);
+    }
+    A[t] = f;
+  }
+}
+
+// symmetrise (round-off of the two GEMMs) and keep the pad rows / columns exactly zero
+__global__ void kl_symmetrize(double* __restrict__ A, int n, int ne) {
+  const size_t tot = (size_t)ne * ne;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(t / ne), j = (int)(t - (size_t)i * ne);
+    if (i < j) {
+      const double a = (i < n && j < n) ? 0.5 * (A[(size_t)i * ne + j] + A[(size_t)j * ne + i]) : 0.0;
+      A[(size_t)i * ne + j] = a;
+      A[(size_t)j * ne + i] = a;
+    } else if (i == j && i >= n) {
+      A[t] = 0.0;
+    }
+  }
+}
+
+__global__ void kl_offmax(const double* __restrict__ A, int ne, LargeState* st) {
+  __shared__ double red[32];
+  const size_t tot = (size_t)ne * ne;
+  double off = 0.0;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(t / ne), j = (int)(t - (size_t)i * ne);
+    if (i != j) off = fmax(off, fabs(A[t]));
+  }
+  off = block_max(off, red);
+  if (threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned long long*>(&st->off), (unsigned long long)__double_as_longlong(off));
+}
+
+// start basis: C[:, k] = U[:, k] / sqrt(s_k) (columns of the eigenvectors of S scaled by the inverse root of the eigenvalue)
+__global__ void kl_scale_cols(double* __restrict__ C, const double* __restrict__ A, int n, int ne, LargeState* st) {
+  const size_t tot = (size_t)ne * ne;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(t / ne), k = (int)(t - (size_t)i * ne);
+    if (k < n && i < n) {
+      const double s = A[(size_t)k * ne + k];
+      if (!(s > 0.0)) {
+        if (i == 0) atomicOr(&st->status, XTB_STATUS_S_NOT_POSDEF);
+        C[t] = 0.0;
+      } else {
+        C[t] *= rsqrt(s);
+      }
+    } else {
+      C[t] = 0.0;
+    }
+  }
+}
+
+// M = 3/2 I - 1/2 sym(G) (Newton-Schulz factor of the re-orthonormalisation)
+__global__ void kl_ns_factor(double* __restrict__ A, int ne) {
+  const size_t tot = (size_t)ne * ne;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(t / ne), j = (int)(t - (size_t)i * ne);
+    if (i <= j) {
+      const double g = 0.5 * (A[(size_t)i * ne + j] + A[(size_t)j * ne + i]);
+      const double m = (i == j ? 1.5 : 0.0) - 0.5 * g;
+      A[(size_t)i * ne + j] = m;
+      A[(size_t)j * ne + i] = m;
+    }
+  }
+}
+
+// dst = src^T (ne x ne, 32 x 32 tiles)
+__global__ void kl_transpose(double* __restrict__ dst, const double* __restrict__ src, int ne) {
+  __shared__ double tile[32][33];
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) tile[r][tx] = src[(size_t)(i0 + r) * ne + j0 + tx];
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) dst[(size_t)(j0 + r) * ne + i0 + tx] = tile[tx][r];
+}
+
+// Y[kk][i] = w_k C[i][k] for the occupied orbitals k = occl[kk] (rows nocc..kocc-1 zero); which = 0: w = sqrt(f) -> X;
+// which = 1: w = f eps -> X and w = 1 -> A (energy-weighted density, W = Y1^T Y2)
+__global__ void kl_build_y(double* __restrict__ X, double* __restrict__ A2, const double* __restrict__ C, const double* __restrict__ focc,
+                           const double* __restrict__ eps, const int* __restrict__ occl, int n, int ne, int nocc, int kocc, int which) {
+  __shared__ double tile[32][33];
+  // 32 x 32 transposing tiles: block (bx over i, by over kk)
+  const int i0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int i = i0 + r, kk = k0 + tx;
+    double v = 0.0;
+    if (kk < nocc && i < n) v = C[(size_t)i * ne + occl[kk]];
+    tile[r][tx] = v;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int kk = k0 + r, i = i0 + tx;
+    if (kk < kocc) {
+      const double cv = tile[tx][r];
+      double w = 0.0;
+      if (kk < nocc) {
+        const int k = occl[kk];
+        w = which == 0 ? sqrt(focc[k]) : focc[k] * eps[k];
+      }
+      X[(size_t)kk * ne + i] = w * cv;
+      if (which == 1) A2[(size_t)kk * ne + i] = cv;
+    }
+  }
+}
+
+// Mulliken populations and orbital-resolved H0 energies: one warp per row of P (wavefunction/mulliken.py)
+__global__ void kl_mulliken(const double* __restrict__ P, const double* __restrict__ S, const double* __restrict__ H0,
+                            const double* __restrict__ n0, double* __restrict__ q, double* __restrict__ eorb, int n, int ne) {
+  const int lane = threadIdx.x & 31;
+  const int mu = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (mu >= n) return;
+  const double* pr = P + (size_t)mu * ne;
+  const double* sr = S + (size_t)mu * n;
+  const double* hr = H0 + (size_t)mu * n;
+  double pop = 0.0, e = 0.0;
+  for (int nu = lane; nu < n; nu += 32) {
+    const double p = pr[nu];
+    pop = fma(p, sr[nu], pop);
+    e = fma(p, hr[nu], e);
+  }
+  pop = warp_sum(pop);
+  e = warp_sum(e);
+  if (lane == 0) {
+    q[mu] = n0[mu] - pop;
+    eorb[mu] = e;
+  }
+}
+
+// ---- fp64 tensor-core GEMM  Out[i][j] = sum_k L[k][i] R[k][j]  (all ld = ne, ne % 128 == 0, K % 16 == 0) ------------
+// 128 x 128 tile per CTA, 16 warps with 32 x 32 warp tiles (4 x 4 DMMA tiles), K chunks of 16 double buffered through
+// shared memory with register staging of the next chunk.
+__global__ void __launch_bounds__(NT, 1)
+kl_gemm_tn(const double* __restrict__ L, const double* __restrict__ R, double* __restrict__ Out, int ld, int K) {
+  extern __shared__ double gsm[];
+  double* Ls = gsm;                  // [2][GK][GLD]
+  double* Rs = gsm + 2 * GK * GLD;   // [2][GK][GLD]
+  const int i0 = blockIdx.y * GT, j0 = blockIdx.x * GT;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, tg = lane & 3;
+  const int wi = (warp >> 2) * 32, wj = (warp & 3) * 32;
+  // staging: thread -> (row = t / 32, 4 consecutive columns)
+  const int srow = threadIdx.x >> 5, scol = (threadIdx.x & 31) * 4;
+  double d[4][4][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) d[a][b][0] = d[a][b][1] = 0.0;
+  double2 l0, l1, r0, r1;
+  auto gload = [&](int k0) {
+    const double* lp = L + (size_t)(k0 + srow) * ld + i0 + scol;
+    const double* rp = R + (size_t)(k0 + srow) * ld + j0 + scol;
+    l0 = *reinterpret_cast<const double2*>(lp); l1 = *reinterpret_cast<const double2*>(lp + 2);
+    r0 = *reinterpret_cast<const double2*>(rp); r1 = *reinterpret_cast<const double2*>(rp + 2);
+  };
+  auto sstore = [&](int buf) {
+    double* lp = Ls + (buf * GK + srow) * GLD + scol;
+    double* rp = Rs + (buf * GK + srow) * GLD + scol;
+    *reinterpret_cast<double2*>(lp) = l0; *reinterpret_cast<double2*>(lp + 2) = l1;
+    *reinterpret_cast<double2*>(rp) = r0; *reinterpret_cast<double2*>(rp + 2) = r1;
+  };
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  const int nchunk = K / GK;
+  for (int ch = 0; ch < nchunk; ++ch) {
+    const int buf = ch & 1;
+    if (ch + 1 < nchunk) gload((ch + 1) * GK);
+    const double* lb = Ls + buf * GK * GLD;
+    const double* rb = Rs + buf * GK * GLD;
+#pragma unroll
+    for (int k4 = 0; k4 < GK / 4; ++k4) {
+      double a[4], b[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        a[t] = lb[(4 * k4 + tg) * GLD + wi + 8 * t + g];
+        b[t] = rb[(4 * k4 + tg) * GLD + wj + 8 * t + g];
+      }
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) dmma884(d[mt][nt][0], d[mt][nt][1], a[mt], b[nt]);
+    }
+    if (ch + 1 < nchunk) sstore(buf ^ 1);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      double* o = Out + (size_t)(i0 + wi + 8 * mt + g) * ld + j0 + wj + 8 * nt + 2 * tg;
+      *reinterpret_cast<double2*>(o) = make_double2(d[mt][nt][0], d[mt][nt][1]);
+    }
+}
+
+// ---- two-level block Jacobi ------------------------------------------------------------------------------------------
+
+// global index of local index l (0..63) of the outer block pair (I, J)
+XTB_DEV int op_index(int I, int J, int l) { return (l < OB ? I * OB : J * OB - OB) + l; }
+
+// round-robin pairing of nblk blocks (nblk even): pair w of round r
+XTB_DEV void rr_pair(int nblk, int r, int w, int& I, int& J) {
+  if (w == 0) { I = r; J = nblk - 1; }
+  else {
+    I = (r + w) % (nblk - 1);
+    J = (r - w + 2 * (nblk - 1)) % (nblk - 1);
+  }
+  if (I > J) { const int t = I; I = J; J = t; }
+}
+
+constexpr int SUB_MAT = OP * SLD;  // doubles of a 64 x 68 shared-memory matrix
+constexpr int SUB_NBP = OP / JB2;  // block pairs of the in-CTA solver on a 64 x 64 sub-problem
+constexpr int SUB_SMEM = (2 * SUB_MAT + SUB_NBP * JB2 * QLD + NGRP * (JB2 * MLD + 48) + 32 + 2 * SUB_NBP) * 8;
+
+// One CTA per outer block pair: 64 x 64 sub-problem on the diagonal tile, one in-CTA Jacobi sweep, Q -> global.
+__global__ void __launch_bounds__(NT, 1)
+kl_jacobi_sub(const double* __restrict__ A, double* __restrict__ Qs, int* __restrict__ bij, int ne, int r, double tol) {
+  extern __shared__ double ssm[];
+  double* As = ssm;
+  double* Vs = ssm + SUB_MAT;
+  Ctx c;
+  c.ne = OP; c.ld = SLD; c.n = OP; c.np = OP / 2;
+  double* p = ssm + 2 * SUB_MAT;
+  c.jq = p; p += SUB_NBP * JB2 * QLD;
+  c.jm = p; p += NGRP * JB2 * MLD;
+  c.jr = p; p += NGRP * 48;
+  c.red = p; p += 32;
+  c.pp = (int*)p;
+  c.status = 0; c.sweeps = 0;
+  const int w = blockIdx.x, nblk = ne / OB;
+  int I, J;
+  rr_pair(nblk, r, w, I, J);
+  for (int t = threadIdx.x; t < OP * OP; t += NT) {
+    const int a = t >> 6, b = t & 63;
+    As[a * SLD + b] = A[(size_t)op_index(I, J, a) * ne + op_index(I, J, b)];
+    Vs[a * SLD + b] = (a == b) ? 1.0 : 0.0;
+  }
+  if (threadIdx.x == 0) { bij[2 * w] = I; bij[2 * w + 1] = J; }
+  __syncthreads();
+  jacobi<true, true>(c, As, Vs, OP, tol, 1);
+  __syncthreads();
+  double* Q = Qs + (size_t)w * OP * OP;
+  for (int t = threadIdx.x; t < OP * OP; t += NT) Q[t] = Vs[(t >> 6) * SLD + (t & 63)];
+}
+
+constexpr int PASS_SMEM = 3 * SUB_MAT * 8;
+
+// Apply the accumulated rotations of one outer round: A <- Q^T A Q (tiles P >= R, mirrored) and V <- V Q.
+__global__ void __launch_bounds__(NT, 2)
+kl_jacobi_pass(double* __restrict__ A, double* __restrict__ V, const double* __restrict__ Qs, const int* __restrict__ bij, int ne, int nbp) {
+  extern __shared__ double psm[];
+  double* B0 = psm;
+  double* B1 = psm + SUB_MAT;
+  double* B2 = psm + 2 * SUB_MAT;
+  const int nfused = nbp * (nbp + 1) / 2;
+  const int u = blockIdx.x;
+  if (u < nfused) {
+    int P = (int)((sqrtf(8.0f * (float)u + 1.0f) - 1.0f) * 0.5f);
+    while ((P + 1) * (P + 2) / 2 <= u) ++P;
+    while (P * (P + 1) / 2 > u) --P;
+    const int R = u - P * (P + 1) / 2;
+    const int IP = bij[2 * P], JP = bij[2 * P + 1], IR = bij[2 * R], JR = bij[2 * R + 1];
+    const double* QP = Qs + (size_t)P * OP * OP;
+    const double* QR = Qs + (size_t)R * OP * OP;
+    // B0[k][i] = A[R_k][P_i] (= A[P_i][R_k], A symmetric), B1 = Q_R
+    for (int t = threadIdx.x; t < OP * OP; t += NT) {
+      const int k = t >> 6, i = t & 63;
+      B0[k * SLD + i] = A[(size_t)op_index(IR, JR, k) * ne + op_index(IP, JP, i)];
+      B1[k * SLD + i] = QR[t];
+    }
+    __syncthreads();
+    gemm_tn<true, true>(OP, OP, B0, B1, SLD, B2, SLD, OP);  // T = A_PR Q_R
+    for (int t = threadIdx.x; t < OP * OP; t += NT) B1[(t >> 6) * SLD + (t & 63)] = QP[t];
+    __syncthreads();
+    gemm_tn<true, true>(OP, OP, B1, B2, SLD, B0, SLD, OP);  // B' = Q_P^T T
+    for (int t = threadIdx.x; t < OP * OP; t += NT) {
+      const int i = t >> 6, j = t & 63;
+      A[(size_t)op_index(IP, JP, i) * ne + op_index(IR, JR, j)] = B0[i * SLD + j];
+    }
+    if (P != R) {
+      for (int t = threadIdx.x; t < OP * OP; t += NT) {
+        const int j = t >> 6, i = t & 63;
+        A[(size_t)op_index(IR, JR, j) * ne + op_index(IP, JP, i)] = B0[i * SLD + j];
+      }
+    }
+  } else {
+    const int rem = u - nfused;
+    const int k = rem % nbp, rt = rem / nbp;
+    const int I = bij[2 * k], J = bij[2 * k + 1];
+    const double* Q = Qs + (size_t)k * OP * OP;
+    // B0[c][i] = V[64 rt + i][idx_c], B1 = Q
+    for (int t = threadIdx.x; t < OP * OP; t += NT) {
+      const int i = t >> 6, cc = t & 63;
+      B0[cc * SLD + i] = V[(size_t)(rt * OP + i) * ne + op_index(I, J, cc)];
+      B1[i * SLD + cc] = Q[t];
+    }
+    __syncthreads();
+    gemm_tn<true, true>(OP, OP, B0, B1, SLD, B2, SLD, OP);
+    for (int t = threadIdx.x; t < OP * OP; t += NT) {
+      const int i = t >> 6, j = t & 63;
+      V[(size_t)(rt * OP + i) * ne + op_index(I, J, j)] = B2[i * SLD + j];
+    }
+  }
+}
+
+// ---- single-CTA vector stages (reuse the device functions of the batch kernel) ----------------------------------------
+enum Phase { PH_INIT = 0, PH_FERMI = 1, PH_POT = 2, PH_MIX = 3, PH_COPYV = 4, PH_EMIT = 5 };
+
+__global__ void __launch_bounds__(NT, 1)
+kl_vec(int phase, const xtb_batch b, const xtb_scf_opts o, int m, const double* __restrict__ S, const double* __restrict__ H0,
+       const double* __restrict__ gamma, const double* __restrict__ nel_ab, const double* __restrict__ q0_at, double* __restrict__ work,
+       double* __restrict__ q_orb, double* __restrict__ q_sh, double* __restrict__ q_at, double* __restrict__ v_orb,
+       double* __restrict__ e_atom, double* __restrict__ fenergy, double* __restrict__ emo, double* __restrict__ occ,
+       int32_t* __restrict__ iterations, int32_t* __restrict__ status, int iters) {
+  Ctx c;
+  large_ctx(c, b, m, work, o.generations, S, H0, gamma);
+  const Layout l = layout(c.n, c.ns, c.na, o.generations);
+  LargeState* st = reinterpret_cast<LargeState*>(work + l.state);
+  const int n = c.n;
+  if (phase == PH_INIT) {
+    for (int mu = threadIdx.x; mu < n; mu += NT) {
+      const int sh = c.ao_sh[mu];
+      const int a = c.sh_atom[sh];
+      const double deg = (double)(2 * b.sh_l[c.s0 + sh] + 1);
+      c.n0[mu] = b.sh_par[(size_t)(c.s0 + sh) * XTB_SHPAR + XTB_SH_REFOCC] / deg;   // scf/iterator.py:147-170
+      c.q[mu] = q0_at[c.a0 + a] / (double)c.at_nsh[a] / deg;                          // scf/guess.py:122-182
+    }
+    if (threadIdx.x == 0) {
+      st->g = 0.0; st->off = 0.0; st->mixer_step = 0; st->mixer_head = 0; st->status = 0; st->sweeps = 0; st->nocc = 0;
+      st->converged = 0;
+    }
+    __syncthreads();
+    potential(c, c.q, c.v);
+  } else if (phase == PH_FERMI) {
+    for (int k = threadIdx.x; k < n; k += NT) c.eps[k] = c.A[(size_t)k * c.ld + k];
+    __syncthreads();
+    const double g = fermi_fill(c, nel_ab[2 * m], nel_ab[2 * m + 1], o);
+    if (threadIdx.x == 0) {
+      int no = 0;
+      for (int k = 0; k < n; ++k)
+        if (c.focc[k] > 0.0) c.occl[no++] = k;
+      c.occl[n] = no;
+      st->nocc = no;
+      st->g = g;
+      st->status |= c.status;
+    }
+  } else if (phase == PH_POT) {
+    potential(c, c.q, c.vnew);
+  } else if (phase == PH_MIX) {
+    Mixer mx;
+    mx.step = st->mixer_step;
+    mx.head = st->mixer_head;
+    __syncthreads();
+    const bool conv = mix(c, mx, o, c.cs);
+    if (threadIdx.x == 0) {
+      st->mixer_step = mx.step;
+      st->mixer_head = mx.head;
+      st->converged = conv ? 1 : 0;
+    }
+  } else if (phase == PH_COPYV) {
+    for (int k = threadIdx.x; k < n; k += NT) c.v[k] = c.vnew[k];
+  } else if (phase == PH_EMIT) {
+    c.status = st->status;
+    c.sweeps = st->sweeps;
+    emit_results(c, b, m, st->g, iters, q_orb, q_sh, q_at, v_orb, e_atom, fenergy, emo, occ, iterations, status);
+  }
+}
+
+template <typename F>
+int set_smem(F f, int bytes) {
+  cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+}  // namespace
+
+extern "C" int64_t xtb_scf_large_workspace_bytes(int32_t nao, int32_t nsh, int32_t nat, int32_t generations) {
+  if (nao <= 0 || nsh <= 0 || nat <= 0 || generations < 1) return -1;
+  return (int64_t)layout(nao, nsh, nat, generations).total * 8 + 256;
+}
+
+// SCF of molecule `mol` of the batch on the whole device (host-driven; synchronises `stream`).
+extern "C" int xtb_scf_run_large(const xtb_batch* b, const xtb_scf_opts* o, int32_t mol, int32_t nao, int32_t nsh, int32_t nat,
+                                 const double* S, const double* H0, const double* gamma, const double* nel_ab, const double* q0_at,
+                                 void* work_, double* q_orb, double* q_sh, double* q_at, double* v_orb, double* e_atom, double* fenergy,
+                                 double* emo, double* occ, int32_t* iterations, int32_t* status, double* P, double* W,
+                                 int64_t mat_off, void* stream) {
+  if (!b || !o || !S || !H0 || !gamma || !nel_ab || !q0_at || !work_ || !q_orb || !q_sh || !q_at || !v_orb || !e_atom || !fenergy ||
+      !emo || !occ || !iterations || !status)
+    return -1;
+  if (o->want_density && (!P || !W)) return -1;
+  if (o->generations > 5 || o->generations < 1) return -3;
+  if (mol < 0 || mol >= b->nb) return -1;
+  cudaStream_t st = (cudaStream_t)stream;
+  double* work = (double*)work_;
+  const Layout l = layout(nao, nsh, nat, o->generations);
+  const int n = nao, ne = l.ne, nbp = l.nbp, nblk = ne / OB;
+  double *C = work + l.C, *A = work + l.A, *X = work + l.X, *Qs = work + l.Q;
+  int* bij = (int*)(work + l.bij);
+  LargeState* dst = reinterpret_cast<LargeState*>(work + l.state);
+  const double* Sm = S + mat_off;
+  const double* Hm = H0 + mat_off;
+  double* vecp = work + l.vec;
+  const int nmx = n + 2;
+  double *eps = vecp, *focc = vecp + 2 * (size_t)nmx, *v = vecp + 3 * (size_t)nmx, *q = vecp + 5 * (size_t)nmx, *n0 = vecp + 6 * (size_t)nmx,
+         *eorb = vecp + 7 * (size_t)nmx;
+  const int* occl = (const int*)(vecp + 8 * (size_t)nmx + 2 * (size_t)nsh + nat + 32 + 36);
+
+  static bool configured = false;
+  if (!configured) {
+    int e = set_smem(kl_gemm_tn, 4 * GK * GLD * 8);
+    if (!e) e = set_smem(kl_jacobi_sub, SUB_SMEM);
+    if (!e) e = set_smem(kl_jacobi_pass, PASS_SMEM);
+    if (e) return e;
+    configured = true;
+  }
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int ew_grid = 4 * n_sm;  // elementwise kernels: grid-stride
+  LargeState hs;
+  auto read_state = [&]() -> int {
+    cudaError_t e = cudaMemcpyAsync(&hs, dst, sizeof(LargeState), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaStreamSynchronize(st);
+    return e == cudaSuccess ? 0 : (int)e;
+  };
+  auto vec = [&](int phase, int iters) {
+    kl_vec<<<1, NT, 0, st>>>(phase, *b, *o, mol, S, H0, gamma, nel_ab, q0_at, work, q_orb, q_sh, q_at, v_orb, e_atom, fenergy, emo, occ,
+                             iterations, status, iters);
+  };
+  auto gemm = [&](const double* L, const double* R, double* Out, int K) {
+    kl_gemm_tn<<<dim3(ne / GT, ne / GT), NT, 4 * GK * GLD * 8, st>>>(L, R, Out, ne, K);
+  };
+  int total_sweeps = 0, hstatus = 0;
+  // Jacobi on (Am, Vm) until max |off-diagonal| <= tol
+  auto jacobi_large = [&](double* Am, double* Vm, double tol, int maxsweeps) -> int {
+    const int npass = nbp * (nbp + 1) / 2 + (ne / OP) * nbp;
+    for (int sweep = 0;; ++sweep) {
+      cudaMemsetAsync(&dst->off, 0, sizeof(double), st);
+      kl_offmax<<<ew_grid, 256, 0, st>>>(Am, ne, dst);
+      if (int e = read_state()) return e;
+      if (hs.off <= tol) return 0;
+      if (sweep >= maxsweeps) { hstatus |= XTB_STATUS_JACOBI_NOT_CONVERGED; return 0; }
+      ++total_sweeps;
+      for (int r = 0; r < nblk - 1; ++r) {
+        kl_jacobi_sub<<<nbp, NT, SUB_SMEM, st>>>(Am, Qs, bij, ne, r, tol);
+        kl_jacobi_pass<<<npass, NT, PASS_SMEM, st>>>(Am, Vm, Qs, bij, ne, nbp);
+      }
+    }
+  };
+  // one SCF map evaluation v -> q -> vnew
+  auto fcn = [&](double jtol) -> int {
+    kl_fock<<<ew_grid, 256, 0, st>>>(A, Hm, Sm, v, n, ne);
+    gemm(A, C, X, ne);  // X = F C (F symmetric)
+    gemm(C, X, A, ne);  // A = C^T X
+    kl_symmetrize<<<ew_grid, 256, 0, st>>>(A, n, ne);
+    if (int e = jacobi_large(A, C, jtol, o->jacobi_max_sweeps)) return e;
+    vec(PH_FERMI, 0);
+    if (int e = read_state()) return e;
+    const int nocc = hs.nocc, kocc = (nocc + GK - 1) / GK * GK;
+    if (kocc > 0) {
+      kl_build_y<<<dim3(ne / 32, (kocc + 31) / 32), 256, 0, st>>>(X, nullptr, C, focc, eps, occl, n, ne, nocc, kocc, 0);
+      gemm(X, X, A, kocc);  // P = Y^T Y
+    } else {
+      cudaMemsetAsync(A, 0, (size_t)ne * ne * 8, st);
+    }
+    kl_mulliken<<<(n + 7) / 8, 256, 0, st>>>(A, Sm, Hm, n0, q, eorb, n, ne);
+    vec(PH_POT, 0);
+    return launch_status();
+  };
+
+  // one Newton-Schulz step C <- C (3/2 I - 1/2 C^T S C), see reorthonormalize() in xtb_scf.cu
+  auto reorthonormalize = [&]() {
+    kl_load<<<ew_grid, 256, 0, st>>>(A, Sm, n, ne, 0.0);
+    gemm(A, C, X, ne);  // X = S C
+    gemm(C, X, A, ne);  // A = C^T S C
+    kl_ns_factor<<<ew_grid, 256, 0, st>>>(A, ne);
+    kl_transpose<<<dim3(ne / 32, ne / 32), 256, 0, st>>>(X, C, ne);
+    gemm(X, A, C, ne);  // C = C M
+  };
+
+  vec(PH_INIT, 0);
+  // start basis from the eigendecomposition of S (pad diagonal 1 keeps the padded matrix positive definite)
+  kl_load<<<ew_grid, 256, 0, st>>>(A, Sm, n, ne, 1.0);
+  kl_load<<<ew_grid, 256, 0, st>>>(C, Sm, 0, ne, 1.0);  // identity
+  if (int e = jacobi_large(A, C, o->jacobi_tol, 2 * o->jacobi_max_sweeps)) return e;
+  kl_scale_cols<<<ew_grid, 256, 0, st>>>(C, A, n, ne, dst);
+  reorthonormalize();
+
+  int iters = 1;
+  bool converged = true;
+  if (int e = fcn(o->maxiter > 0 ? o->jacobi_tol_iter : o->jacobi_tol)) return e;
+  if (o->maxiter > 0) {
+    converged = false;
+    vec(PH_MIX, 0);  // mix_guess (unrolling/default.py:93-94); convergence is not tested here
+    for (int it = 0; it < o->maxiter; ++it) {
+      if (int e = fcn(o->jacobi_tol_iter)) return e;
+      ++iters;
+      vec(PH_MIX, 0);
+      if (int e = read_state()) return e;
+      if (hs.converged) { converged = true; break; }
+    }
+    vec(PH_COPYV, 0);  // converged_to_charges: one more solve with the un-mixed potential
+    reorthonormalize();
+    if (int e = fcn(o->jacobi_tol)) return e;
+  }
+  if (!converged) hstatus |= XTB_STATUS_SCF_NOT_CONVERGED;
+  // fold the host-side status / sweep count into the device state, then emit
+  if (int e = read_state()) return e;
+  hs.status |= hstatus;
+  hs.sweeps = total_sweeps;
+  cudaMemcpyAsync(dst, &hs, sizeof(LargeState), cudaMemcpyHostToDevice, st);
+  vec(PH_EMIT, iters);
+  if (o->want_density) {
+    kl_pack<<<ew_grid, 256, 0, st>>>(P + mat_off, A, n, ne);
+    const int nocc = hs.nocc, kocc = (nocc + GK - 1) / GK * GK;
+    if (kocc > 0) {
+      // W = C diag(f eps) C^T = Y1^T Y2 (X, A buffers) -> C buffer (no longer needed)
+      kl_build_y<<<dim3(ne / 32, (kocc + 31) / 32), 256, 0, st>>>(X, A, C, focc, eps, occl, n, ne, nocc, kocc, 1);
+      // C is read by kl_build_y and overwritten by the GEMM: same stream, ordered
+      gemm(X, A, C, kocc);
+      kl_pack<<<ew_grid, 256, 0, st>>>(W + mat_off, C, n, ne);
+    } else {
+      cudaMemsetAsync(W + mat_off, 0, (size_t)n * n * 8, st);
+    }
+  }
+  cudaError_t e = cudaStreamSynchronize(st);  // hs lives on this stack frame
+  if (e != cudaSuccess) return (int)e;
+  return launch_status();
+}

@@ -89,7 +89,8 @@ typedef struct xtb_scf_opts {
   int32_t soft_start;       /* 1 */
   int32_t fermi_maxiter;    /* 200 */
   int32_t want_density;     /* 1: write P, W (needed by xtb_grad_bwd) */
-  int32_t use_smem;         /* 1: matrices in shared memory (host checks capacity) */
+  int32_t use_smem;         /* kernel variant: 1 = C, A, X matrices in shared memory; 2 = hybrid (A in shared memory, C and X in the
+                               workspace); 0 = all in the workspace.  The host checks capacity (xtb_scf_smem_bytes_mode) */
   int32_t jacobi_max_sweeps;/* 30 */
   double damp;              /* 0.5 */
   double damp_init;         /* 0.1 */
@@ -137,9 +138,24 @@ int xtb_overlap_h0_fwd(const xtb_batch* b, const double* pos, const double* cn, 
 
 /* Bytes of workspace xtb_scf_run needs for this batch / option set. */
 int64_t xtb_scf_workspace_bytes(const xtb_batch* b, const xtb_scf_opts* o);
+/* Large-system SCF (BASELINE config 4, e.g. sh3 with 3104 AOs): molecule `mol` of the batch runs on the WHOLE device
+   as a sequence of grid-wide kernels (tensor-core GEMMs + two-level block Jacobi) driven from the host; synchronises
+   `stream`.  Same inputs / outputs / status bits as xtb_scf_run; `mat_off` = offset of the molecule in S/H0/P/W (doubles);
+   `work` holds xtb_scf_large_workspace_bytes(nao, nsh, nat, generations) bytes.  Replaces the same reference loop as
+   xtb_scf_run (scf/unrolling/default.py:64-137 with scf/base.py:818-907) for systems the one-CTA kernel cannot hold. */
+int64_t xtb_scf_large_workspace_bytes(int32_t nao, int32_t nsh, int32_t nat, int32_t generations);
+int xtb_scf_run_large(const xtb_batch* b, const xtb_scf_opts* o, int32_t mol, int32_t nao, int32_t nsh, int32_t nat, const double* S,
+                      const double* H0, const double* gamma, const double* nel_ab, const double* q0_at, void* work, double* q_orb,
+                      double* q_sh, double* q_at, double* v_orb, double* e_atom, double* fenergy, double* emo, double* occ,
+                      int32_t* iterations, int32_t* status, double* P, double* W, int64_t mat_off, void* stream);
+
 /* Dynamic shared memory the SCF kernel needs with use_smem=1 (host compares with the device limit). */
 int64_t xtb_scf_smem_bytes(const xtb_batch* b);
 int64_t xtb_scf_smem_bytes_for(int32_t nao_max, int32_t nsh_max, int32_t nat_max);
+/* Same for kernel variant `mode` (the use_smem values).  Variants 0 and 2 run two CTAs per SM when the launch has at
+   least 1.5 molecules per SM and this is at most XTB_SMEM_2CTA. */
+int64_t xtb_scf_smem_bytes_mode(int32_t mode, int32_t nao_max, int32_t nsh_max, int32_t nat_max);
+#define XTB_SMEM_2CTA (113 * 1024)
 
 /* The whole SCF (scf/iterator.py:51-144, scf/unrolling/default.py:71-136, scf/base.py:651-907,
  * mixer/anderson.py:163-317, wavefunction/filling.py:201-366): one CTA per molecule, no host round-trips.

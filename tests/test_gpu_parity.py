@@ -155,11 +155,15 @@ def test_global_memory_variant_matches_shared_memory_variant(mols):
     numbers, pos, chrg = _pack(mols, ["H2O", "CH4", "caffeine", "NO2"], dev)
     a = GFN1Calculator(numbers, opts=NODISP, device=dev, dtype=torch.float64)
     b = GFN1Calculator(numbers, opts=NODISP, device=dev, dtype=torch.float64)
-    assert a._use_smem == 1
+    c = GFN1Calculator(numbers, opts=NODISP, device=dev, dtype=torch.float64)
+    assert a._variants == [1]
     b._use_smem_override = 0
-    ea, eb = a.get_energy(pos, chrg), b.get_energy(pos, chrg)
+    c._use_smem_override = 2  # hybrid: only the A buffer in shared memory
+    ea, eb, ec = a.get_energy(pos, chrg), b.get_energy(pos, chrg), c.get_energy(pos, chrg)
     assert torch.allclose(ea, eb, rtol=0, atol=1e-11)
+    assert torch.allclose(ea, ec, rtol=0, atol=1e-11)
     assert torch.equal(a.get_iterations(), b.get_iterations())
+    assert torch.equal(a.get_iterations(), c.get_iterations())
 
 
 def test_large_molecule_global_path(mols):
@@ -169,7 +173,7 @@ def test_large_molecule_global_path(mols):
     dev = _dev()
     numbers, pos, chrg = _pack(mols, ["vancoh2"], dev)
     calc = GFN1Calculator(numbers, opts=NODISP, device=dev, dtype=torch.float64)
-    assert calc._use_smem == 0
+    assert calc._variants == [0]
     e = calc.get_energy(pos, chrg)
     r = _oracle(mols, "vancoh2")
     assert abs(float(e[0]) - r.energy) < E_TOL
@@ -279,16 +283,16 @@ def test_single_molecule_unbatched_shapes(mols):
     assert abs(float(e) - r.energy) < E_TOL
 
 
-def test_mixed_sizes_use_two_buckets(mols):
-    """Ragged batch (SURVEY 8a row 14 'culling'): small molecules run the shared-memory variant, large ones the
-    global-memory variant, results independent of the bucketing."""
+def test_mixed_sizes_use_three_buckets(mols):
+    """Ragged batch (SURVEY 8a row 14 'culling'): small molecules run the shared-memory variant, medium ones the
+    hybrid variant, large ones the global-memory variant; results independent of the bucketing."""
     from dxtb_b200 import GFN1Calculator
 
     dev = _dev()
-    names = ["H2O", "LYS_xao", "caffeine", "capsaicin", "CH4", "nicotine"]
+    names = ["H2O", "LYS_xao", "caffeine", "capsaicin", "CH4", "nicotine", "C60"]
     numbers, pos, chrg = _pack(mols, names, dev)
     calc = GFN1Calculator(numbers, opts=NODISP, device=dev, dtype=torch.float64)
-    assert sorted(bk["use_smem"] for bk in calc._buckets) == [0, 1]
+    assert calc._variants == [0, 1, 2]
     assert sum(bk["len"] for bk in calc._buckets) == len(names)
     p = pos.clone().requires_grad_(True)
     e = calc.get_energy(p, chrg)
@@ -428,3 +432,46 @@ def test_property_getters_match_oracle(mols):
         assert float(P[i, k:, :].abs().max()) == 0.0 if P.shape[1] > k else True
     # a C-H bond of caffeine has a Wiberg bond order close to one
     assert 0.8 < float(wbo[1].max()) < 2.2
+
+
+def test_large_system_path_matches_one_cta_path(mols, monkeypatch):
+    """vancoh2 (nao 550) through the multi-CTA large-system SCF (xtb_scf_run_large) and through the one-CTA kernel."""
+    from dxtb_b200 import GFN1Calculator
+
+    dev = _dev()
+    numbers, pos, chrg = _pack(mols, ["vancoh2", "H2O"], dev)
+    a = GFN1Calculator(numbers, opts=NODISP, device=dev, dtype=torch.float64)
+    monkeypatch.setenv("DXTB_B200_LARGE_MIN_NAO", "500")
+    b = GFN1Calculator(numbers, opts=NODISP, device=dev, dtype=torch.float64)
+    assert a._variants == [0, 1] and b._variants == [1, 3]
+    pa, pb = pos.clone().requires_grad_(True), pos.clone().requires_grad_(True)
+    ea, eb = a.get_energy(pa, chrg), b.get_energy(pb, chrg)
+    (ga,) = torch.autograd.grad(ea.sum(), pa)
+    (gb,) = torch.autograd.grad(eb.sum(), pb)
+    assert torch.allclose(ea, eb, rtol=0, atol=1e-10)
+    assert torch.equal(a.get_iterations(), b.get_iterations())
+    assert (ga - gb).abs().max() < 1e-8
+    assert (a.get_atomic_charges() - b.get_atomic_charges()).abs().max() < 1e-7
+    r = _oracle(mols, "vancoh2")
+    assert abs(float(eb[0]) - r.energy) < E_TOL
+
+
+def test_sh3_config4_against_oracle_fixture(mols):
+    """BASELINE config 4: sh3, 1027 atoms, nao 3104, energy + forces on one GPU through the large-system path,
+    against the oracle result committed in tests/golden/sh3_oracle.npz (tests/golden/make_sh3_oracle.py)."""
+    from dxtb_b200 import GFN1Calculator
+
+    dev = _dev()
+    from pathlib import Path
+
+    ref = np.load(Path(__file__).resolve().parent / "golden" / "sh3_oracle.npz")
+    numbers, pos, chrg = _pack(mols, ["ex_sh3"], dev)
+    calc = GFN1Calculator(numbers, opts=NODISP, device=dev, dtype=torch.float64)
+    assert calc._variants == [3]
+    p = pos.clone().requires_grad_(True)
+    e = calc.get_energy(p, chrg)
+    (g,) = torch.autograd.grad(e.sum(), p)
+    assert abs(float(e[0]) - float(ref["energy"])) < E_TOL
+    assert int(calc.get_iterations()[0]) == int(ref["iterations"])
+    assert np.abs(g[0].cpu().numpy() - ref["gradient"]).max() < F_TOL
+    assert np.abs(calc.get_atomic_charges()[0].cpu().numpy() - ref["q_atom"]).max() < Q_TOL

@@ -32,7 +32,7 @@ pos = positions.clone().requires_grad_(True)
 t = time.time()
 e = calc.get_energy(pos, chrg)
 torch.cuda.synchronize()
-print("forward time %.3fs" % (time.time() - t), "use_smem", calc._use_smem)
+print("forward time %.3fs" % (time.time() - t), "use_smem", calc._variants)
 ws = calc.cache["ws"]
 (g,) = torch.autograd.grad(e.sum(), pos)
 torch.cuda.synchronize()

@@ -23,6 +23,6 @@ def run(name, nb, forces=True):
             (g,) = torch.autograd.grad(e.sum(), p)
         torch.cuda.synchronize(); dt = time.perf_counter() - t0
     st = calc.cache["status"]
-    print(f"{name:10s} nb={nb:5d} nao={int(calc.desc.nao[0]):4d} smem={calc._use_smem} {dt*1e3:9.1f} ms  {nb/dt:9.1f} SP/s  iters {float(calc.get_iterations().float().mean()):.1f} sweeps {float((st>>8).float().mean()):.1f}")
+    print(f"{name:10s} nb={nb:5d} nao={int(calc.desc.nao[0]):4d} smem={calc._variants} {dt*1e3:9.1f} ms  {nb/dt:9.1f} SP/s  iters {float(calc.get_iterations().float().mean()):.1f} sweeps {float((st>>8).float().mean()):.1f}")
 for name, nb in [("caffeine", 1024), ("LYS_xao", 592), ("capsaicin", 592), ("C60", 296), ("vancoh2", 148)]:
     run(name, nb)
