@@ -61,6 +61,7 @@ EXPORTS = {
     "xtb_sizeof_scf_opts": (C.c_int, []),
     "xtb_geometry_fwd": (C.c_int, [_vp] * 6),
     "xtb_eeq_guess": (C.c_int, [_vp] * 6),
+    "xtb_eeq_guess_large": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int64, C.c_int64] + [_vp] * 5),
     "xtb_gamma_fwd": (C.c_int, [_vp] * 4),
     "xtb_overlap_h0_fwd": (C.c_int, [_vp] * 6),
     "xtb_scf_workspace_bytes": (C.c_int64, [_vp, _vp]),

@@ -80,6 +80,7 @@ class BatchDescriptor:
         self.mat_off = _excl_cumsum(nao * nao)
         self.gam_off = _excl_cumsum(nsh * nsh)
         self.eeq_off = _excl_cumsum((nat + 1) * (nat + 1))
+        self.eeq_large = [int(i) for i in np.flatnonzero(nat >= 256)]  # XTB_EEQ_LARGE_NAT (include/xtb_b200.h)
         self.nat_tot, self.nsh_tot, self.nao_tot = int(z.size), nsh_tot, nao_tot
         self.z = z
 

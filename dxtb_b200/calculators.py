@@ -116,6 +116,9 @@ class _SinglePoint(torch.autograd.Function):
         if calc.opts["guess"] == "eeq":
             eeq_work = torch.empty(int(d.struct.eeq_total) + 2 * (d.nat_tot + d.nb), dtype=torch.float64, device=d.device)
             _abi.check(lib.xtb_eeq_guess(d.ptr, pos.data_ptr(), chrg.data_ptr(), eeq_work.data_ptr(), ws.q0_at.data_ptr(), st), "xtb_eeq_guess")
+            for m in d.eeq_large:  # molecules the batched one-CTA LU skips (XTB_EEQ_LARGE_NAT)
+                _abi.check(lib.xtb_eeq_guess_large(d.ptr, m, int(d.nat[m]), int(d.at_off[m]), int(d.eeq_off[m]), pos.data_ptr(),
+                                                   chrg.data_ptr(), eeq_work.data_ptr(), ws.q0_at.data_ptr(), st), "xtb_eeq_guess_large")
         if "es2" not in excl:
             _abi.check(lib.xtb_gamma_fwd(d.ptr, pos.data_ptr(), ws.gamma.data_ptr(), st), "xtb_gamma_fwd")
         _abi.check(lib.xtb_overlap_h0_fwd(d.ptr, pos.data_ptr(), ws.cn.data_ptr(), ws.S.data_ptr(), ws.H0.data_ptr(), st), "xtb_overlap_h0_fwd")

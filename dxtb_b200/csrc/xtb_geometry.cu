@@ -102,6 +102,7 @@ __global__ void k_eeq(const xtb_batch b, const double* __restrict__ pos, const d
   __shared__ int s_piv;
   const int m = blockIdx.x;
   const int a0 = b.at_off[m], na = b.at_off[m + 1] - a0;
+  if (na >= XTB_EEQ_LARGE_NAT) return;  // solved by xtb_eeq_guess_large on the whole device
   const int n = na + 1;
   double* A = work + b.eeq_off[m];
   double* rhs = work + b.eeq_total + 2 * (size_t)(a0 + m);
@@ -198,6 +199,115 @@ __global__ void k_eeq(const xtb_batch b, const double* __restrict__ pos, const d
     __syncthreads();
   }
   for (int a = threadIdx.x; a < na; a += blockDim.x) qat[a0 + a] = x[a];
+}
+
+// ---------------------------------------------------------------------------------------------
+// EEQ guess of ONE large molecule (nat >= XTB_EEQ_LARGE_NAT) on the whole device: the same system and the same
+// elimination order as k_eeq, but every stage is a grid-wide kernel (the one-CTA LU needs 0.7 s for the 1028 x 1028
+// system of sh3).  Per column: one CTA finds the pivot and swaps the rows, then all CTAs eliminate.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_eeq_build(const xtb_batch b, int m, const double* __restrict__ pos, const double* __restrict__ chrg,
+                            double* __restrict__ work) {
+  const int a0 = b.at_off[m], na = b.at_off[m + 1] - a0;
+  const int n = na + 1;
+  double* A = work + b.eeq_off[m];
+  double* rhs = work + b.eeq_total + 2 * (size_t)(a0 + m);
+  const double* p = pos + 3 * (size_t)a0;
+  const double kcn = 7.5, cn_max = 8.0, cn_cut = 25.0;
+  const size_t gt = blockIdx.x * (size_t)blockDim.x + threadIdx.x, gs = (size_t)gridDim.x * blockDim.x;
+  for (size_t a = gt; a < (size_t)na; a += gs) {
+    const double* pa = b.at_par + (size_t)(a0 + a) * XTB_ATPAR;
+    double c = 0.0;
+    for (int j = 0; j < na; ++j) {
+      if (j == (int)a) continue;
+      const double d = safe_dist(p[3 * a] - p[3 * j], p[3 * a + 1] - p[3 * j + 1], p[3 * a + 2] - p[3 * j + 2]);
+      if (d <= cn_cut) {
+        const double r0 = pa[XTB_AT_RCOV] + b.at_par[(size_t)(a0 + j) * XTB_ATPAR + XTB_AT_RCOV];
+        c += 0.5 * (1.0 + erf(-kcn * (d / r0 - 1.0)));
+      }
+    }
+    c = log(1.0 + exp(cn_max)) - log(1.0 + exp(cn_max - c));
+    rhs[a] = -pa[XTB_AT_EEQ_CHI] + sqrt(fmax(c, kEps)) * pa[XTB_AT_EEQ_KCN];
+  }
+  if (gt == 0) rhs[na] = chrg[m];
+  for (size_t t = gt; t < (size_t)n * n; t += gs) {
+    const int i = (int)(t / n), j = (int)(t - (size_t)i * n);
+    double v;
+    if (i == na || j == na) {
+      v = (i == j) ? 0.0 : 1.0;
+    } else {
+      const double ri = b.at_par[(size_t)(a0 + i) * XTB_ATPAR + XTB_AT_EEQ_RAD];
+      if (i == j) {
+        v = b.at_par[(size_t)(a0 + i) * XTB_ATPAR + XTB_AT_EEQ_ETA] + sqrt(2.0 / kPi) / ri;
+      } else {
+        const double rj = b.at_par[(size_t)(a0 + j) * XTB_ATPAR + XTB_AT_EEQ_RAD];
+        const double d = safe_dist(p[3 * i] - p[3 * j], p[3 * i + 1] - p[3 * j + 1], p[3 * i + 2] - p[3 * j + 2]);
+        v = erf(d / sqrt(ri * ri + rj * rj)) / d;
+      }
+    }
+    A[t] = v;
+  }
+}
+
+// column k: partial pivot (first index wins on ties, as idamax) and row swap; one CTA
+__global__ void k_eeq_pivot(double* __restrict__ A, double* __restrict__ rhs, int n, int k) {
+  __shared__ double red[32];
+  __shared__ int redi[32];
+  __shared__ int s_piv;
+  double best = -1.0;
+  int bi = k;
+  for (int i = k + threadIdx.x; i < n; i += blockDim.x) {
+    const double v = fabs(A[(size_t)i * n + k]);
+    if (v > best) { best = v; bi = i; }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = best; redi[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double bb = red[0];
+    int ii = redi[0];
+    for (int w = 1; w < (int)((blockDim.x + 31) >> 5); ++w)
+      if (red[w] > bb || (red[w] == bb && redi[w] < ii)) { bb = red[w]; ii = redi[w]; }
+    s_piv = ii;
+  }
+  __syncthreads();
+  const int piv = s_piv;
+  if (piv != k) {
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+      const double t1 = A[(size_t)k * n + j];
+      A[(size_t)k * n + j] = A[(size_t)piv * n + j];
+      A[(size_t)piv * n + j] = t1;
+    }
+    if (threadIdx.x == 0) { const double t1 = rhs[k]; rhs[k] = rhs[piv]; rhs[piv] = t1; }
+  }
+}
+
+// eliminate column k from the rows below (4 rows per CTA, 64 threads per row), rhs carried along
+__global__ void k_eeq_eliminate(double* __restrict__ A, double* __restrict__ rhs, int n, int k) {
+  const int sub = threadIdx.x & 63;
+  const int i = k + 1 + blockIdx.x * 4 + (threadIdx.x >> 6);
+  if (i >= n) return;
+  const double f = A[(size_t)i * n + k] / A[(size_t)k * n + k];
+  const double* rk = A + (size_t)k * n;
+  double* ri = A + (size_t)i * n;
+  for (int j = k + 1 + sub; j < n; j += 64) ri[j] -= f * rk[j];
+  if (sub == 0) rhs[i] -= f * rhs[k];
+}
+
+__global__ void k_eeq_backsub(const double* __restrict__ A, double* __restrict__ rhs, double* __restrict__ x, int n,
+                              double* __restrict__ qat, int na) {
+  for (int i = n - 1; i >= 0; --i) {
+    const double xi = rhs[i] / A[(size_t)i * n + i];
+    __syncthreads();
+    if (threadIdx.x == 0) x[i] = xi;
+    for (int j = threadIdx.x; j < i; j += blockDim.x) rhs[j] -= A[(size_t)j * n + i] * xi;
+    __syncthreads();
+  }
+  for (int a = threadIdx.x; a < na; a += blockDim.x) qat[a] = x[a];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -393,6 +503,23 @@ extern "C" int xtb_eeq_guess(const xtb_batch* b, const double* pos, const double
   if (!b || !pos || !chrg || !work || !q_at) return -1;
   if (b->nb == 0) return 0;
   k_eeq<<<b->nb, 256, 0, (cudaStream_t)stream>>>(*b, pos, chrg, work, q_at);
+  return launch_status();
+}
+
+extern "C" int xtb_eeq_guess_large(const xtb_batch* b, int32_t mol, int32_t nat, int64_t at_off, int64_t eeq_off, const double* pos,
+                                   const double* chrg, double* work, double* q_at, void* stream) {
+  if (!b || !pos || !chrg || !work || !q_at || mol < 0 || mol >= b->nb || nat < 1) return -1;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = nat + 1;
+  double* A = work + eeq_off;
+  double* rhs = work + b->eeq_total + 2 * (size_t)(at_off + mol);
+  k_eeq_build<<<592, 256, 0, st>>>(*b, mol, pos, chrg, work);
+  for (int k = 0; k < n; ++k) {
+    k_eeq_pivot<<<1, 256, 0, st>>>(A, rhs, n, k);
+    const int rem = n - k - 1;
+    if (rem > 0) k_eeq_eliminate<<<(rem + 3) / 4, 256, 0, st>>>(A, rhs, n, k);
+  }
+  k_eeq_backsub<<<1, 256, 0, st>>>(A, rhs, rhs + n, n, q_at + at_off, nat);
   return launch_status();
 }
 

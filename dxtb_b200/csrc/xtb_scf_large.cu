@@ -365,63 +365,120 @@ kl_jacobi_sub(const double* __restrict__ A, double* __restrict__ Qs, int* __rest
   for (int t = threadIdx.x; t < OP * OP; t += NT) Q[t] = Vs[(t >> 6) * SLD + (t & 63)];
 }
 
-constexpr int PASS_SMEM = 3 * SUB_MAT * 8;
+constexpr int PASS_SMEM = 2 * SUB_MAT * 8;
 
-// Apply the accumulated rotations of one outer round: A <- Q^T A Q (tiles P >= R, mirrored) and V <- V Q.
-__global__ void __launch_bounds__(NT, 2)
+// 16-byte asynchronous copy global -> shared (LDGSTS), no register staging
+XTB_DEV void cp_async16(double* smem_dst, const double* gmem_src) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem_src) : "memory");
+}
+XTB_DEV void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory"); }
+
+// dst[r][c] (ld SLD) = src[rowbase(r)][colbase(c)] for a 64 x 64 tile whose rows / columns are two 32-blocks (I, J)
+XTB_DEV void load_tile_async(double* dst, const double* __restrict__ src, int ne, int rI, int rJ, int cI, int cJ) {
+  for (int t = threadIdx.x; t < OP * OP / 2; t += NT) {
+    const int r = t >> 5, c = (t & 31) << 1;
+    cp_async16(dst + r * SLD + c, src + (size_t)op_index(rI, rJ, r) * ne + op_index(cI, cJ, c));
+  }
+}
+XTB_DEV void load_q_async(double* dst, const double* __restrict__ Q) {
+  for (int t = threadIdx.x; t < OP * OP / 2; t += NT) {
+    const int r = t >> 5, c = (t & 31) << 1;
+    cp_async16(dst + r * SLD + c, Q + r * OP + c);
+  }
+}
+
+// 16 x 16 warp tile of a 64 x 64 x 64 product with both operands in shared memory (ld SLD, conflict-free either way):
+//   LT == false: d[i][j] = sum_k L[k][i] R[k][j];   LT == true: d[i][j] = sum_k L[i][k] R[k][j]
+template <bool LT>
+XTB_DEV void tile_gemm64(const double* __restrict__ L, const double* __restrict__ R, int i0, int j0, int g, int tg, double (&d)[2][2][2]) {
+  XTB_ASSUME_SHARED(L); XTB_ASSUME_SHARED(R);
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) d[a][b][0] = d[a][b][1] = 0.0;
+#pragma unroll 4
+  for (int k0 = 0; k0 < OP; k0 += 4) {
+    double a0, a1;
+    if (LT) { a0 = L[(i0 + g) * SLD + k0 + tg]; a1 = L[(i0 + 8 + g) * SLD + k0 + tg]; }
+    else { a0 = L[(k0 + tg) * SLD + i0 + g]; a1 = L[(k0 + tg) * SLD + i0 + 8 + g]; }
+    const double b0 = R[(k0 + tg) * SLD + j0 + g], b1 = R[(k0 + tg) * SLD + j0 + 8 + g];
+    dmma884(d[0][0][0], d[0][0][1], a0, b0);
+    dmma884(d[0][1][0], d[0][1][1], a0, b1);
+    dmma884(d[1][0][0], d[1][0][1], a1, b0);
+    dmma884(d[1][1][0], d[1][1][1], a1, b1);
+  }
+}
+
+// Apply the accumulated rotations of one outer round: A <- Q^T A Q (tiles P >= R, mirrored) and V <- V Q.  One 64 x 64
+// tile per CTA, 16 warps x (16 x 16) DMMA warp tiles, operands staged with cp.async into two shared-memory buffers
+// (3 CTAs per SM overlap the loads of one tile with the tensor-core work of the others); results go from the
+// accumulators straight to global memory.
+__global__ void __launch_bounds__(NT, 3)
 kl_jacobi_pass(double* __restrict__ A, double* __restrict__ V, const double* __restrict__ Qs, const int* __restrict__ bij, int ne, int nbp) {
   extern __shared__ double psm[];
   double* B0 = psm;
   double* B1 = psm + SUB_MAT;
-  double* B2 = psm + 2 * SUB_MAT;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, tg = lane & 3;
+  const int i0 = (warp >> 2) << 4, j0 = (warp & 3) << 4;
   const int nfused = nbp * (nbp + 1) / 2;
   const int u = blockIdx.x;
+  double d[2][2][2];
   if (u < nfused) {
     int P = (int)((sqrtf(8.0f * (float)u + 1.0f) - 1.0f) * 0.5f);
     while ((P + 1) * (P + 2) / 2 <= u) ++P;
     while (P * (P + 1) / 2 > u) --P;
     const int R = u - P * (P + 1) / 2;
     const int IP = bij[2 * P], JP = bij[2 * P + 1], IR = bij[2 * R], JR = bij[2 * R + 1];
-    const double* QP = Qs + (size_t)P * OP * OP;
-    const double* QR = Qs + (size_t)R * OP * OP;
-    // B0[k][i] = A[R_k][P_i] (= A[P_i][R_k], A symmetric), B1 = Q_R
-    for (int t = threadIdx.x; t < OP * OP; t += NT) {
-      const int k = t >> 6, i = t & 63;
-      B0[k * SLD + i] = A[(size_t)op_index(IR, JR, k) * ne + op_index(IP, JP, i)];
-      B1[k * SLD + i] = QR[t];
-    }
+    // B0[i][k] = A[P_i][R_k], B1 = Q_R
+    load_tile_async(B0, A, ne, IP, JP, IR, JR);
+    load_q_async(B1, Qs + (size_t)R * OP * OP);
+    cp_async_wait_all();
     __syncthreads();
-    gemm_tn<true, true>(OP, OP, B0, B1, SLD, B2, SLD, OP);  // T = A_PR Q_R
-    for (int t = threadIdx.x; t < OP * OP; t += NT) B1[(t >> 6) * SLD + (t & 63)] = QP[t];
+    tile_gemm64<true>(B0, B1, i0, j0, g, tg, d);  // T = A_PR Q_R
     __syncthreads();
-    gemm_tn<true, true>(OP, OP, B1, B2, SLD, B0, SLD, OP);  // B' = Q_P^T T
-    for (int t = threadIdx.x; t < OP * OP; t += NT) {
-      const int i = t >> 6, j = t & 63;
-      A[(size_t)op_index(IP, JP, i) * ne + op_index(IR, JR, j)] = B0[i * SLD + j];
-    }
-    if (P != R) {
-      for (int t = threadIdx.x; t < OP * OP; t += NT) {
-        const int j = t >> 6, i = t & 63;
-        A[(size_t)op_index(IR, JR, j) * ne + op_index(IP, JP, i)] = B0[i * SLD + j];
+    load_q_async(B1, Qs + (size_t)P * OP * OP);
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+        *reinterpret_cast<double2*>(B0 + (i0 + 8 * a + g) * SLD + j0 + 8 * b + 2 * tg) = make_double2(d[a][b][0], d[a][b][1]);
+    cp_async_wait_all();
+    __syncthreads();
+    tile_gemm64<false>(B1, B0, i0, j0, g, tg, d);  // B' = Q_P^T T
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int gi = op_index(IP, JP, i0 + 8 * a + g);
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int gj = op_index(IR, JR, j0 + 8 * b + 2 * tg);  // 2 tg and 2 tg + 1 lie in the same 32-block
+        *reinterpret_cast<double2*>(A + (size_t)gi * ne + gj) = make_double2(d[a][b][0], d[a][b][1]);
+        if (P != R) {  // mirror
+          A[(size_t)gj * ne + gi] = d[a][b][0];
+          A[(size_t)(gj + 1) * ne + gi] = d[a][b][1];
+        }
       }
     }
   } else {
     const int rem = u - nfused;
     const int k = rem % nbp, rt = rem / nbp;
     const int I = bij[2 * k], J = bij[2 * k + 1];
-    const double* Q = Qs + (size_t)k * OP * OP;
-    // B0[c][i] = V[64 rt + i][idx_c], B1 = Q
-    for (int t = threadIdx.x; t < OP * OP; t += NT) {
-      const int i = t >> 6, cc = t & 63;
-      B0[cc * SLD + i] = V[(size_t)(rt * OP + i) * ne + op_index(I, J, cc)];
-      B1[i * SLD + cc] = Q[t];
+    // B0[i][c] = V[64 rt + i][idx_c], B1 = Q
+    for (int t = threadIdx.x; t < OP * OP / 2; t += NT) {
+      const int r = t >> 5, c = (t & 31) << 1;
+      cp_async16(B0 + r * SLD + c, V + (size_t)(rt * OP + r) * ne + op_index(I, J, c));
     }
+    load_q_async(B1, Qs + (size_t)k * OP * OP);
+    cp_async_wait_all();
     __syncthreads();
-    gemm_tn<true, true>(OP, OP, B0, B1, SLD, B2, SLD, OP);
-    for (int t = threadIdx.x; t < OP * OP; t += NT) {
-      const int i = t >> 6, j = t & 63;
-      V[(size_t)(rt * OP + i) * ne + op_index(I, J, j)] = B2[i * SLD + j];
-    }
+    tile_gemm64<true>(B0, B1, i0, j0, g, tg, d);
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+        *reinterpret_cast<double2*>(V + (size_t)(rt * OP + i0 + 8 * a + g) * ne + op_index(I, J, j0 + 8 * b + 2 * tg)) =
+            make_double2(d[a][b][0], d[a][b][1]);
   }
 }
 
