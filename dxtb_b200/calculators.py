@@ -128,10 +128,17 @@ class _SinglePoint(torch.autograd.Function):
         if calc.scf_events is not None:  # bench.py: device time of the SCF kernel alone
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record(torch.cuda.current_stream(d.device))
-        for bk in calc._buckets:
-            if bk["use_smem"] == 3:
-                calc._run_large(bk, o, ws, nel_ab, need_grad, st)
-                continue
+        # size buckets run concurrently on side streams (a bucket of a few big molecules occupies only a few SMs for a long
+        # time: the small molecules fill the rest of the device meanwhile); the large-system path drives the main stream
+        main = torch.cuda.current_stream(d.device)
+        small = [bk for bk in calc._buckets if bk["use_smem"] != 3]
+        side = calc._side_streams(len(small)) if len(calc._buckets) > 1 else [main] * len(small)
+        if side and side[0] is not main:
+            fork = torch.cuda.Event()
+            fork.record(main)
+        for bk, stream in zip(small, side):
+            if stream is not main:
+                stream.wait_event(fork)
             o.use_smem = bk["use_smem"] if calc._use_smem_override is None else calc._use_smem_override
             o.mol_list, o.list_len = bk["list"].data_ptr(), bk["len"]
             o.list_nao_max, o.list_nsh_max, o.list_nat_max = bk["nao"], bk["nsh"], bk["nat"]
@@ -141,10 +148,16 @@ class _SinglePoint(torch.autograd.Function):
                     ws.q0_at.data_ptr(), ws.work.data_ptr(), ws.q_orb.data_ptr(), ws.q_sh.data_ptr(), ws.q_at.data_ptr(),
                     ws.v_orb.data_ptr(), ws.e_atom.data_ptr(), ws.fenergy.data_ptr(), ws.emo.data_ptr(), ws.occ.data_ptr(),
                     ws.iterations.data_ptr(), ws.status.data_ptr(), ws.P.data_ptr() if need_grad else None,
-                    ws.W.data_ptr() if need_grad else None, st,
+                    ws.W.data_ptr() if need_grad else None, stream.cuda_stream,
                 ),
                 "xtb_scf_run",
             )
+        for bk in calc._buckets:
+            if bk["use_smem"] == 3:
+                calc._run_large(bk, o, ws, nel_ab, need_grad, st)
+        for stream in side:
+            if stream is not main:
+                main.wait_stream(stream)
         if ev is not None:
             ev[1].record(torch.cuda.current_stream(d.device))
             calc.scf_events.append(ev)
@@ -265,7 +278,9 @@ class GFN1Calculator:
         self._use_smem_override: int | None = None  # tests: force the global-memory variant
         self._prefer_hybrid = os.environ.get("DXTB_B200_PREFER_HYBRID", "0") != "0"
         self._large_min_nao = int(os.environ.get("DXTB_B200_LARGE_MIN_NAO", "1000000"))
+        self._large_max_count = int(os.environ.get("DXTB_B200_LARGE_MAX_COUNT", "8"))
         self._buckets = self._make_buckets()
+        self._streams: list = []
 
     # ------------------------------------------------------------------------------------------
     def _make_buckets(self) -> list[dict[str, Any]]:
@@ -290,6 +305,11 @@ class GFN1Calculator:
         # the one-CTA kernel no longer fit in shared memory, or from `large_min_nao` atomic orbitals on
         mode = np.where(need[:, 1] <= _SMEM_LIMIT, 1, np.where(need[:, 2] <= _SMEM_LIMIT, 2, 0))
         mode[(need[:, 0] > _SMEM_LIMIT) | (d.nao >= self._large_min_nao)] = 3
+        # a handful of big molecules cannot fill the device with one CTA each: the large-system path is ~10x faster per
+        # molecule (vancoh2: 0.10 s against 1.1 s latency), the one-CTA kernel only wins from ~a dozen such molecules on
+        big = (mode == 0) & (d.nao >= 256)
+        if 0 < int(big.sum()) <= self._large_max_count:
+            mode[big] = 3
         if self._prefer_hybrid:
             two = (need[:, 2] <= _SMEM_2CTA) & (mode == 1)
             if 2 * int(two.sum()) >= 3 * _sm_count(self.device):
@@ -307,6 +327,12 @@ class GFN1Calculator:
                 "mols": [int(i) for i in idx] if use_smem == 3 else None,
             })
         return buckets
+
+    def _side_streams(self, n: int) -> list:
+        """One CUDA stream per concurrently running size bucket (created once per calculator)."""
+        while len(self._streams) < n:
+            self._streams.append(torch.cuda.Stream(self.device))
+        return self._streams[:n]
 
     def _run_large(self, bk, o, ws, nel_ab, need_grad: bool, st: int) -> None:
         """Molecules of the large-system bucket, one after the other on the whole device (xtb_scf_run_large)."""

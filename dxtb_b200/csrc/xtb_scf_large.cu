@@ -46,7 +46,7 @@ __host__ __device__ inline Layout layout(int n, int ns, int na, int gen) {
   l.C = p; p += m;
   l.A = p; p += m;
   l.X = p; p += m;
-  l.Q = p; p += (size_t)l.nbp * OP * OP;
+  l.Q = p; p += (size_t)2 * l.nbp * OP * OP;  // accumulated rotations, double buffered by round parity
   l.vec = p; p += (size_t)8 * (n + 2) + 2 * ns + na + 32 + 36 + (n + 4) / 2 + 2;
   p += p & 1;
   l.hist = p; p += (size_t)2 * (gen + 1) * n;
@@ -330,13 +330,22 @@ XTB_DEV void rr_pair(int nblk, int r, int w, int& I, int& J) {
   if (I > J) { const int t = I; I = J; J = t; }
 }
 
+// block paired with block x in round r of the same schedule
+XTB_DEV int rr_partner(int nblk, int r, int x) {
+  const int nb1 = nblk - 1;
+  if (x == nb1) return r;
+  int y = (2 * r - x) % nb1;
+  if (y < 0) y += nb1;
+  return y == x ? nb1 : y;
+}
+
 constexpr int SUB_MAT = OP * SLD;  // doubles of a 64 x 68 shared-memory matrix
 constexpr int SUB_NBP = OP / JB2;  // block pairs of the in-CTA solver on a 64 x 64 sub-problem
 constexpr int SUB_SMEM = (2 * SUB_MAT + SUB_NBP * JB2 * QLD + NGRP * (JB2 * MLD + 48) + 32 + 2 * SUB_NBP) * 8;
 
 // One CTA per outer block pair: 64 x 64 sub-problem on the diagonal tile, one in-CTA Jacobi sweep, Q -> global.
 __global__ void __launch_bounds__(NT, 1)
-kl_jacobi_sub(const double* __restrict__ A, double* __restrict__ Qs, int* __restrict__ bij, int ne, int r, double tol) {
+kl_jacobi_sub(const double* __restrict__ A, double* __restrict__ Qs, int ne, int r, double tol) {
   extern __shared__ double ssm[];
   double* As = ssm;
   double* Vs = ssm + SUB_MAT;
@@ -357,7 +366,6 @@ kl_jacobi_sub(const double* __restrict__ A, double* __restrict__ Qs, int* __rest
     As[a * SLD + b] = A[(size_t)op_index(I, J, a) * ne + op_index(I, J, b)];
     Vs[a * SLD + b] = (a == b) ? 1.0 : 0.0;
   }
-  if (threadIdx.x == 0) { bij[2 * w] = I; bij[2 * w + 1] = J; }
   __syncthreads();
   jacobi<true, true>(c, As, Vs, OP, tol, 1);
   __syncthreads();
@@ -415,7 +423,7 @@ XTB_DEV void tile_gemm64(const double* __restrict__ L, const double* __restrict_
 // (3 CTAs per SM overlap the loads of one tile with the tensor-core work of the others); results go from the
 // accumulators straight to global memory.
 __global__ void __launch_bounds__(NT, 3)
-kl_jacobi_pass(double* __restrict__ A, double* __restrict__ V, const double* __restrict__ Qs, const int* __restrict__ bij, int ne, int nbp) {
+kl_jacobi_pass(double* __restrict__ A, double* __restrict__ V, const double* __restrict__ Qs, int ne, int nbp, int r, int phase) {
   extern __shared__ double psm[];
   double* B0 = psm;
   double* B1 = psm + SUB_MAT;
@@ -430,7 +438,17 @@ kl_jacobi_pass(double* __restrict__ A, double* __restrict__ V, const double* __r
     while ((P + 1) * (P + 2) / 2 <= u) ++P;
     while (P * (P + 1) / 2 > u) --P;
     const int R = u - P * (P + 1) / 2;
-    const int IP = bij[2 * P], JP = bij[2 * P + 1], IR = bij[2 * R], JR = bij[2 * R + 1];
+    const int nblk = ne / OB;
+    int IP, JP, IR, JR;
+    rr_pair(nblk, r, P, IP, JP);
+    rr_pair(nblk, r, R, IR, JR);
+    if (phase != 0) {
+      // tiles holding a block pair of the NEXT round (incl. all diagonal tiles) are updated first (phase 1), so that the
+      // next sub-problems can start while the remaining tiles (phase 2) are still being rotated
+      const int pi = rr_partner(nblk, r + 1, IP), pj = rr_partner(nblk, r + 1, JP);
+      const bool needed = P == R || pi == IR || pi == JR || pj == IR || pj == JR;
+      if (needed != (phase == 1)) return;
+    }
     // B0[i][k] = A[P_i][R_k], B1 = Q_R
     load_tile_async(B0, A, ne, IP, JP, IR, JR);
     load_q_async(B1, Qs + (size_t)R * OP * OP);
@@ -461,9 +479,11 @@ kl_jacobi_pass(double* __restrict__ A, double* __restrict__ V, const double* __r
       }
     }
   } else {
+    if (phase == 1) return;
     const int rem = u - nfused;
     const int k = rem % nbp, rt = rem / nbp;
-    const int I = bij[2 * k], J = bij[2 * k + 1];
+    int I, J;
+    rr_pair(ne / OB, r, k, I, J);
     // B0[i][c] = V[64 rt + i][idx_c], B1 = Q
     for (int t = threadIdx.x; t < OP * OP / 2; t += NT) {
       const int r = t >> 5, c = (t & 31) << 1;
@@ -575,7 +595,6 @@ extern "C" int xtb_scf_run_large(const xtb_batch* b, const xtb_scf_opts* o, int3
   const Layout l = layout(nao, nsh, nat, o->generations);
   const int n = nao, ne = l.ne, nbp = l.nbp, nblk = ne / OB;
   double *C = work + l.C, *A = work + l.A, *X = work + l.X, *Qs = work + l.Q;
-  int* bij = (int*)(work + l.bij);
   LargeState* dst = reinterpret_cast<LargeState*>(work + l.state);
   const double* Sm = S + mat_off;
   const double* Hm = H0 + mat_off;
@@ -598,6 +617,16 @@ extern "C" int xtb_scf_run_large(const xtb_batch* b, const xtb_scf_opts* o, int3
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  }
+  // second stream (highest priority) and events for the sub-problem / pass overlap of the Jacobi rounds
+  static cudaStream_t side = nullptr;
+  static cudaEvent_t ev_a = nullptr, ev_s = nullptr;
+  if (!side) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, hi) != cudaSuccess) return -5;
+    if (cudaEventCreateWithFlags(&ev_a, cudaEventDisableTiming) != cudaSuccess) return -5;
+    if (cudaEventCreateWithFlags(&ev_s, cudaEventDisableTiming) != cudaSuccess) return -5;
   }
   const int ew_grid = 4 * n_sm;  // elementwise kernels: grid-stride
   LargeState hs;
@@ -625,9 +654,24 @@ extern "C" int xtb_scf_run_large(const xtb_batch* b, const xtb_scf_opts* o, int3
       if (hs.off <= tol) return 0;
       if (sweep >= maxsweeps) { hstatus |= XTB_STATUS_JACOBI_NOT_CONVERGED; return 0; }
       ++total_sweeps;
+      // Round r: sub-problems -> Q (buffer r & 1), then the rotation pass.  The pass first updates the few tiles the
+      // sub-problems of round r + 1 read (phase 1); those sub-problems (nbp CTAs, a third of the SMs) then run on a second,
+      // higher-priority stream concurrently with the bulk of the pass (phase 2).
+      const size_t qsz = (size_t)nbp * OP * OP;
+      kl_jacobi_sub<<<nbp, NT, SUB_SMEM, st>>>(Am, Qs, ne, 0, tol);
       for (int r = 0; r < nblk - 1; ++r) {
-        kl_jacobi_sub<<<nbp, NT, SUB_SMEM, st>>>(Am, Qs, bij, ne, r, tol);
-        kl_jacobi_pass<<<npass, NT, PASS_SMEM, st>>>(Am, Vm, Qs, bij, ne, nbp);
+        const double* Qr = Qs + (size_t)(r & 1) * qsz;
+        if (r + 1 < nblk - 1) {
+          kl_jacobi_pass<<<nbp * (nbp + 1) / 2, NT, PASS_SMEM, st>>>(Am, Vm, Qr, ne, nbp, r, 1);
+          cudaEventRecord(ev_a, st);
+          cudaStreamWaitEvent(side, ev_a, 0);
+          kl_jacobi_sub<<<nbp, NT, SUB_SMEM, side>>>(Am, Qs + (size_t)((r + 1) & 1) * qsz, ne, r + 1, tol);
+          cudaEventRecord(ev_s, side);
+          kl_jacobi_pass<<<npass, NT, PASS_SMEM, st>>>(Am, Vm, Qr, ne, nbp, r, 2);
+          cudaStreamWaitEvent(st, ev_s, 0);
+        } else {
+          kl_jacobi_pass<<<npass, NT, PASS_SMEM, st>>>(Am, Vm, Qr, ne, nbp, r, 0);
+        }
       }
     }
   };

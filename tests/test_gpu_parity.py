@@ -166,10 +166,12 @@ def test_global_memory_variant_matches_shared_memory_variant(mols):
     assert torch.equal(a.get_iterations(), c.get_iterations())
 
 
-def test_large_molecule_global_path(mols):
-    """vancoh2 (176 atoms, nao 550) runs the global-memory variant."""
+def test_large_molecule_global_path(mols, monkeypatch):
+    """vancoh2 (176 atoms, nao 550) through the global-memory variant of the one-CTA kernel (a single big molecule would
+    otherwise take the large-system path)."""
     from dxtb_b200 import GFN1Calculator
 
+    monkeypatch.setenv("DXTB_B200_LARGE_MAX_COUNT", "0")
     dev = _dev()
     numbers, pos, chrg = _pack(mols, ["vancoh2"], dev)
     calc = GFN1Calculator(numbers, opts=NODISP, device=dev, dtype=torch.float64)
@@ -440,8 +442,9 @@ def test_large_system_path_matches_one_cta_path(mols, monkeypatch):
 
     dev = _dev()
     numbers, pos, chrg = _pack(mols, ["vancoh2", "H2O"], dev)
+    monkeypatch.setenv("DXTB_B200_LARGE_MAX_COUNT", "0")
     a = GFN1Calculator(numbers, opts=NODISP, device=dev, dtype=torch.float64)
-    monkeypatch.setenv("DXTB_B200_LARGE_MIN_NAO", "500")
+    monkeypatch.setenv("DXTB_B200_LARGE_MAX_COUNT", "8")
     b = GFN1Calculator(numbers, opts=NODISP, device=dev, dtype=torch.float64)
     assert a._variants == [0, 1] and b._variants == [1, 3]
     pa, pb = pos.clone().requires_grad_(True), pos.clone().requires_grad_(True)
