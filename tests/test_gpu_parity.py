@@ -478,3 +478,38 @@ def test_sh3_config4_against_oracle_fixture(mols):
     assert int(calc.get_iterations()[0]) == int(ref["iterations"])
     assert np.abs(g[0].cpu().numpy() - ref["gradient"]).max() < F_TOL
     assert np.abs(calc.get_atomic_charges()[0].cpu().numpy() - ref["q_atom"]).max() < Q_TOL
+
+
+def test_large_system_path_small_edge_cases(mols, monkeypatch):
+    """The large-system kernels on molecules far below their intended size (padding to 128, 2 outer block pairs, one
+    occupied orbital, cation, radical): same results as the one-CTA kernel."""
+    from dxtb_b200 import GFN1Calculator
+
+    dev = _dev()
+    names = ["H", "LiH", "H2O", "NO2", "AD7en+", "caffeine"]
+    numbers, pos, chrg = _pack(mols, names, dev)
+    a = GFN1Calculator(numbers, opts=NODISP, device=dev, dtype=torch.float64)
+    monkeypatch.setenv("DXTB_B200_LARGE_MIN_NAO", "1")
+    b = GFN1Calculator(numbers, opts=NODISP, device=dev, dtype=torch.float64)
+    assert b._variants == [3]
+    pa, pb = pos.clone().requires_grad_(True), pos.clone().requires_grad_(True)
+    ea, eb = a.get_energy(pa, chrg), b.get_energy(pb, chrg)
+    (ga,) = torch.autograd.grad(ea.sum(), pa)
+    (gb,) = torch.autograd.grad(eb.sum(), pb)
+    assert torch.allclose(ea, eb, rtol=0, atol=1e-10)
+    assert torch.equal(a.get_iterations(), b.get_iterations())
+    assert (ga - gb).abs().max() < 1e-8
+    assert (a.get_charges() - b.get_charges()).abs().max() < 1e-8
+
+
+def test_large_system_path_reports_non_convergence(mols, monkeypatch):
+    from dxtb_b200 import GFN1Calculator
+    from dxtb_b200.exceptions import SCFConvergenceWarning
+
+    dev = _dev()
+    numbers, pos, chrg = _pack(mols, ["caffeine"], dev)
+    monkeypatch.setenv("DXTB_B200_LARGE_MIN_NAO", "1")
+    calc = GFN1Calculator(numbers, opts={"exclude": ["disp"], "maxiter": 3}, device=dev, dtype=torch.float64)
+    with pytest.warns(SCFConvergenceWarning):
+        calc.get_energy(pos, chrg)
+    assert int(calc.get_iterations()[0]) == 4
