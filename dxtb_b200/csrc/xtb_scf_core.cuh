@@ -92,15 +92,23 @@ __device__ void gemm_tn(int ne, int K, const double* __restrict__ L, const doubl
   __syncthreads();
 }
 
-// named barrier for a thread group of 3 warps (ids 1..NGRP; id 0 is __syncthreads)
-constexpr int GS = 96;            // threads per sub-problem group
-constexpr int NGRP = NT / GS;     // 5 groups of 3 warps (the 16th warp idles during the sub-problems)
-XTB_DEV void group_bar(int grp) { asm volatile("bar.sync %0, 96;" ::"r"(grp + 1) : "memory"); }
+constexpr int NGRP = 8;  // sub-problems solved concurrently (one warp each; every warp has its own 16x16 copy)
 
 constexpr int JB = 8;        // Jacobi block size
 constexpr int JB2 = 2 * JB;  // indices of a block pair
 constexpr int MLD = 24;      // leading dimension of the 16x16 sub-problem copy (== 8 mod 16: conflict-free 2x2-block updates)
 constexpr int QLD = 20;      // leading dimension of the accumulated 16x16 rotation (== 4 mod 16: conflict-free DMMA fragments)
+
+// 1/sqrt(x) for normal x > 0: MUFU seed (rsqrt.approx.ftz.f64, ~2^-22) + two Newton steps, straight-line code (the
+// library rsqrt() has a slow path behind a branch, which stops the scheduler from interleaving independent work).
+XTB_DEV double rsqrt_nr(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  y = y * fma(-hx * y, y, 1.5);
+  y = y * fma(-hx * y, y, 1.5);
+  return y;
+}
 
 // Global index of local index l (0..15) of block pair (I, J).
 XTB_DEV int bp_index(int I, int J, int l) { return (l < JB ? I * JB : J * JB - JB) + l; }
@@ -108,8 +116,8 @@ XTB_DEV int bp_index(int I, int J, int l) { return (l < JB ? I * JB : J * JB - J
 // BLOCKED two-sided Jacobi (block size 8) on the symmetric ne x ne matrix A (ne % 16 == 0), accumulating
 // the transformation into the columns of V (ne rows).
 //   Per block round (round-robin over the ne/8 blocks, ne/16 disjoint block pairs):
-//   1. one thread group (3 warps) per block pair copies its 16x16 sub-matrix, runs the scalar rotations of the pair on the
-//      copy (warp-synchronous, no CTA barrier) and accumulates them into a 16x16 orthogonal Q;
+//   1. one warp per block pair copies its 16x16 sub-matrix, runs the scalar rotations of the pair on the copy
+//      (warp-synchronous: no CTA or named barrier) and accumulates them into a 16x16 orthogonal Q;
 //   2. all warps apply the Q's with fp64 tensor-core MMAs: every 16x16 block of A two-sided (Q_P^T B Q_R), V <- V Q.
 //   A sweep = one "self" round (block pairs (0,1),(2,3),..: the 2 x 28 in-block index pairs) followed by the
 //   nblk-1 round-robin rounds in which the 64 cross pairs of a block pair are rotated: every index pair once.
@@ -121,18 +129,12 @@ __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, in
   const int nblk = ne / JB, nbp = nblk / 2, ntile = ne / 8;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int NW = NT / 32;
-  constexpr int NG = NGRP;  // thread groups of 3 warps for the sub-problems
-  // group g = warps 3g..3g+2: warp 0 of a group computes the rotations (8 lanes) and, with warp 1, updates the
-  // sub-matrix; warps 1 and 2 accumulate Q.  Since 3g mod 4 cycles through the SM sub-partitions, the fp64-heavy
-  // rotation chains of concurrently running groups do not pile up on one sub-partition.
-  const int grp = warp / 3, gt = (int)threadIdx.x - GS * grp;
-  const int vt = gt;
+  constexpr int NG = NGRP;  // warps that solve sub-problems concurrently
   double* Qs = c.jq;  // [nbp][16][QLD]
   double* Ms = c.jm;  // [NG][16][MLD]  sub-problem copy of the group
-  double* Rs = c.jr;  // [NG][48] rotation parameters (double buffered)
   int* bij = c.pp;    // [nbp][2] blocks of the pairs of this round
   XTB_ASSUME_SHARED(bij);
-  XTB_ASSUME_SHARED(Qs); XTB_ASSUME_SHARED(Ms); XTB_ASSUME_SHARED(Rs);
+  XTB_ASSUME_SHARED(Qs); XTB_ASSUME_SHARED(Ms);
   if (AS) XTB_ASSUME_SHARED(A);
   if (VS) XTB_ASSUME_SHARED(V);
   (void)nrow;
@@ -149,8 +151,12 @@ __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, in
     if (sweep >= maxsweeps) return -sweep;
     ++sweep;
     for (int r = -1; r < nblk - 1; ++r) {
-      // ---- 1. sub-problems: a group of 4 warps (128 threads, named barrier) owns a block pair ----------
-      for (int w = grp; w < nbp && grp < NG; w += NG) {
+      // ---- 1. sub-problems: ONE WARP per block pair, warp-synchronous (no CTA or named barriers) ------------------
+      //   Every lane computes the rotation k = lane & 7 of the inner round (4 redundant copies, so there is no divergent
+      //   branch and the parameters of any rotation are one shuffle away); the warp then updates the 16x16 copy M on the
+      //   8x8 grid of 2x2 blocks (2 blocks per lane) and, one inner round behind and therefore off the dependent chain
+      //   rot(t) -> M(t) -> rot(t+1), accumulates the rotations into Q (4 row items per lane, its own rotation).
+      for (int w = warp; w < nbp && warp < NG; w += NG) {
         int I, J;
         if (r < 0) { I = 2 * w; J = 2 * w + 1; }
         else if (w == 0) { I = r; J = nblk - 1; }
@@ -159,88 +165,103 @@ __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, in
           J = (r - w + 2 * (nblk - 1)) % (nblk - 1);
         }
         if (I > J) { const int t = I; I = J; J = t; }
-        double* M = Ms + grp * (JB2 * MLD);
+        double* M = Ms + warp * (JB2 * MLD);
         double* Q = Qs + w * (JB2 * QLD);
-        double2* rcs = reinterpret_cast<double2*>(Rs + grp * 48);   // [2][8] (c, s), double buffered
-        int2* rpq = reinterpret_cast<int2*>(Rs + grp * 48 + 32);    // [2][8] (p, q)
-        if (gt == 0) { bij[2 * w] = I; bij[2 * w + 1] = J; }
-        for (int e = gt; e < JB2 * JB2; e += GS) {
+        if (lane == 0) { bij[2 * w] = I; bij[2 * w + 1] = J; }
+        for (int e = lane; e < JB2 * JB2; e += 32) {
           const int rr = e >> 4, cc = e & 15;
           M[rr * MLD + cc] = A[(size_t)bp_index(I, J, rr) * ld + bp_index(I, J, cc)];
           Q[rr * QLD + cc] = (rr == cc) ? 1.0 : 0.0;
         }
-        group_bar(grp);
+        __syncwarp();
         const int nin = (r < 0) ? JB - 1 : JB;
-        // Software pipeline: between the two group barriers of inner round t, warp 0 computes the 8 rotations of
-        // round t while warps 1..3 apply the rotations of round t-1 to Q (Q is off the critical path
-        // rot(t) -> M(t) -> rot(t+1)); rotation parameters are double buffered.
-        auto q_update = [&](int buf) {
-          // 128 items (16 rows x 8 pairs) on 64 threads; every half-warp covers 4 rows x 4 pairs (conflict-free)
-          for (int it = vt - 32; it < 128; it += GS - 32) {
-            const int qk = (it & 3) + 4 * ((it >> 4) & 1), qi = ((it >> 2) & 3) + 4 * (it >> 5);
-            const int2 pqq = rpq[8 * buf + qk];
-            const double2 csq = rcs[8 * buf + qk];
-            const double vp = Q[qi * QLD + pqq.x], vq = Q[qi * QLD + pqq.y];
-            Q[qi * QLD + pqq.x] = csq.x * vp - csq.y * vq;
-            Q[qi * QLD + pqq.y] = csq.y * vp + csq.x * vq;
+        const bool self = r < 0;
+        // index pair (p, q) of rotation k in inner round t
+        auto pair_of = [&](int t, int k, int& p, int& q) {
+          if (self) {
+            // self round: the 28 in-block pairs of block I (k < 4) and of block J (k >= 4), round-robin on 8 indices
+            const int kk = k & 3, h = (k >> 2) * JB;
+            if (kk == 0) { p = t; q = JB - 1; }
+            else { p = t + kk; if (p >= JB - 1) p -= JB - 1; q = t - kk; if (q < 0) q += JB - 1; }
+            if (p > q) { const int x = p; p = q; q = x; }
+            p += h; q += h;
+          } else {
+            p = k; q = JB + ((k + t) & (JB - 1));
           }
         };
+        const int k = lane & 7;
+        // Q items of this lane: rotation k, rows qrow + 4 j (lanes 0-7: row 0, 8-15: row 2, 16-23: row 1, 24-31: row 3,
+        // so that the two rows of a half-warp are 2 apart: conflict free with QLD == 4 mod 16)
+        const int qrow = 2 * ((lane >> 3) & 1) + (lane >> 4);
+        double pc = 1.0, ps = 0.0;  // rotation of the previous inner round (for the Q update)
+        int pp_ = 0, pq_ = 0;
         for (int t = 0; t < nin; ++t) {
-          const int buf = t & 1;
-          if (vt < 8) {
-            // the 8 disjoint index pairs of this inner round
-            const int l = vt;
-            int p, q;
-            if (r < 0) {
-              // self round: the 28 in-block pairs of block I (l < 4) and of block J (l >= 4), round-robin on 8
-              const int k = l & 3, h = (l >> 2) * JB;
-              if (k == 0) { p = t; q = JB - 1; }
-              else { p = t + k; if (p >= JB - 1) p -= JB - 1; q = t - k; if (q < 0) q += JB - 1; }
-              if (p > q) { const int x = p; p = q; q = x; }
-              p += h; q += h;
-            } else {
-              p = l; q = JB + ((l + t) & (JB - 1));
-            }
-            const double app = M[p * MLD + p], aqq = M[q * MLD + q], apq = M[p * MLD + q];
-            double cs_ = 1.0, sn = 0.0;
-            // Small-angle Jacobi rotation from the double-angle identities (two dependent rsqrt instead of three
-            // divisions/square roots; rsqrt is a 62-cycle chain on sm_100a, tools/microbench/lat.cu):
-            //   r = sqrt(d^2 + 4 apq^2), cos 2t = |d| / r, sin 2t = sign(d) 2 apq / r,
-            //   c^2 = (1 + cos 2t) / 2,  c = c^2 rsqrt(c^2),  s = sin 2t / (2 c).
-            // s has no cancellation for small angles; c^2 + s^2 = 1 holds to a few ulp.
-            const double d = aqq - app;
-            const double x = d * d + 4.0 * apq * apq;
-            if (x > 1e-280) {
-              const double ir = rsqrt(x);
-              const double c2 = 0.5 + 0.5 * fabs(d) * ir;
-              const double ic = rsqrt(c2);
-              cs_ = c2 * ic;
-              sn = copysign(apq * ir, d * apq) * ic;
-            }
-            rcs[8 * buf + l] = make_double2(cs_, sn);
-            rpq[8 * buf + l] = make_int2(p, q);
-          } else if (vt >= 32 && t > 0) {
-            q_update(buf ^ 1);
+          int p, q;
+          pair_of(t, k, p, q);
+          const double app = M[p * MLD + p], aqq = M[q * MLD + q], apq = M[p * MLD + q];
+          // M items of this lane: (kp, kq) = (lane >> 3, lane & 7) and (kp + 4, kq); loads issued before the rotation
+          // parameters are known
+          int p1[2], q1[2], p2, q2;
+          pair_of(t, lane >> 3, p1[0], q1[0]);
+          pair_of(t, (lane >> 3) + 4, p1[1], q1[1]);
+          p2 = p; q2 = q;
+          double a00[2], a01[2], a10[2], a11[2];
+#pragma unroll
+          for (int it = 0; it < 2; ++it) {
+            a00[it] = M[p1[it] * MLD + p2]; a01[it] = M[p1[it] * MLD + q2];
+            a10[it] = M[q1[it] * MLD + p2]; a11[it] = M[q1[it] * MLD + q2];
           }
-          group_bar(grp);
-          if (vt < 64) {
-            // M <- J^T M J on the 8x8 grid of 2x2 blocks: thread -> (kp, kq) = (vt >> 3, vt & 7)
-            const int kp = vt >> 3, kq = vt & 7;
-            const int2 pq1 = rpq[8 * buf + kp], pq2 = rpq[8 * buf + kq];
-            const double2 cs1 = rcs[8 * buf + kp], cs2 = rcs[8 * buf + kq];
-            const int p1 = pq1.x, q1 = pq1.y, p2 = pq2.x, q2 = pq2.y;
-            const double c1 = cs1.x, s1 = cs1.y, c2 = cs2.x, s2 = cs2.y;
-            const double a00 = M[p1 * MLD + p2], a01 = M[p1 * MLD + q2], a10 = M[q1 * MLD + p2], a11 = M[q1 * MLD + q2];
-            const double x00 = c1 * a00 - s1 * a10, x01 = c1 * a01 - s1 * a11;
-            const double x10 = s1 * a00 + c1 * a10, x11 = s1 * a01 + c1 * a11;
-            double y00 = c2 * x00 - s2 * x01, y01 = s2 * x00 + c2 * x01;
-            double y10 = c2 * x10 - s2 * x11, y11 = s2 * x10 + c2 * x11;
-            if (kp == kq) { y01 = 0.0; y10 = 0.0; }
-            M[p1 * MLD + p2] = y00; M[p1 * MLD + q2] = y01; M[q1 * MLD + p2] = y10; M[q1 * MLD + q2] = y11;
+          // Small-angle Jacobi rotation from the double-angle identities (two dependent rsqrt instead of three
+          // divisions/square roots):
+          //   r = sqrt(d^2 + 4 apq^2), cos 2t = |d| / r, sin 2t = sign(d) 2 apq / r,
+          //   c^2 = (1 + cos 2t) / 2,  c = c^2 rsqrt(c^2),  s = sin 2t / (2 c).
+          // s has no cancellation for small angles; c^2 + s^2 = 1 holds to a few ulp.
+          // branch-free (straight-line code lets the scheduler interleave the Q update below with this dependent chain)
+          const double d = aqq - app;
+          const double x = fma(d, d, 4.0 * apq * apq);
+          const double ir = rsqrt_nr(fmax(x, 1e-280));
+          const double c2 = fma(0.5 * fabs(d), ir, 0.5);
+          const double ic = rsqrt_nr(c2);
+          const bool rot = x > 1e-280;
+          const double cs_ = rot ? c2 * ic : 1.0;
+          const double sn = rot ? copysign(apq * ir, d * apq) * ic : 0.0;
+          // Q <- Q J(t-1): rotation k of the previous inner round on 4 rows (independent of the chain above; all loads
+          // before the stores, the compiler cannot prove that the rows do not alias)
+          if (t > 0) {
+            double vp[4], vq[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { vp[j] = Q[(qrow + 4 * j) * QLD + pp_]; vq[j] = Q[(qrow + 4 * j) * QLD + pq_]; }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              Q[(qrow + 4 * j) * QLD + pp_] = pc * vp[j] - ps * vq[j];
+              Q[(qrow + 4 * j) * QLD + pq_] = ps * vp[j] + pc * vq[j];
+            }
           }
-          group_bar(grp);
+          // M <- J^T M J on the 8x8 grid of 2x2 blocks; column rotation kq = own rotation, row rotation kp by shuffle
+          __syncwarp();  // every lane has read its rotation inputs and block values before any lane stores
+#pragma unroll
+          for (int it = 0; it < 2; ++it) {
+            const int kp = (lane >> 3) + 4 * it;
+            const double c1 = __shfl_sync(0xffffffffu, cs_, kp), s1 = __shfl_sync(0xffffffffu, sn, kp);
+            const double x00 = c1 * a00[it] - s1 * a10[it], x01 = c1 * a01[it] - s1 * a11[it];
+            const double x10 = s1 * a00[it] + c1 * a10[it], x11 = s1 * a01[it] + c1 * a11[it];
+            double y00 = cs_ * x00 - sn * x01, y01 = sn * x00 + cs_ * x01;
+            double y10 = cs_ * x10 - sn * x11, y11 = sn * x10 + cs_ * x11;
+            if (kp == k) { y01 = 0.0; y10 = 0.0; }
+            M[p1[it] * MLD + p2] = y00; M[p1[it] * MLD + q2] = y01;
+            M[q1[it] * MLD + p2] = y10; M[q1[it] * MLD + q2] = y11;
+          }
+          pc = cs_; ps = sn; pp_ = p; pq_ = q;
+          __syncwarp();
         }
-        if (vt >= 32) q_update((nin - 1) & 1);  // rotations of the last inner round
+        // rotations of the last inner round
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int qi = qrow + 4 * j;
+          const double vp = Q[qi * QLD + pp_], vq = Q[qi * QLD + pq_];
+          Q[qi * QLD + pp_] = pc * vp - ps * vq;
+          Q[qi * QLD + pq_] = ps * vp + pc * vq;
+        }
       }
       __syncthreads();
       // ---- 2. apply the rotations with fp64 tensor-core MMAs, one phase ---------------------------------------

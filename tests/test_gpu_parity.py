@@ -373,7 +373,7 @@ def test_ragged_jittered_batch(mols):
         pos[i, : len(z)] = torch.from_numpy(xyz)
         chrg[i] = q
     calc = GFN1Calculator(numbers.to(dev), opts=NODISP, device=dev, dtype=torch.float64)
-    assert len(calc._buckets) == 2
+    assert len(calc._buckets) >= 2
     p = pos.to(dev).requires_grad_(True)
     e = calc.get_energy(p, chrg.to(dev))
     (g,) = torch.autograd.grad(e.sum(), p)
