@@ -6,9 +6,12 @@ no CPU fallback: importing this module without the compiled ``_C.so`` raises.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 _SO = Path(__file__).resolve().parent / "_C.so"
+if os.environ.get("DXTB_B200_LIB"):  # developer A/B builds
+    _SO = Path(os.environ["DXTB_B200_LIB"])
 
 ATPAR, SHPAR, CGTO, MAXPRIM = 12, 6, 16, 7
 (AT_RAD, AT_RCOV, AT_EN, AT_AREP, AT_ZEFF, AT_GAM3, AT_XBOND, AT_EEQ_CHI, AT_EEQ_ETA, AT_EEQ_KCN, AT_EEQ_RAD, AT_R4R2) = range(12)

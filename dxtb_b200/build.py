@@ -47,7 +47,8 @@ def build_extension(force: bool = False, verbose: bool = False) -> Path:
     procs = []
     for s, suffix, extra in SOURCES:
         obj = objdir / (s + suffix + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, *extra, f"-I{INCLUDE}", f"-I{CSRC}", "-c", str(CSRC / s), "-o", str(obj)]
+        dev_flags = os.environ.get("DXTB_B200_NVCC_FLAGS", "").split()  # developer builds, e.g. -DXTB_PROFILE_PHASES
+        cmd = [nvcc, *NVCC_FLAGS, *extra, *dev_flags, f"-I{INCLUDE}", f"-I{CSRC}", "-c", str(CSRC / s), "-o", str(obj)]
         if verbose:
             print(" ".join(cmd))
         procs.append((s + suffix, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -13,6 +13,9 @@
 // workspace (L2-resident for the active CTAs).  Leading dimension ld is odd so that both row and column
 // accesses of fp64 data are bank-conflict free.
 #include "xtb_scf_core.cuh"
+#ifdef XTB_PROFILE_PHASES
+#include <cstdio>
+#endif
 
 namespace {
 
@@ -76,7 +79,14 @@ __device__ double fcn(Ctx& c, const double* __restrict__ v, const xtb_scf_opts& 
     }
   }
   __syncthreads();
-  const int sw = jacobi<AS, CS>(c, c.A, c.C, ne, jtol, o.jacobi_max_sweeps);
+#ifdef XTB_PROFILE_PHASES
+  const long long tj0 = clock64();
+#endif
+  const int sw = (MODE != 1 && c.defer) ? jacobi<AS, CS, MODE != 1>(c, c.A, c.C, ne, jtol, o.jacobi_max_sweeps)
+                                        : jacobi<AS, CS, false>(c, c.A, c.C, ne, jtol, o.jacobi_max_sweeps);
+#ifdef XTB_PROFILE_PHASES
+  c.tjac += clock64() - tj0;
+#endif
   if (sw < 0) c.status |= XTB_STATUS_JACOBI_NOT_CONVERGED;
   c.sweeps += sw < 0 ? -sw : sw;
   for (int k = threadIdx.x; k < n; k += NT) c.eps[k] = c.A[(size_t)k * ld + k];
@@ -144,6 +154,10 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
   c.np = c.ne / 2;
   c.status = 0;
   c.sweeps = 0;
+  c.tp1 = c.tp2 = c.tjac = 0;
+#ifdef XTB_PROFILE_PHASES
+  const long long tk0 = clock64();
+#endif
   const int n = c.n, ne = c.ne, ld = c.ld;
   // shared-memory carve-up (sizes by batch maxima so the layout is launch-uniform)
   const int nmx = lnao + 2, nsx = lnsh, nax = lnat;
@@ -162,7 +176,8 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
     // block-Jacobi scratch, always in shared memory: accumulated rotations Q per block pair, sub-problem copy and
     // rotation parameters per concurrently working thread group
     const int nbpx = (lnao + 15) / 16;
-    c.jq = p; p += nbpx * JB2 * QLD;
+    c.defer = MODE != 1 && nbpx <= XTB_DEFER_NBP;  // pays off when V lives in the L2-resident workspace
+    c.jq = p; p += (c.defer ? 2 : 1) * nbpx * JB2 * QLD;  // double buffered by round parity if the V pass is deferred
     c.jm = p; p += NGRP * JB2 * MLD;
     c.jr = p; p += NGRP * 48;
   }
@@ -236,6 +251,11 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
   if (!converged) c.status |= XTB_STATUS_SCF_NOT_CONVERGED;
 
   emit_results(c, b, m, g, iters, q_orb, q_sh, q_at, v_orb, e_atom, fenergy, emo, occ, iterations, status);
+#ifdef XTB_PROFILE_PHASES
+  if (threadIdx.x == 0 && blockIdx.x == 0)
+    printf("k_scf phases (cycles): total %lld  jacobi %lld  sub-problems %lld  pass %lld  sweeps %d\n", clock64() - tk0, c.tjac, c.tp1, c.tp2,
+           c.sweeps);
+#endif
   if (o.want_density) {
     double* Pm = Pout + b.mat_off[m];
     double* Wm = Wout + b.mat_off[m];
@@ -258,11 +278,12 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
   }
 }
 
-int64_t vec_smem_bytes(int64_t nao_max, int64_t nsx, int64_t nax) {
+int64_t vec_smem_bytes(int64_t nao_max, int64_t nsx, int64_t nax, bool v_global) {
   const int64_t nmx = nao_max + 2;
   int64_t d = 2 * (nmx + (nmx & 1)) + 8 * nmx + 2 * nsx + nax + 32 + 36 + (nmx + 2) / 2 + 1;
   d += d & 1;
-  d += ((nao_max + 15) / 16) * JB2 * QLD + NGRP * (JB2 * MLD + 48);  // block-Jacobi scratch
+  const int64_t nbpx = (nao_max + 15) / 16;
+  d += (v_global && nbpx <= XTB_DEFER_NBP ? 2 : 1) * nbpx * JB2 * QLD + NGRP * (JB2 * MLD + 48);  // block-Jacobi scratch
   d += d & 1;
   return d * 8;
 }
@@ -271,7 +292,7 @@ int64_t vec_smem_bytes(int64_t nao_max, int64_t nsx, int64_t nax) {
 int64_t mode_smem_bytes(int mode, int64_t nao_max, int64_t nsx, int64_t nax) {
   const int64_t nex = (nao_max + 15) & ~15;
   const int64_t nmat = mode == 1 ? 3 : mode == 2 ? 1 : 0;
-  return vec_smem_bytes(nao_max, nsx, nax) + nmat * nex * (nex + 4) * 8;
+  return vec_smem_bytes(nao_max, nsx, nax, mode != 1) + nmat * nex * (nex + 4) * 8;
 }
 
 #define XTB_SCF_ARGS                                                                                                              \

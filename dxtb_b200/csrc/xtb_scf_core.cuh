@@ -32,6 +32,8 @@ struct Ctx {
   int *pp, *qq, *occl;
   double *jq, *jm, *jr;          // block-Jacobi scratch: accumulated rotations / sub-problem copies / rotation params
   bool smem;                     // matrices live in shared memory
+  bool defer;                    // Jacobi: Q double buffered, V pass deferred into the next round's sub-problem phase
+  long long tp1, tp2, tjac;      // XTB_PROFILE_PHASES: cycles in the sub-problem phase / rotation pass / whole eigensolver
   const int *ao_sh, *sh_atom, *at_sh0, *at_nsh, *sh_ao, *sh_l;
   const double* gam3;            // at_par base (stride XTB_ATPAR)
   double *xh, *fh;               // Anderson history [gen+1][n] (global)
@@ -92,6 +94,10 @@ __device__ void gemm_tn(int ne, int K, const double* __restrict__ L, const doubl
   __syncthreads();
 }
 
+#ifndef XTB_DEFER_NBP_MAX
+#define XTB_DEFER_NBP_MAX 16
+#endif
+constexpr int XTB_DEFER_NBP = XTB_DEFER_NBP_MAX;  // up to this many block pairs (nao <= 256) the accumulated rotations are double buffered
 constexpr int NGRP = 8;  // sub-problems solved concurrently (one warp each; every warp has its own 16x16 copy)
 
 constexpr int JB = 8;        // Jacobi block size
@@ -123,22 +129,75 @@ XTB_DEV int bp_index(int I, int J, int l) { return (l < JB ? I * JB : J * JB - J
 //   nblk-1 round-robin rounds in which the 64 cross pairs of a block pair are rotated: every index pair once.
 // Compared with rotating the full matrix after every scalar rotation round this moves A and V through
 // shared memory ~10x instead of ~80x per sweep.  Returns the number of sweeps, or -sweeps if not converged.
-template <bool AS, bool VS>
+template <bool AS, bool VS, bool DEFER = false>
 __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, int nrow, double tol, int maxsweeps) {
   const int ne = c.ne, ld = c.ld;
   const int nblk = ne / JB, nbp = nblk / 2, ntile = ne / 8;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int NW = NT / 32;
   constexpr int NG = NGRP;  // warps that solve sub-problems concurrently
-  double* Qs = c.jq;  // [nbp][16][QLD]
-  double* Ms = c.jm;  // [NG][16][MLD]  sub-problem copy of the group
-  int* bij = c.pp;    // [nbp][2] blocks of the pairs of this round
-  XTB_ASSUME_SHARED(bij);
-  XTB_ASSUME_SHARED(Qs); XTB_ASSUME_SHARED(Ms);
+  double* Qs0 = c.jq;  // [2][nbp][16][QLD]  accumulated rotations, double buffered by round parity
+  double* Ms = c.jm;   // [NG][16][MLD]  sub-problem copy of a warp
+  int* bij0 = c.pp;    // [2][nbp][2] blocks of the pairs of a round
+  XTB_ASSUME_SHARED(bij0);
+  XTB_ASSUME_SHARED(Qs0); XTB_ASSUME_SHARED(Ms);
   if (AS) XTB_ASSUME_SHARED(A);
   if (VS) XTB_ASSUME_SHARED(V);
   (void)nrow;
-  int sweep = 0;
+  const int nga = nbp < NG ? nbp : NG;  // warps busy with sub-problems; the others apply the previous round's Q to V
+  constexpr bool defer = DEFER;  // compile time: the non-deferred instantiation keeps one Q buffer and no pool logic
+  // V[:, idx] <- V[:, idx] Q (m8 n16 k16 tensor-core units) for the round whose rotations are in buffer `buf`
+  auto v_unit = [&](int buf, int u) {
+    const int g = lane >> 2, tg = lane & 3;
+    const double* Qb = Qs0 + (size_t)buf * nbp * (JB2 * QLD);
+    const int* bb = bij0 + buf * 2 * nbp;
+    const int k = (int)__fdividef((float)u + 0.5f, (float)ntile), rt = u - k * ntile;
+    const int I = bb[2 * k], J = bb[2 * k + 1];
+    const double* Q = Qb + k * (JB2 * QLD);
+    double* row = V + (size_t)(rt * 8 + g) * ld;
+    double af[4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) af[kk] = row[bp_index(I, J, 4 * kk + tg)];
+    double d[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) dmma884(d[nt][0], d[nt][1], af[kk], Q[(4 * kk + tg) * QLD + 8 * nt + g]);
+    }
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      const int col = bp_index(I, J, 8 * nt + 2 * tg);  // 2*tg and 2*tg+1 are in the same 8-block: contiguous
+      row[col] = d[nt][0];
+      row[col + 1] = d[nt][1];
+    }
+  };
+  // deferred mode: the V units of the previous round are a pool (counter set `cs`: [0] next unit, [1] sub-problem warps
+  // that finished this round); warps without a sub-problem work on it until the sub-problems are done, everybody drains
+  // the rest after the A update
+  int* ctr = bij0 + 4 * nbp;  // [2][2]
+  auto v_pool = [&](int buf, int cs, bool until_done) {
+    volatile int* vc = ctr + 2 * cs;
+    for (;;) {
+      if (until_done && vc[1] >= nga) break;
+      int u = 0;
+      if (lane == 0) u = atomicAdd(ctr + 2 * cs, 1);
+      u = __shfl_sync(0xffffffffu, u, 0);
+      if (u >= ntile * nbp) break;
+      v_unit(buf, u);
+    }
+  };
+  if (threadIdx.x < 4) ctr[threadIdx.x] = 0;  // made visible by the barriers of the first off-diagonal test
+  int sweep = 0, rc = 0;
+  bool pending = false;  // the V pass of the last finished round (buffer (rc - 1) & 1) is still to be done
+  auto flush = [&]() {
+    if (pending) {
+      v_pool((rc - 1) & 1, rc & 1, false);
+      pending = false;
+      __syncthreads();
+      if (threadIdx.x < 2) ctr[2 * (rc & 1) + threadIdx.x] = 0;  // the set is used again by the next round
+      __syncthreads();
+    }
+  };
   for (;;) {
     double off = 0.0;
     for (int i = warp; i < ne; i += NW) {
@@ -147,10 +206,16 @@ __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, in
         if (i != j) off = fmax(off, fabs(row[j]));
     }
     off = block_max(off, c.red);
-    if (off <= tol) return sweep;
-    if (sweep >= maxsweeps) return -sweep;
+    if (off <= tol) { flush(); return sweep; }
+    if (sweep >= maxsweeps) { flush(); return -sweep; }
     ++sweep;
-    for (int r = -1; r < nblk - 1; ++r) {
+    for (int r = -1; r < nblk - 1; ++r, ++rc) {
+      const int buf = defer ? (rc & 1) : 0;
+      double* Qs = Qs0 + (size_t)buf * nbp * (JB2 * QLD);
+      int* bij = bij0 + buf * 2 * nbp;
+#ifdef XTB_PROFILE_PHASES
+      const long long tq0 = clock64();
+#endif
       // ---- 1. sub-problems: ONE WARP per block pair, warp-synchronous (no CTA or named barriers) ------------------
       //   Every lane computes the rotation k = lane & 7 of the inner round (4 redundant copies, so there is no divergent
       //   branch and the parameters of any rotation are one shuffle away); the warp then updates the 16x16 copy M on the
@@ -161,8 +226,9 @@ __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, in
         if (r < 0) { I = 2 * w; J = 2 * w + 1; }
         else if (w == 0) { I = r; J = nblk - 1; }
         else {
-          I = (r + w) % (nblk - 1);
-          J = (r - w + 2 * (nblk - 1)) % (nblk - 1);
+          // (r + w) mod (nblk - 1), (r - w) mod (nblk - 1) with 0 <= r, w < nblk - 1: one conditional correction each
+          I = r + w; if (I >= nblk - 1) I -= nblk - 1;
+          J = r - w; if (J < 0) J += nblk - 1;
         }
         if (I > J) { const int t = I; I = J; J = t; }
         double* M = Ms + warp * (JB2 * MLD);
@@ -263,7 +329,20 @@ __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, in
           Q[qi * QLD + pq_] = ps * vp + pc * vq;
         }
       }
+      // meanwhile the warps without a sub-problem apply the PREVIOUS round's rotations to V (off the critical path:
+      // only A feeds the next sub-problems)
+      if (defer) {
+        if (warp < nga) {
+          __syncwarp();
+          if (lane == 0) atomicAdd(ctr + 2 * (rc & 1) + 1, 1);
+        } else if (pending) {
+          v_pool((rc - 1) & 1, rc & 1, true);
+        }
+      }
       __syncthreads();
+#ifdef XTB_PROFILE_PHASES
+      const long long tq1 = clock64();
+#endif
       // ---- 2. apply the rotations with fp64 tensor-core MMAs, one phase ---------------------------------------
       //   A: every 16x16 block (pair P, pair R), P >= R, is transformed on BOTH sides in registers, B' = Q_P^T (B Q_R),
       //      and mirrored into (R, P): A is read (half) and written once per block round (the intermediate T = B Q_R is re-laid out from the accumulator
@@ -272,9 +351,11 @@ __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, in
       {
         const int g = lane >> 2, tg = lane & 3;
         // A is symmetric: only the blocks P >= R are computed, P > R blocks are mirrored into (R, P)
-        const int nfused = nbp * (nbp + 1) / 2, nunit = nfused + ntile * nbp;
+        const int nfused = nbp * (nbp + 1) / 2, nunit = nfused + (defer ? 0 : ntile * nbp);
         for (int u = warp; u < nunit; u += NW) {
-          if (u < nfused) {
+          if (u >= nfused) {
+            v_unit(0, u - nfused);  // single Q buffer: V in the same phase
+          } else {
             int P = (int)((sqrtf(8.0f * (float)u + 1.0f) - 1.0f) * 0.5f);
             while ((P + 1) * (P + 2) / 2 <= u) ++P;
             while (P * (P + 1) / 2 > u) --P;
@@ -337,31 +418,19 @@ __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, in
                 }
               }
             }
-          } else {
-            const int rem = u - nfused;
-            const int k = (int)__fdividef((float)rem + 0.5f, (float)ntile), rt = rem - k * ntile;
-            const int I = bij[2 * k], J = bij[2 * k + 1];
-            const double* Q = Qs + k * (JB2 * QLD);
-            double* row = V + (size_t)(rt * 8 + g) * ld;
-            double af[4];
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) af[kk] = row[bp_index(I, J, 4 * kk + tg)];
-            double d[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-#pragma unroll
-              for (int nt = 0; nt < 2; ++nt) dmma884(d[nt][0], d[nt][1], af[kk], Q[(4 * kk + tg) * QLD + 8 * nt + g]);
-            }
-#pragma unroll
-            for (int nt = 0; nt < 2; ++nt) {
-              const int col = bp_index(I, J, 8 * nt + 2 * tg);  // 2*tg and 2*tg+1 are in the same 8-block: contiguous
-              row[col] = d[nt][0];
-              row[col + 1] = d[nt][1];
-            }
           }
         }
       }
+      if (defer) {
+        if (pending) v_pool((rc - 1) & 1, rc & 1, false);               // drain what the idle warps left
+        if (threadIdx.x < 2) ctr[2 * ((rc + 1) & 1) + threadIdx.x] = 0;  // counters of the next round (unused in this one)
+        pending = true;
+      }
       __syncthreads();
+#ifdef XTB_PROFILE_PHASES
+      c.tp1 += tq1 - tq0;
+      c.tp2 += clock64() - tq1;
+#endif
     }
   }
 }
