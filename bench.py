@@ -136,9 +136,9 @@ def run_reference(args) -> None:
 
 # --------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """SM clock / throttle-reason sampler.  Sampled from the timing loop itself (NVML, ~20 us per call) right after
-    a step has been enqueued, i.e. while the GPU is still executing it: a polling thread would fight the timing
-    loop for the GIL and distort the measurement."""
+    """SM clock / throttle-reason sampler (NVML, else nvidia-smi).  One sample is taken in the middle of the timed
+    region from a short-lived helper thread (the NVML call releases the GIL and can take milliseconds of driver time),
+    one right after the last step was enqueued; a continuously polling thread would distort the measurement."""
 
     def __init__(self, index: int):
         self.index, self.samples, self.reasons = index, [], set()
@@ -250,12 +250,18 @@ def run_ours(args) -> None:
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     iter_tensors = []
+    smp = None
     for s in range(args.warmup, nstep):
         step(devpos[s])
         if s == args.warmup + args.steps // 2:
-            sampler.sample()  # one NVML query inside the timed region (each costs milliseconds of driver time)
+            # one NVML query inside the timed region, from a helper thread: the call takes milliseconds of driver time
+            # on some boxes and releases the GIL, so the timing loop keeps enqueueing
+            smp = threading.Thread(target=sampler.sample)
+            smp.start()
         iter_tensors.append(calc.get_iterations())
     e1.record()
+    if smp is not None:
+        smp.join()
     sampler.sample()  # the backward kernels of the last step are still running
     barrier()
     clocks = sampler.stop()
@@ -324,7 +330,7 @@ def run_ours(args) -> None:
                        "opts": "dxtb defaults (EEQ guess, Anderson, x_atol 1e-4/1e-5, 300 K, D3(BJ) with synthetic table)", "note": NODISP_NOTE},
             "roofline": {"bound": "tensor", "pipe": "fp64 (DFMA/DMMA)", "kernel": "k_scf", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": 17.853184e6 / 148 * nb if MOLECULE == "caffeine" else None,  # DRAM bytes of k_scf per molecule, profiles/r1_scf_r6_ncu_full.csv
+                         "traffic": 18.090496e6 / 148 * nb if MOLECULE == "caffeine" else None,  # DRAM bytes of k_scf per molecule, profiles/r1_scf_r7_ncu_full.csv
 
                          "peak_source": "cuBLAS DGEMM 4096^3 best-of-6 measured in this run (MEASURED_PEAKS.json has no fp64 entry)",
                          "scf_kernel_ms": scf_avg_ms, "scf_share_of_step": scf_avg_ms / (ms / args.steps),
