@@ -139,7 +139,8 @@ int xtb_overlap_h0_fwd(const xtb_batch* b, const double* pos, const double* cn, 
 /* Bytes of workspace xtb_scf_run needs for this batch / option set. */
 int64_t xtb_scf_workspace_bytes(const xtb_batch* b, const xtb_scf_opts* o);
 /* EEQ guess of one molecule with nat >= XTB_EEQ_LARGE_NAT on the whole device (xtb_eeq_guess skips those): same system
-   and elimination order, every stage a grid-wide kernel.  at_off / eeq_off = at_off[mol] / eeq_off[mol]. */
+   and elimination order, every stage a grid-wide kernel.  Replaces the same reference call as xtb_eeq_guess
+   (scf/guess.py:118-120 -> tad-multicharge get_eeq_charges).  at_off / eeq_off = at_off[mol] / eeq_off[mol]. */
 #define XTB_EEQ_LARGE_NAT 256
 int xtb_eeq_guess_large(const xtb_batch* b, int32_t mol, int32_t nat, int64_t at_off, int64_t eeq_off, const double* pos,
                         const double* chrg, double* work, double* q_at, void* stream);
