@@ -178,8 +178,9 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
     const int nbpx = (lnao + 15) / 16;
     c.defer = MODE != 1 && nbpx <= XTB_DEFER_NBP;  // pays off when V lives in the L2-resident workspace
     c.jq = p; p += (c.defer ? 2 : 1) * nbpx * JB2 * QLD;  // double buffered by round parity if the V pass is deferred
-    c.jm = p; p += NGRP * JB2 * MLD;
-    c.jr = p; p += NGRP * 48;
+    c.ng = nbpx < NGRP ? nbpx : NGRP;
+    c.jm = p; p += c.ng * JB2 * MLD;
+    c.jr = nullptr;
   }
   p += ((p - sm) & 1);
   c.smem = MODE == 1;
@@ -283,7 +284,7 @@ int64_t vec_smem_bytes(int64_t nao_max, int64_t nsx, int64_t nax, bool v_global)
   int64_t d = 2 * (nmx + (nmx & 1)) + 8 * nmx + 2 * nsx + nax + 32 + 36 + (nmx + 2) / 2 + 1;
   d += d & 1;
   const int64_t nbpx = (nao_max + 15) / 16;
-  d += (v_global && nbpx <= XTB_DEFER_NBP ? 2 : 1) * nbpx * JB2 * QLD + NGRP * (JB2 * MLD + 48);  // block-Jacobi scratch
+  d += (v_global && nbpx <= XTB_DEFER_NBP ? 2 : 1) * nbpx * JB2 * QLD + (nbpx < NGRP ? nbpx : NGRP) * JB2 * MLD;  // block-Jacobi scratch
   d += d & 1;
   return d * 8;
 }

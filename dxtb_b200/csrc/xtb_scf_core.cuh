@@ -32,6 +32,7 @@ struct Ctx {
   int *pp, *qq, *occl;
   double *jq, *jm, *jr;          // block-Jacobi scratch: accumulated rotations / sub-problem copies / rotation params
   bool smem;                     // matrices live in shared memory
+  int ng;                        // Jacobi: number of 16x16 sub-problem copies = warps that solve sub-problems concurrently
   bool defer;                    // Jacobi: Q double buffered, V pass deferred into the next round's sub-problem phase
   long long tp1, tp2, tjac;      // XTB_PROFILE_PHASES: cycles in the sub-problem phase / rotation pass / whole eigensolver
   const int *ao_sh, *sh_atom, *at_sh0, *at_nsh, *sh_ao, *sh_l;
@@ -98,7 +99,7 @@ __device__ void gemm_tn(int ne, int K, const double* __restrict__ L, const doubl
 #define XTB_DEFER_NBP_MAX 16
 #endif
 constexpr int XTB_DEFER_NBP = XTB_DEFER_NBP_MAX;  // up to this many block pairs (nao <= 256) the accumulated rotations are double buffered
-constexpr int NGRP = 8;  // sub-problems solved concurrently (one warp each; every warp has its own 16x16 copy)
+constexpr int NGRP = 16;  // upper bound of sub-problems solved concurrently (one warp each with its own 16x16 copy; Ctx::ng)
 
 constexpr int JB = 8;        // Jacobi block size
 constexpr int JB2 = 2 * JB;  // indices of a block pair
@@ -135,7 +136,7 @@ __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, in
   const int nblk = ne / JB, nbp = nblk / 2, ntile = ne / 8;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int NW = NT / 32;
-  constexpr int NG = NGRP;  // warps that solve sub-problems concurrently
+  const int NG = c.ng;  // warps that solve sub-problems concurrently (each has its own 16x16 copy in shared memory)
   double* Qs0 = c.jq;  // [2][nbp][16][QLD]  accumulated rotations, double buffered by round parity
   double* Ms = c.jm;   // [NG][16][MLD]  sub-problem copy of a warp
   int* bij0 = c.pp;    // [2][nbp][2] blocks of the pairs of a round

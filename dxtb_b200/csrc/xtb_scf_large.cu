@@ -341,7 +341,7 @@ XTB_DEV int rr_partner(int nblk, int r, int x) {
 
 constexpr int SUB_MAT = OP * SLD;  // doubles of a 64 x 68 shared-memory matrix
 constexpr int SUB_NBP = OP / JB2;  // block pairs of the in-CTA solver on a 64 x 64 sub-problem
-constexpr int SUB_SMEM = (2 * SUB_MAT + SUB_NBP * JB2 * QLD + NGRP * (JB2 * MLD + 48) + 32 + 2 * SUB_NBP + 2) * 8;
+constexpr int SUB_SMEM = (2 * SUB_MAT + SUB_NBP * JB2 * QLD + SUB_NBP * JB2 * MLD + 32 + 2 * SUB_NBP + 2) * 8;
 
 // One CTA per outer block pair: 64 x 64 sub-problem on the diagonal tile, one in-CTA Jacobi sweep, Q -> global.
 __global__ void __launch_bounds__(NT, 1)
@@ -353,8 +353,9 @@ kl_jacobi_sub(const double* __restrict__ A, double* __restrict__ Qs, int ne, int
   c.ne = OP; c.ld = SLD; c.n = OP; c.np = OP / 2;
   double* p = ssm + 2 * SUB_MAT;
   c.jq = p; p += SUB_NBP * JB2 * QLD;
-  c.jm = p; p += NGRP * JB2 * MLD;
-  c.jr = p; p += NGRP * 48;
+  c.ng = SUB_NBP;
+  c.jm = p; p += SUB_NBP * JB2 * MLD;
+  c.jr = nullptr;
   c.red = p; p += 32;
   c.pp = (int*)p;
   c.status = 0; c.sweeps = 0; c.defer = false;
