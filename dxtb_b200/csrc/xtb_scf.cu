@@ -1,17 +1,17 @@
 // On-device self-consistent field loop of the GFN1-xTB single point: ONE CTA PER MOLECULE runs the whole
 // SCF (Fock build, eigensolve, Fermi filling, density, Mulliken populations, ES2/ES3 potential, Anderson
-// mixing, per-molecule convergence, final energies) with no host round trip.
+// mixing, per-molecule convergence, final energies) with no host round trip (scf/unrolling/default.py:71-136).
 //
 // Eigensolver: the generalised problem F C = S C eps is solved in the S-orthonormal basis of the previous
-// iteration's eigenvectors (C^T S C = I), i.e. A = C^T F C is nearly diagonal after the first iterations
-// and a cyclic parallel-order Jacobi (round-robin pairing, all n/2 rotations of a round applied in one
-// conflict-free pass over 2x2 blocks) converges in 2-3 sweeps instead of 6-8.  The rotations are applied
-// to C directly, so no separate back-transformation is needed.  The first basis is S^{-1/2}-like
-// (eigenvectors of S scaled by 1/sqrt(eigenvalue)), obtained with the same Jacobi routine.
+// iteration's eigenvectors (C^T S C = I), i.e. A = C^T F C is nearly diagonal after the first iterations and the
+// blocked two-sided Jacobi of xtb_scf_core.cuh (warp-synchronous 16x16 sub-problems + fp64 tensor-core rotation
+// passes) converges in 2-3 sweeps instead of 7-9.  The rotations are applied to C directly, so there is no
+// back-transformation.  The first basis is C0 = L^-T from an in-CTA Cholesky factorisation S = L L^T, followed by
+// one Newton-Schulz re-orthonormalisation step.
 //
-// Matrices (C, A/F, X/P) live in shared memory when 3*ne*ld*8 B fit (nao <= ~96), otherwise in a global
-// workspace (L2-resident for the active CTAs).  Leading dimension ld is odd so that both row and column
-// accesses of fp64 data are bank-conflict free.
+// Kernel variants (template parameter MODE = xtb_scf_opts::use_smem): 1 = C, A/F/P and X in shared memory (nao <= 80),
+// 2 = only A in shared memory, C and X in the L2-resident workspace (nao <= ~128), 0 = all three in the workspace.
+// Leading dimension ld = ne + 4 (== 4 mod 16): every DMMA fragment load is bank-conflict free.
 #include "xtb_scf_core.cuh"
 #ifdef XTB_PROFILE_PHASES
 #include <cstdio>

@@ -12,9 +12,9 @@ namespace {
 //   primary   (XTB_MINB = 1): 1 CTA/SM, up to 128 registers per thread (no spills; measured 8 % faster than 1024
 //                             threads x 64 registers) -- the shared-memory variant, the global-memory variant for
 //                             small buckets, and the C entry points;
-//   secondary (-DXTB_SECONDARY -DXTB_MINB=2): the global-memory variant at 2 CTAs/SM (64 registers), so that one
-//                             molecule's latency-bound sub-problem phase overlaps the other's L2-bound tensor-core
-//                             passes.  Exports only xtb_scf_launch_global_512().
+//   secondary (-DXTB_SECONDARY -DXTB_MINB=2): the global-memory and hybrid variants at 2 CTAs/SM (64 registers), so that
+//                             one molecule's latency-bound sub-problem phase overlaps the other's L2-bound tensor-core
+//                             passes.  Exports only xtb_scf_launch_2cta().
 #ifndef XTB_NT
 #define XTB_NT 512
 #endif
@@ -30,7 +30,7 @@ struct Ctx {
   const double *S, *H0, *gam;    // global, n x n / ns x ns
   double *eps, *srt, *focc, *v, *vnew, *q, *n0, *eorb, *qsh, *vsh, *qat, *red, *cs;
   int *pp, *qq, *occl;
-  double *jq, *jm, *jr;          // block-Jacobi scratch: accumulated rotations / sub-problem copies / rotation params
+  double *jq, *jm, *jr;          // block-Jacobi scratch: accumulated rotations / sub-problem copies / (unused)
   bool smem;                     // matrices live in shared memory
   int ng;                        // Jacobi: number of 16x16 sub-problem copies = warps that solve sub-problems concurrently
   bool defer;                    // Jacobi: Q double buffered, V pass deferred into the next round's sub-problem phase
