@@ -305,11 +305,14 @@ int64_t mode_smem_bytes(int mode, int64_t nao_max, int64_t nsx, int64_t nax) {
 template <int MODE>
 int launch_mode(XTB_SCF_ARGS) {
   const int64_t smem = mode_smem_bytes(MODE, lnao, lnsh, lnat);
-  static int64_t configured = 0;
-  if (smem > configured) {
+  static int64_t configured[64] = {};  // function attributes are per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return -5;
+  if (smem > configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(k_scf<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    configured = smem;
+    configured[dev] = smem;
   }
   k_scf<MODE><<<nblocks, NT, (size_t)smem, st>>>(*b, *o, S, H0, gamma, nel_ab, q0_at, work, q_orb, q_sh, q_at, v_orb, e_atom, fenergy, emo,
                                                   occ, iterations, status, P, W);

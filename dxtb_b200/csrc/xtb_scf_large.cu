@@ -605,30 +605,41 @@ extern "C" int xtb_scf_run_large(const xtb_batch* b, const xtb_scf_opts* o, int3
          *eorb = vecp + 7 * (size_t)nmx;
   const int* occl = (const int*)(vecp + 8 * (size_t)nmx + 2 * (size_t)nsh + nat + 32 + 36);
 
-  static bool configured = false;
-  if (!configured) {
-    int e = set_smem(kl_gemm_tn, 4 * GK * GLD * 8);
-    if (!e) e = set_smem(kl_jacobi_sub, SUB_SMEM);
-    if (!e) e = set_smem(kl_jacobi_pass, PASS_SMEM);
-    if (e) return e;
-    configured = true;
+  static bool configured[64] = {};  // function attributes are per device
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return -5;
+    if (!configured[dev]) {
+      int e = set_smem(kl_gemm_tn, 4 * GK * GLD * 8);
+      if (!e) e = set_smem(kl_jacobi_sub, SUB_SMEM);
+      if (!e) e = set_smem(kl_jacobi_pass, PASS_SMEM);
+      if (e) return e;
+      configured[dev] = true;
+    }
   }
-  static int n_sm = 0;
-  if (n_sm == 0) {
+  int n_sm = 0;
+  {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   }
-  // second stream (highest priority) and events for the sub-problem / pass overlap of the Jacobi rounds
-  static cudaStream_t side = nullptr;
-  static cudaEvent_t ev_a = nullptr, ev_s = nullptr;
-  if (!side) {
+  // second stream (highest priority) and events for the sub-problem / pass overlap of the Jacobi rounds, per device
+  constexpr int kMaxDev = 64;
+  static cudaStream_t side_s[kMaxDev] = {};
+  static cudaEvent_t ev_a_s[kMaxDev] = {}, ev_s_s[kMaxDev] = {};
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  if (cur_dev < 0 || cur_dev >= kMaxDev) return -5;
+  if (!side_s[cur_dev]) {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
-    if (cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, hi) != cudaSuccess) return -5;
-    if (cudaEventCreateWithFlags(&ev_a, cudaEventDisableTiming) != cudaSuccess) return -5;
-    if (cudaEventCreateWithFlags(&ev_s, cudaEventDisableTiming) != cudaSuccess) return -5;
+    if (cudaStreamCreateWithPriority(&side_s[cur_dev], cudaStreamNonBlocking, hi) != cudaSuccess) return -5;
+    if (cudaEventCreateWithFlags(&ev_a_s[cur_dev], cudaEventDisableTiming) != cudaSuccess) return -5;
+    if (cudaEventCreateWithFlags(&ev_s_s[cur_dev], cudaEventDisableTiming) != cudaSuccess) return -5;
   }
+  cudaStream_t side = side_s[cur_dev];
+  cudaEvent_t ev_a = ev_a_s[cur_dev], ev_s = ev_s_s[cur_dev];
   const int ew_grid = 4 * n_sm;  // elementwise kernels: grid-stride
   LargeState hs;
   auto read_state = [&]() -> int {
