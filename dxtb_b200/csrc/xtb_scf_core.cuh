@@ -165,6 +165,7 @@ __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, in
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt) dmma884(d[nt][0], d[nt][1], af[kk], Q[(4 * kk + tg) * QLD + 8 * nt + g]);
     }
+    __syncwarp();  // in-place update of the 8 x 16 strip
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt) {
       const int col = bp_index(I, J, 8 * nt + 2 * tg);  // 2*tg and 2*tg+1 are in the same 8-block: contiguous
@@ -405,6 +406,7 @@ __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, in
               dmma884(d[1][0][0], d[1][0][1], a1, bfr[0]);
               dmma884(d[1][1][0], d[1][1][1], a1, bfr[1]);
             }
+            __syncwarp();  // every lane's reads of this block precede the MMAs; made explicit for the in-place update
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
               double* row = A + (size_t)bp_index(IP, JP, 8 * mt + g) * ld;

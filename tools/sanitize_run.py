@@ -1,0 +1,43 @@
+#!/usr/bin/env python
+"""Tiny workload for compute-sanitizer (memcheck / racecheck / synccheck): every kernel variant once, energy + forces.
+    compute-sanitizer --tool racecheck python tools/sanitize_run.py"""
+import json, os, sys
+from pathlib import Path
+import torch
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from dxtb_b200 import GFN1Calculator
+mols = json.load(open(ROOT / "tests/golden/molecules.json"))
+dev = torch.device("cuda:0")
+
+def run(names, override=None, **env):
+    for k, v in env.items():
+        os.environ[k] = str(v)
+    nat = max(len(mols[n]["numbers"]) for n in names)
+    numbers = torch.zeros((len(names), nat), dtype=torch.long)
+    pos = torch.zeros((len(names), nat, 3), dtype=torch.float64)
+    chrg = torch.zeros(len(names), dtype=torch.float64)
+    for i, n in enumerate(names):
+        m = mols[n]
+        k = len(m["numbers"])
+        numbers[i, :k] = torch.tensor(m["numbers"]); pos[i, :k] = torch.tensor(m["positions"], dtype=torch.float64); chrg[i] = m["charge"]
+    calc = GFN1Calculator(numbers.to(dev), opts={"exclude": ["disp"], "maxiter": int(os.environ.get("SAN_MAXITER", "3"))}, device=dev, dtype=torch.float64)
+    calc._use_smem_override = override
+    p = pos.to(dev).requires_grad_(True)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        e = calc.get_energy(p, chrg.to(dev))
+    (g,) = torch.autograd.grad(e.sum(), p)
+    torch.cuda.synchronize()
+    print(names, calc._variants, [round(float(x), 6) for x in e])
+
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+if which in ("all", "smem"):
+    run(["H2O", "caffeine"])                                        # variant 1
+if which in ("all", "hybrid"):
+    run(["LYS_xao"])                                                # variant 2 (V pass pooled)
+if which in ("all", "global"):
+    run(["nicotine", "H2O"], override=0)                            # variant 0 (forced)
+if which in ("all", "large"):
+    run(["H2O", "caffeine"], DXTB_B200_LARGE_MIN_NAO=1)            # variant 3
