@@ -14,7 +14,7 @@ CSRC = ROOT / "csrc"
 INCLUDE = ROOT.parent / "include"
 SO_PATH = ROOT / "_C.so"
 # (source, object suffix, extra flags): xtb_scf.cu is built twice, see the comment at its top
-SOURCES = [("xtb_geometry.cu", "", []), ("xtb_integrals.cu", "", []), ("xtb_scf.cu", "", []), ("xtb_scf_large.cu", "", []), ("xtb_scf.cu", ".2cta", ["-DXTB_SECONDARY", "-DXTB_MINB=2"])]
+SOURCES = [("xtb_geometry.cu", "", []), ("xtb_integrals.cu", "", []), ("xtb_scf.cu", "", []), ("xtb_scf_large.cu", "", []), ("xtb_scf.cu", ".2cta", ["-DXTB_SECONDARY", "-DXTB_MINB=2", "-DXTB_JACOBI_SMALL_SIN=0.0"])]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "-diag-suppress", "177",

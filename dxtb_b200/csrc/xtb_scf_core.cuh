@@ -101,6 +101,9 @@ __device__ void gemm_tn(int ne, int K, const double* __restrict__ L, const doubl
 constexpr int XTB_DEFER_NBP = XTB_DEFER_NBP_MAX;  // up to this many block pairs (nao <= 256) the accumulated rotations are double buffered
 constexpr int NGRP = 16;  // upper bound of sub-problems solved concurrently (one warp each with its own 16x16 copy; Ctx::ng)
 
+#ifndef XTB_JACOBI_SMALL_SIN
+#define XTB_JACOBI_SMALL_SIN 0.03  // sub-problems whose rotations all have |sin| below this take the small-angle shortcut
+#endif
 constexpr int JB = 8;        // Jacobi block size
 constexpr int JB2 = 2 * JB;  // indices of a block pair
 constexpr int MLD = 24;      // leading dimension of the 16x16 sub-problem copy (== 8 mod 16: conflict-free 2x2-block updates)
@@ -263,7 +266,50 @@ __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, in
         const int qrow = 2 * ((lane >> 3) & 1) + (lane >> 4);
         double pc = 1.0, ps = 0.0;  // rotation of the previous inner round (for the Q update)
         int pp_ = 0, pq_ = 0;
-        for (int t = 0; t < nin; ++t) {
+        // Small-angle shortcut: all rotations of the sub-problem from the UN-UPDATED copy, two per lane (inner rounds
+        // lane >> 3 and (lane >> 3) + 4), i.e. without the dependent chain rot(t) -> M(t) -> rot(t+1).  Rotations by small
+        // angles commute to second order, so the sub-matrix is left with O(angle^2) off-diagonals exactly as after the
+        // sequential rounds (quadratic regime); Q is still a product of exact Givens rotations.  Taken only if every angle
+        // of the sub-problem is small (warp-uniform decision); otherwise the sequential rounds below.
+        bool small_angles = false;
+        if (XTB_JACOBI_SMALL_SIN > 0.0) {
+          double cr[2], sr[2];
+#pragma unroll
+          for (int sl = 0; sl < 2; ++sl) {
+            const int t = (lane >> 3) + 4 * sl;
+            int p, q;
+            pair_of(t < nin ? t : 0, k, p, q);
+            const double app = M[p * MLD + p], aqq = M[q * MLD + q], apq = M[p * MLD + q];
+            const double d = aqq - app;
+            const double x = fma(d, d, 4.0 * apq * apq);
+            const double ir = rsqrt_nr(fmax(x, 1e-280));
+            const double c2 = fma(0.5 * fabs(d), ir, 0.5);
+            const double ic = rsqrt_nr(c2);
+            const bool rot = x > 1e-280 && t < nin;
+            cr[sl] = rot ? c2 * ic : 1.0;
+            sr[sl] = rot ? copysign(apq * ir, d * apq) * ic : 0.0;
+          }
+          small_angles = __all_sync(0xffffffffu, fabs(sr[0]) <= XTB_JACOBI_SMALL_SIN && fabs(sr[1]) <= XTB_JACOBI_SMALL_SIN);
+          if (small_angles) {
+            for (int t = 0; t < nin; ++t) {
+              const int src = k + 8 * (t & 3);
+              const double cv = __shfl_sync(0xffffffffu, (t >> 2) ? cr[1] : cr[0], src);
+              const double sv = __shfl_sync(0xffffffffu, (t >> 2) ? sr[1] : sr[0], src);
+              int p, q;
+              pair_of(t, k, p, q);
+              double vp[4], vq[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { vp[j] = Q[(qrow + 4 * j) * QLD + p]; vq[j] = Q[(qrow + 4 * j) * QLD + q]; }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                Q[(qrow + 4 * j) * QLD + p] = cv * vp[j] - sv * vq[j];
+                Q[(qrow + 4 * j) * QLD + q] = sv * vp[j] + cv * vq[j];
+              }
+              __syncwarp();
+            }
+          }
+        }
+        for (int t = 0; t < nin && !small_angles; ++t) {
           int p, q;
           pair_of(t, k, p, q);
           const double app = M[p * MLD + p], aqq = M[q * MLD + q], apq = M[p * MLD + q];
@@ -322,7 +368,7 @@ __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, in
           pc = cs_; ps = sn; pp_ = p; pq_ = q;
           __syncwarp();
         }
-        // rotations of the last inner round
+        // rotations of the last inner round (pc = 1, ps = 0 after the small-angle path: no-op)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int qi = qrow + 4 * j;
