@@ -331,7 +331,7 @@ def run_ours(args) -> None:
                        "opts": "dxtb defaults (EEQ guess, Anderson, x_atol 1e-4/1e-5, 300 K, D3(BJ) with synthetic table)", "note": NODISP_NOTE},
             "roofline": {"bound": "tensor", "pipe": "fp64 (DFMA/DMMA)", "kernel": "k_scf", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": 18.090496e6 / 148 * nb if MOLECULE == "caffeine" else None,  # DRAM bytes of k_scf per molecule, profiles/r1_scf_r7_ncu_full.csv
+                         "traffic": 17.909760e6 / 148 * nb if MOLECULE == "caffeine" else None,  # DRAM bytes of k_scf per molecule, profiles/r1_scf_r8_ncu_full.csv
 
                          "peak_source": "cuBLAS DGEMM 4096^3 best-of-6 measured in this run (MEASURED_PEAKS.json has no fp64 entry)",
                          "scf_kernel_ms": scf_avg_ms, "scf_share_of_step": scf_avg_ms / (ms / args.steps),

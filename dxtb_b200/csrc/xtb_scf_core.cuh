@@ -102,7 +102,7 @@ constexpr int XTB_DEFER_NBP = XTB_DEFER_NBP_MAX;  // up to this many block pairs
 constexpr int NGRP = 16;  // upper bound of sub-problems solved concurrently (one warp each with its own 16x16 copy; Ctx::ng)
 
 #ifndef XTB_JACOBI_SMALL_SIN
-#define XTB_JACOBI_SMALL_SIN 0.03  // sub-problems whose rotations all have |sin| below this take the small-angle shortcut
+#define XTB_JACOBI_SMALL_SIN 0.1  // sub-problems whose rotations all have |sin| below this take the small-angle shortcut
 #endif
 constexpr int JB = 8;        // Jacobi block size
 constexpr int JB2 = 2 * JB;  // indices of a block pair

@@ -22,5 +22,6 @@ for name, nb in [("caffeine", 1024), ("LYS_xao", 592), ("capsaicin", 592), ("C60
         calc.get_energy(p, chrg)
         torch.cuda.synchronize()
         ts.append(calc.scf_events[0][0].elapsed_time(calc.scf_events[0][1]))
-    out.append(f"{name}{calc._variants} {min(ts[1:]):.2f}")
+    st = calc.cache["status"]
+    out.append(f"{name}{calc._variants} {min(ts[1:]):.2f} (sw {float((st >> 8).float().mean()):.1f} it {int(calc.get_iterations().sum())})")
 print(os.environ.get("DXTB_B200_LIB", "default"), " | ".join(out))
