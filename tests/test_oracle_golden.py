@@ -153,3 +153,29 @@ def test_atomic_scf_energies_all_elements(energies, tblite_units):
             r = O.singlepoint([z], [[0.0, 0.0, 0.0]], opts=dict(exclude=("disp",), x_atol=1e-9, x_atol_max=1e-9, maxiter=300, guess="sad"))
         worst = max(worst, abs(r.e_scf - refs[z - 1]))
     assert worst < 1e-7
+
+
+def test_readme_batch_example_bounds_the_missing_dispersion_term():
+    """examples/batch-2.py:83-93 prints dxtb's own default-path energies (10 digits, D3(BJ) included) for the formamide
+    dimer / monomer.  The D3 reference table is third-party data, so the oracle can only be compared
+    without dispersion: the implied D3 energies must be small, negative and attractive for the dimer -- a bound, not a pin
+    (it catches any error of the SCF / repulsion part beyond ~1 mEh and a wrong sign or unit of the total)."""
+    sym = {"C": 6, "N": 7, "H": 1, "O": 8}
+    n1 = [sym[s] for s in "C C N N H H H H H H O O".split()]
+    p1 = np.array([[-3.81469488143921, 0.09993441402912, 0], [3.81469488143921, -0.09993441402912, 0],
+                   [-2.66030049324036, -2.15898251533508, 0], [2.66030049324036, 2.15898251533508, 0],
+                   [-0.73178529739380, -2.28237795829773, 0], [-5.89039325714111, -0.02589114569128, 0],
+                   [-3.71254944801331, -3.73605775833130, 0], [3.71254944801331, 3.73605775833130, 0],
+                   [0.73178529739380, 2.28237795829773, 0], [5.89039325714111, 0.02589114569128, 0],
+                   [-2.74426102638245, 2.16115570068359, 0], [2.74426102638245, -2.16115570068359, 0]])
+    n2 = [sym[s] for s in "C O N H H H".split()]
+    p2 = np.array([[-0.55569743203406, 1.09030425468557, 0], [0.51473634678469, 3.15152550263611, 0],
+                   [0.59869690244446, -1.16861263789477, 0], [-0.45355203669134, -2.74568780438064, 0],
+                   [2.52721209544999, -1.29200800956867, 0], [-2.63139587595376, 0.96447869452240, 0]])
+    ed = []
+    for n, p, ref in ((n1, p1, -23.2835232516), (n2, p2, -11.6302093800)):
+        r = O.singlepoint(np.array(n), p, 0.0, opts={"exclude": ("disp",)})
+        assert r.converged
+        ed.append(ref - r.energy)  # implied D3(BJ) energy
+    assert -6.0e-3 < ed[0] < -2.0e-3 and -2.0e-3 < ed[1] < -0.5e-3
+    assert -3.0e-3 < ed[0] - 2 * ed[1] < -0.5e-3  # dispersion part of the dimer interaction energy is attractive
