@@ -239,12 +239,6 @@ __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, in
         double* M = Ms + warp * (JB2 * MLD);
         double* Q = Qs + w * (JB2 * QLD);
         if (lane == 0) { bij[2 * w] = I; bij[2 * w + 1] = J; }
-        for (int e = lane; e < JB2 * JB2; e += 32) {
-          const int rr = e >> 4, cc = e & 15;
-          M[rr * MLD + cc] = A[(size_t)bp_index(I, J, rr) * ld + bp_index(I, J, cc)];
-          Q[rr * QLD + cc] = (rr == cc) ? 1.0 : 0.0;
-        }
-        __syncwarp();
         const int nin = (r < 0) ? JB - 1 : JB;
         const bool self = r < 0;
         // index pair (p, q) of rotation k in inner round t
@@ -279,7 +273,9 @@ __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, in
             const int t = (lane >> 3) + 4 * sl;
             int p, q;
             pair_of(t < nin ? t : 0, k, p, q);
-            const double app = M[p * MLD + p], aqq = M[q * MLD + q], apq = M[p * MLD + q];
+            // rotation inputs straight from A: the 16x16 copy is only made if the sequential rounds are needed
+            const size_t gp = (size_t)bp_index(I, J, p), gq = (size_t)bp_index(I, J, q);
+            const double app = A[gp * ld + gp], aqq = A[gq * ld + gq], apq = A[gp * ld + gq];
             const double d = aqq - app;
             const double x = fma(d, d, 4.0 * apq * apq);
             const double ir = rsqrt_nr(fmax(x, 1e-280));
@@ -297,17 +293,35 @@ __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, in
               const double sv = __shfl_sync(0xffffffffu, (t >> 2) ? sr[1] : sr[0], src);
               int p, q;
               pair_of(t, k, p, q);
-              double vp[4], vq[4];
+              if (t == 0) {
+                // first layer on the identity: columns p, q of J_0 written directly (the 8 rotations cover all 16 columns)
 #pragma unroll
-              for (int j = 0; j < 4; ++j) { vp[j] = Q[(qrow + 4 * j) * QLD + p]; vq[j] = Q[(qrow + 4 * j) * QLD + q]; }
+                for (int j = 0; j < 4; ++j) {
+                  const int qi = qrow + 4 * j;
+                  Q[qi * QLD + p] = (qi == p) ? cv : (qi == q) ? -sv : 0.0;
+                  Q[qi * QLD + q] = (qi == p) ? sv : (qi == q) ? cv : 0.0;
+                }
+              } else {
+                double vp[4], vq[4];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                Q[(qrow + 4 * j) * QLD + p] = cv * vp[j] - sv * vq[j];
-                Q[(qrow + 4 * j) * QLD + q] = sv * vp[j] + cv * vq[j];
+                for (int j = 0; j < 4; ++j) { vp[j] = Q[(qrow + 4 * j) * QLD + p]; vq[j] = Q[(qrow + 4 * j) * QLD + q]; }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  Q[(qrow + 4 * j) * QLD + p] = cv * vp[j] - sv * vq[j];
+                  Q[(qrow + 4 * j) * QLD + q] = sv * vp[j] + cv * vq[j];
+                }
               }
               __syncwarp();
             }
           }
+        }
+        if (!small_angles) {
+          for (int e = lane; e < JB2 * JB2; e += 32) {
+            const int rr = e >> 4, cc = e & 15;
+            M[rr * MLD + cc] = A[(size_t)bp_index(I, J, rr) * ld + bp_index(I, J, cc)];
+            Q[rr * QLD + cc] = (rr == cc) ? 1.0 : 0.0;
+          }
+          __syncwarp();
         }
         for (int t = 0; t < nin && !small_angles; ++t) {
           int p, q;
@@ -368,9 +382,9 @@ __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, in
           pc = cs_; ps = sn; pp_ = p; pq_ = q;
           __syncwarp();
         }
-        // rotations of the last inner round (pc = 1, ps = 0 after the small-angle path: no-op)
+        // rotations of the last inner round of the sequential path
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 4 && !small_angles; ++j) {
           const int qi = qrow + 4 * j;
           const double vp = Q[qi * QLD + pp_], vq = Q[qi * QLD + pq_];
           Q[qi * QLD + pp_] = pc * vp - ps * vq;
