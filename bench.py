@@ -15,7 +15,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 from pathlib import Path
 
@@ -137,9 +136,9 @@ def run_reference(args) -> None:
 
 # --------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """SM clock / throttle-reason sampler (NVML, else nvidia-smi).  One sample is taken in the middle of the timed
-    region from a short-lived helper thread (the NVML call releases the GIL and can take milliseconds of driver time),
-    one right after the last step was enqueued; a continuously polling thread would distort the measurement."""
+    """SM clock / throttle-reason sampler (NVML, else nvidia-smi): one sample right after the last timed step was
+    enqueued, while the GPU still executes the timed region.  Inside the launch loop the SM clock is measured on the
+    device instead (xtb_clock_probe): NVML queries there stall kernel submission (measured 5..80 ms per query)."""
 
     def __init__(self, index: int):
         self.index, self.samples, self.reasons = index, [], set()
@@ -251,21 +250,24 @@ def run_ours(args) -> None:
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     iter_tensors = []
-    smp = None
+    # SM clock under load: a 20 us on-device probe (clock64 / globaltimer) after every step -- no NVML call inside the launch
+    # loop: an in-process NVML query (and even a one-shot nvidia-smi in another process) was measured to stall kernel
+    # submission by 5..80 ms on some boxes.  Throttle reasons + the NVML clock are read once, right after the last step
+    # has been enqueued, i.e. while the GPU is still executing the timed region.
+    from dxtb_b200 import _abi
+    probe = torch.zeros(args.steps, dtype=torch.float64, device=dev)
     for s in range(args.warmup, nstep):
         step(devpos[s])
-        if s == args.warmup + args.steps // 2:
-            # one NVML query inside the timed region, from a helper thread: the call takes milliseconds of driver time
-            # on some boxes and releases the GIL, so the timing loop keeps enqueueing
-            smp = threading.Thread(target=sampler.sample)
-            smp.start()
+        _abi.lib().xtb_clock_probe(probe[s - args.warmup :].data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
         iter_tensors.append(calc.get_iterations())
     e1.record()
-    if smp is not None:
-        smp.join()
-    sampler.sample()  # the backward kernels of the last step are still running
+    if rank == 0:
+        sampler.sample()
     barrier()
     clocks = sampler.stop()
+    clocks["sm_mhz_on_device"] = [round(float(x), 1) for x in probe.cpu()]
+    if clocks["sm_mhz"] is None:
+        clocks["sm_mhz"] = float(np.median(clocks["sm_mhz_on_device"]))
     iters_total = sum(int(t.sum()) for t in iter_tensors) + 2 * nb * args.steps  # + final solve + start basis per molecule
     ms = e0.elapsed_time(e1)
     scf_ms = [a.elapsed_time(b) for a, b in calc.scf_events]

@@ -60,6 +60,7 @@ class XtbScfOpts(C.Structure):
 
 EXPORTS = {
     "xtb_version": (C.c_int, []),
+    "xtb_clock_probe": (C.c_int, [_vp, _vp]),
     "xtb_sizeof_batch": (C.c_int, []),
     "xtb_sizeof_scf_opts": (C.c_int, []),
     "xtb_geometry_fwd": (C.c_int, [_vp] * 6),

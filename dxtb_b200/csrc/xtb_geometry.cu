@@ -486,6 +486,25 @@ __global__ void k_d3_pairs(const xtb_batch b, const double* __restrict__ pos, co
 // ---------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------
+// Diagnostic: SM clock measured on the device (cycles of clock64 per nanosecond of globaltimer over ~20 us), so that a
+// benchmark can record the clock under load without an NVML query (which takes a driver lock that stalls kernel launches).
+__global__ void k_clock_probe(double* mhz) {
+  unsigned long long g0, g1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
+  const long long c0 = clock64();
+  do {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+  } while (g1 - g0 < 20000ull);
+  const long long c1 = clock64();
+  *mhz = 1.0e3 * (double)(c1 - c0) / (double)(g1 - g0);
+}
+
+extern "C" int xtb_clock_probe(double* mhz_out, void* stream) {
+  if (!mhz_out) return -1;
+  k_clock_probe<<<1, 1, 0, (cudaStream_t)stream>>>(mhz_out);
+  return launch_status();
+}
+
 extern "C" int xtb_version(void) { return 100; }
 extern "C" int xtb_sizeof_batch(void) { return (int)sizeof(xtb_batch); }
 extern "C" int xtb_sizeof_scf_opts(void) { return (int)sizeof(xtb_scf_opts); }

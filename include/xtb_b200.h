@@ -138,6 +138,10 @@ int xtb_overlap_h0_fwd(const xtb_batch* b, const double* pos, const double* cn, 
 
 /* Bytes of workspace xtb_scf_run needs for this batch / option set. */
 int64_t xtb_scf_workspace_bytes(const xtb_batch* b, const xtb_scf_opts* o);
+/* Diagnostic (bench.py): SM clock in MHz measured on the device over ~20 us (clock64 / globaltimer), written to the
+   device double *mhz_out; no reference counterpart. */
+int xtb_clock_probe(double* mhz_out, void* stream);
+
 /* EEQ guess of one molecule with nat >= XTB_EEQ_LARGE_NAT on the whole device (xtb_eeq_guess skips those): same system
    and elimination order, every stage a grid-wide kernel.  Replaces the same reference call as xtb_eeq_guess
    (scf/guess.py:118-120 -> tad-multicharge get_eeq_charges).  at_off / eeq_off = at_off[mol] / eeq_off[mol]. */
