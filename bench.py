@@ -108,7 +108,7 @@ def run_reference(args) -> None:
 
     os.environ["OMP_NUM_THREADS"] = "1"
     cores = os.cpu_count() or 1
-    nsample = 8 * cores  # bounded sample of the 1024-conformer batch per step
+    nsample = int(os.environ.get("BENCH_REF_SAMPLE_PER_CORE", "8")) * cores  # bounded sample of the 1024-conformer batch per step
     times = []
     with mp.get_context("fork").Pool(cores) as pool:
         pool.map(_oracle_one, _jobs(cores, 7), chunksize=1)  # start + warm every worker
