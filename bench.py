@@ -341,7 +341,7 @@ def run_ours(args) -> None:
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": 1, "kind": "port",
                              "sample": f"{CPU_SAMPLE} conformers energy+forces, oracle/gfn1_oracle.py single thread ({cpu_dt:.1f} s)"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": 22 * args.steps,
+            "gpu_launches": 23 * args.steps,  # 13 forward + 9 backward kernels + the clock probe per step
             "clocks": clocks,
             "scf_iterations_mean": (iters_total / args.steps - 2 * nb) / nb,
             "parity": {"checked": len(idx), "max_abs_dE_Eh": de, "max_abs_dF_Eh_per_bohr": dg, "scf_iterations_equal": it_equal,
