@@ -144,7 +144,36 @@ def main():
             out[m.group(1)] = float(m.group(2))
         return out
 
+    num = r"[-+]?\d\.\d+e[-+]?\d+"
+
+    def floats_after(txt, start, key, stop):
+        blk = txt[txt.index(key, start):]
+        return [float(x) for x in re.findall(num, blk[: blk.index(stop)])]
+
+    # repulsion energies (fp64 literals) for the molecules whose geometries are in-tree: test_classical/test_repulsion/samples.py
+    rtxt = open(REF / "test/test_classical/test_repulsion/samples.py").read()
+    repulsion = {}
+    for name in ("H2", "H2O", "SiH4", "LYS_xao", "MB16_43_01"):
+        m = re.search(r'"%s": \{\s*"gfn1": torch\.tensor\(([-0-9.e+]+)\)' % re.escape(name), rtxt)
+        repulsion[name] = float(m.group(1))
+    # second / third order electrostatics at fixed charges: test_coulomb/samples.py
+    ctxt = open(REF / "test/test_coulomb/samples.py").read()
+    es2_shell = {}
+    for name in ("SiH4", "LiH"):
+        i = ctxt.index('"%s": {  # shell-resolved' % name)
+        es2 = float(re.search(r'"es2": torch\.tensor\(\s*([-0-9.e+]+)', ctxt[i:]).group(1))
+        es2_shell[name] = {"q_shell": floats_after(ctxt, i, '"q": torch.tensor(', "]"), "es2": es2,
+                           "grad": floats_after(ctxt, i, '"grad": torch.tensor(', "dtype")}
+    i = ctxt.index('"MB16_43_01": {')
+    es3_atom = {"MB16_43_01": {"q_atom": floats_after(ctxt, i, '"q": torch.tensor(', "]"),
+                               "es3": float(re.search(r'"es3": torch\.tensor\(\s*([-0-9.e+]+)', ctxt[i:]).group(1))}}
+
     energies = {
+        "repulsion_gfn1": repulsion,
+        "repulsion_source": "test/test_classical/test_repulsion/samples.py:50-420 (fp64 literals)",
+        "es2_shell_gfn1": es2_shell,
+        "es3_atom_gfn1": es3_atom,
+        "coulomb_source": "test/test_coulomb/samples.py:60-170, 576-660 (charges, ES2 energy and nuclear gradient at fixed shell charges; ES3 with float32-precision atomic charges; the LiH energy literal is a 0.0 placeholder there)",
         "scf_gfn1_tblite": {k: v for k, v in literals(REF / "test/test_scf/samples.py", "egfn1").items() if k in mols},
         "total_gfn1_tblite": literals(REF / "test/test_singlepoint/samples.py", "egfn1"),
         "eeq_guess_CH": [-0.11593066900969, -0.03864355757833, -0.03864355757833, -0.03864355757833, 0.11593066900969, 0.11593066900969],

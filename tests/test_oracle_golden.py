@@ -179,3 +179,48 @@ def test_readme_batch_example_bounds_the_missing_dispersion_term():
         ed.append(ref - r.energy)  # implied D3(BJ) energy
     assert -6.0e-3 < ed[0] < -2.0e-3 and -2.0e-3 < ed[1] < -0.5e-3
     assert -3.0e-3 < ed[0] - 2 * ed[1] < -0.5e-3  # dispersion part of the dimer interaction energy is attractive
+
+
+@pytest.mark.parametrize("name", ["H2", "H2O", "SiH4", "LYS_xao", "MB16_43_01"])
+def test_repulsion_energy_vs_reference_literals(mols, energies, name):
+    """Classical repulsion (components/classicals/repulsion/base.py:250-335) against the fp64 literals of
+    test/test_classical/test_repulsion/samples.py (same geometries as test/test_singlepoint/mols)."""
+    m = mols[name]
+    r = O.singlepoint(np.array(m["numbers"]), np.array(m["positions"]), float(m["charge"]), opts={"exclude": ("disp",), "maxiter": 1})
+    assert abs(r.e_rep - energies["repulsion_gfn1"][name]) < 1e-13
+
+
+@pytest.mark.parametrize("name", ["SiH4", "LiH"])
+def test_es2_shell_energy_and_gradient_at_fixed_charges(mols, energies, name):
+    """Shell-resolved second-order electrostatics (secondorder.py:374-382, 799-926; harmonic Hubbard average, gexp = 2):
+    energy 1/2 q^T gamma q and its nuclear gradient at the fixed shell charges of test/test_coulomb/samples.py:576-660."""
+    ref = energies["es2_shell_gfn1"][name]
+    m = mols[name]
+    mol = O.make_mol(np.array(m["numbers"]))
+    pos = np.array(m["positions"])
+    q = np.array(ref["q_shell"])
+    assert q.shape == (mol.nsh,)
+
+    def e(p):
+        return 0.5 * q @ O.gamma_shell(mol, p) @ q
+
+    if name != "LiH":  # the LiH energy literal is a 0.0 placeholder in the reference file
+        assert abs(e(pos) - ref["es2"]) < 1e-14
+    g = np.array(ref["grad"]).reshape(-1, 3)
+    fd, h = np.zeros_like(pos), 1e-5
+    for a in range(mol.nat):
+        for x in range(3):
+            pp, pm = pos.copy(), pos.copy()
+            pp[a, x] += h
+            pm[a, x] -= h
+            fd[a, x] = (e(pp) - e(pm)) / (2 * h)
+    assert np.abs(fd - g).max() < 1e-10
+
+
+def test_es3_atom_energy_at_fixed_charges(mols, energies):
+    """Third-order on-site electrostatics (thirdorder.py:246-276), 1/3 sum Gamma_A q_A^3, with the (float32-precision)
+    atomic charges of test/test_coulomb/samples.py:60-110."""
+    ref = energies["es3_atom_gfn1"]["MB16_43_01"]
+    mol = O.make_mol(np.array(mols["MB16_43_01"]["numbers"]))
+    q = np.array(ref["q_atom"])
+    assert abs(float((O.gam3(mol) * q**3).sum() / 3.0) - ref["es3"]) < 1e-8
