@@ -168,7 +168,20 @@ def main():
     es3_atom = {"MB16_43_01": {"q_atom": floats_after(ctxt, i, '"q": torch.tensor(', "]"),
                                "es3": float(re.search(r'"es3": torch\.tensor\(\s*([-0-9.e+]+)', ctxt[i:]).group(1))}}
 
+    # Fermi filling known answer: SiH4 orbital energies (test_wavefunction/samples.py:375-), occupations and electronic
+    # free energy at 5000 K (test_wavefunction/test_filling.py:185-268)
+    wtxt = open(REF / "test/test_wavefunction/samples.py").read()
+    i = wtxt.index('"SiH4": {')
+    eb = wtxt[wtxt.index('"emo": torch.tensor(', i):]
+    emo = [float(x) for x in re.findall(r"[-+]?\d\.\d+(?:e[-+]?\d+)?", eb[: eb.index(")")])][:17]
+    ftxt = open(REF / "test/test_wavefunction/test_filling.py").read()
+    j = ftxt.index("5000.0: emo.new_tensor(\n            [")
+    focc = [float(x) for x in re.findall(r"[-+]?\d\.\d+(?:e[-+]?\d+)?", ftxt[j + 10 : ftxt.index("]", j)])]
+    fen = float(re.search(r"5000\.0: emo\.new_tensor\(([-0-9.e+]+)\)", ftxt).group(1))
+    fermi = {"emo": emo, "nel": 8.0, "kelvin": 5000.0, "focc": focc, "fenergy": fen}
+
     energies = {
+        "fermi_sih4_5000K": fermi,
         "repulsion_gfn1": repulsion,
         "repulsion_source": "test/test_classical/test_repulsion/samples.py:50-420 (fp64 literals)",
         "es2_shell_gfn1": es2_shell,

@@ -224,3 +224,17 @@ def test_es3_atom_energy_at_fixed_charges(mols, energies):
     mol = O.make_mol(np.array(mols["MB16_43_01"]["numbers"]))
     q = np.array(ref["q_atom"])
     assert abs(float((O.gam3(mol) * q**3).sum() / 3.0) - ref["es3"]) < 1e-8
+
+
+def test_fermi_filling_known_answer_5000K(energies):
+    """Fermi smearing at 5000 K on the SiH4 orbital energies (wavefunction/filling.py:201-366) and the electronic free
+    energy kT sum ln(f^f (1-f)^(1-f)) (scf/base.py:586-594) against test/test_wavefunction/test_filling.py:185-268
+    (reference tolerance there: 1.5e-7)."""
+    ref = energies["fermi_sih4_5000K"]
+    par = O.params()
+    kt = ref["kelvin"] * par.kelvin2au
+    f = O.fermi_occupation(np.array([ref["nel"] / 2, ref["nel"] / 2]), np.array(ref["emo"]), kt)
+    assert np.abs(f.sum(0) - np.array(ref["focc"])).max() < 1e-8
+    o1, o2 = np.maximum(f, O.EPS), np.maximum(1.0 - f, O.EPS)
+    g = kt * float(np.sum(np.log(o1**o1 * o2**o2)))
+    assert abs(g - ref["fenergy"]) < 1e-8
