@@ -180,7 +180,19 @@ def main():
     fen = float(re.search(r"5000\.0: emo\.new_tensor\(([-0-9.e+]+)\)", ftxt).group(1))
     fermi = {"emo": emo, "nel": 8.0, "kelvin": 5000.0, "focc": focc, "fenergy": fen}
 
+    # Wiberg bond orders and Mulliken atomic charges of the converged GFN1 density: test_wavefunction/samples.py
+    wiberg = {}
+    for name in ("H2", "LiH", "SiH4"):
+        i = wtxt.index('"%s": {' % name)
+        wb = wtxt[wtxt.index('"wiberg": torch.tensor(', i):]
+        mc = wtxt[wtxt.index('"mulliken_charges": torch.tensor(', i):]
+        fl = r"[-+]?\d\.\d+(?:e[-+]?\d+)?"
+        wiberg[name] = {"wiberg": [float(x) for x in re.findall(fl, wb[: wb.index(")")])],
+                        "mulliken_charges": [float(x) for x in re.findall(fl, mc[: mc.index(")")])]}
+
     energies = {
+        "wiberg_gfn1": wiberg,
+        "wiberg_source": "test/test_wavefunction/samples.py (H2, LiH, SiH4: flattened nat x nat Wiberg matrix, 5-digit Mulliken charges)",
         "fermi_sih4_5000K": fermi,
         "repulsion_gfn1": repulsion,
         "repulsion_source": "test/test_classical/test_repulsion/samples.py:50-420 (fp64 literals)",

@@ -513,3 +513,21 @@ def test_large_system_path_reports_non_convergence(mols, monkeypatch):
     with pytest.warns(SCFConvergenceWarning):
         calc.get_energy(pos, chrg)
     assert int(calc.get_iterations()[0]) == 4
+
+
+def test_bond_orders_vs_reference_literals(mols, energies):
+    """get_bond_orders on the CUDA path against the Wiberg literals of test/test_wavefunction/samples.py."""
+    from dxtb_b200 import GFN1Calculator
+
+    dev = _dev()
+    names = ["H2", "LiH", "SiH4"]
+    numbers, pos, chrg = _pack(mols, names, dev)
+    calc = GFN1Calculator(numbers, opts={"exclude": ["disp"], "x_atol": 1e-10, "x_atol_max": 1e-10, "maxiter": 100}, device=dev,
+                          dtype=torch.float64)
+    wbo = calc.get_bond_orders(pos, chrg).cpu().numpy()
+    q = calc.get_atomic_charges().cpu().numpy()
+    for i, n in enumerate(names):
+        ref = energies["wiberg_gfn1"][n]
+        k = len(mols[n]["numbers"])
+        assert np.abs(wbo[i, :k, :k] - np.array(ref["wiberg"]).reshape(k, k)).max() < 1e-8
+        assert np.abs(q[i, :k] - np.array(ref["mulliken_charges"])).max() < 6e-6

@@ -238,3 +238,26 @@ def test_fermi_filling_known_answer_5000K(energies):
     o1, o2 = np.maximum(f, O.EPS), np.maximum(1.0 - f, O.EPS)
     g = kt * float(np.sum(np.log(o1**o1 * o2**o2)))
     assert abs(g - ref["fenergy"]) < 1e-8
+
+
+def _wiberg(mol, P, S):
+    ps = P @ S
+    t = ps * ps.T
+    w = np.zeros((mol.nat, mol.nat))
+    np.add.at(w, (mol.ao_atom[:, None], mol.ao_atom[None, :]), t)
+    np.fill_diagonal(w, 0.0)
+    return w
+
+
+@pytest.mark.parametrize("name", ["H2", "LiH", "SiH4"])
+def test_converged_density_vs_reference_wiberg_and_mulliken(mols, energies, name):
+    """Wiberg bond orders (wavefunction/wiberg.py:33-60) and Mulliken atomic charges of the converged SCF density against
+    the literals of test/test_wavefunction/samples.py: pins P (and through it the whole SCF) at the 1e-8 level."""
+    ref = energies["wiberg_gfn1"][name]
+    m = mols[name]
+    r = O.singlepoint(np.array(m["numbers"]), np.array(m["positions"]), 0.0,
+                      opts={"exclude": ("disp",), "x_atol": 1e-10, "x_atol_max": 1e-10, "maxiter": 100})
+    mol = O.make_mol(np.array(m["numbers"]))
+    w = _wiberg(mol, r.P, r.S)
+    assert np.abs(w - np.array(ref["wiberg"]).reshape(mol.nat, mol.nat)).max() < 1e-8
+    assert np.abs(r.q_at - np.array(ref["mulliken_charges"])).max() < 6e-6  # the reference lists 5 digits
