@@ -126,7 +126,8 @@ class _SinglePoint(torch.autograd.Function):
         nel_ab = calc._electrons(chrg, spin)
         ev = None
         if calc.scf_events is not None:  # bench.py: device time of the SCF kernel alone
-            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            # events from the pre-created pool if there is one (event creation inside a timed loop costs driver time)
+            ev = calc.scf_event_pool.pop() if calc.scf_event_pool else (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record(torch.cuda.current_stream(d.device))
         # size buckets run concurrently on side streams (a bucket of a few big molecules occupies only a few SMs for a long
         # time: the small molecules fill the rest of the device meanwhile); the large-system path drives the main stream
@@ -275,6 +276,7 @@ class GFN1Calculator:
         self.ihelp = self.desc  # index maps live in the descriptor
         self.cache: dict[str, Any] = {}
         self.scf_events: list | None = None
+        self.scf_event_pool: list = []
         self._use_smem_override: int | None = None  # tests: force the global-memory variant
         self._prefer_hybrid = os.environ.get("DXTB_B200_PREFER_HYBRID", "0") != "0"
         self._large_min_nao = int(os.environ.get("DXTB_B200_LARGE_MIN_NAO", "1000000"))
