@@ -703,6 +703,7 @@ class Result:
     occ: np.ndarray = None
     cn: np.ndarray = None
     gradient: np.ndarray = None  # dE/dR (analytic, converged-SCF)
+    gradient_parts: dict = None  # "h0_dedr": overlap-derivative + scaling-function part of the electronic gradient
 
 
 def _potential(m: Mol, q_orb, gam, g3):
@@ -836,14 +837,16 @@ def singlepoint(numbers, positions, chrg: float = 0.0, opts: dict | None = None,
         focc = occ.sum(0)
         W = (st["C"] * (focc * st["emo"])[None, :]) @ st["C"].T
         res.W = W
-        g_tot += _electronic_gradient(m, pos, S, dS, st["P"], W, v_fin, cn, dcfdr, st["q_sh"], gam)
+        parts: dict = {}
+        g_tot += _electronic_gradient(m, pos, S, dS, st["P"], W, v_fin, cn, dcfdr, st["q_sh"], gam, parts)
+        res.gradient_parts = parts
         if d3_dedcn is not None:  # CN chain rule of the dispersion energy (same exp-count CN as H0)
             g_tot += (dcfdr * (d3_dedcn[:, None] + d3_dedcn[None, :])[:, :, None]).sum(1)
         res.gradient = g_tot
     return res
 
 
-def _electronic_gradient(m: Mol, pos, S, dS, P, W, v, cn, dcfdr, q_sh, gam):
+def _electronic_gradient(m: Mol, pos, S, dS, P, W, v, cn, dcfdr, q_sh, gam, parts: dict | None = None):
     """calculators/types/analytical.py:63-222 + xtb/gfn1.py:185-408 + secondorder.py:873-926 + ncoord/utils.py:30-52."""
     f = _h0_shell_factors(m, pos, cn)
     a2s = m.ao_sh
@@ -867,6 +870,8 @@ def _electronic_gradient(m: Mol, pos, S, dS, P, W, v, cn, dcfdr, q_sh, gam):
     np.add.at(dpi_at, (m.sh_atom[:, None], m.sh_atom[None, :]), dpi_sh)
     rij = pos[:, None, :] - pos[None, :, :]
     g += (dpi_at[:, :, None] * rij).sum(1)
+    if parts is not None:
+        parts["h0_dedr"] = g.copy()  # = dedr of GFN1Hamiltonian.get_gradient (xtb/gfn1.py:185-408), without the CN chain
     # CN term
     ps_sh = np.zeros((m.nsh, m.nsh))
     np.add.at(ps_sh, (a2s[:, None], a2s[None, :]), P * S)

@@ -9,7 +9,8 @@ Writes
   tests/golden/molecules.json   geometries (bohr) from test/test_singlepoint/mols/*/coord and
                                 examples/molecules/*, plus the caffeine geometry used by bench.py
   tests/golden/reference.npz    float32 goldens of test_overlap/overlap.npz, test_hamiltonian/h0.npz,
-                                test_scf/grad.npz (tblite), test_hamiltonian/grad_no_overlap.npz (*_dcn)
+                                test_scf/grad.npz (tblite), test_hamiltonian/grad_no_overlap.npz (*_dcn),
+                                test_hamiltonian/grad.npz (H0 part of the nuclear gradient)
   tests/golden/energies.json    tblite fp64 literals: SCF energies (test_scf/samples.py), total
                                 energies (test_singlepoint/samples.py), EEQ known answer (test_scf/test_guess.py)
 """
@@ -125,6 +126,7 @@ def main():
     h0 = np.load(REF / "test/test_hamiltonian/h0.npz")
     gs = np.load(REF / "test/test_scf/grad.npz")
     gn = np.load(REF / "test/test_hamiltonian/grad_no_overlap.npz")
+    gh = np.load(REF / "test/test_hamiltonian/grad.npz")
     for k, name in names.items():
         if k in ov.files:
             arrays[f"overlap/{name}"] = ov[k]
@@ -132,6 +134,8 @@ def main():
             arrays[f"h0/{name}"] = h0[k]
         if k in gs.files:
             arrays[f"scf_grad/{name}"] = gs[k]
+        if k in gh.files:
+            arrays[f"h0_grad/{name}"] = gh[k]
         if f"{k}_dcn" in gn.files:
             arrays[f"dcn/{name}"] = gn[f"{k}_dcn"]
             arrays[f"dedcn/{name}"] = gn[f"{k}_dedcn"]

@@ -261,3 +261,14 @@ def test_converged_density_vs_reference_wiberg_and_mulliken(mols, energies, name
     w = _wiberg(mol, r.P, r.S)
     assert np.abs(w - np.array(ref["wiberg"]).reshape(mol.nat, mol.nat)).max() < 1e-8
     assert np.abs(r.q_at - np.array(ref["mulliken_charges"])).max() < 6e-6  # the reference lists 5 digits
+
+
+@pytest.mark.parametrize("name,tol", [("H2", 2e-7), ("LiH", 3e-7), ("H2O", 2e-7), ("CH4", 2e-7), ("SiH4", 2e-7),
+                                      ("MB16_43_01", 2e-6), ("LYS_xao", 6e-6)])
+def test_h0_gradient_part_vs_reference_goldens(mols, goldens, name, tol):
+    """Overlap-derivative + scaling-function part of the electronic gradient (= `dedr` of GFN1Hamiltonian.get_gradient,
+    xtb/gfn1.py:185-408) against test/test_hamiltonian/grad.npz (float32, generated at x_atol = 1e-6)."""
+    m = mols[name]
+    r = O.singlepoint(np.array(m["numbers"]), np.array(m["positions"]), float(m["charge"]),
+                      opts={"exclude": ("disp",), "x_atol": 1e-6, "x_atol_max": 1e-6}, grad=True)
+    assert np.abs(r.gradient_parts["h0_dedr"] - goldens[f"h0_grad/{name}"]).max() < tol
