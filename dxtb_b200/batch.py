@@ -112,9 +112,9 @@ class BatchDescriptor:
         at_par[:, _abi.AT_RCOV] = par.cov_d3[z]
         at_par[:, _abi.AT_EN] = par.en[z]
         at_par[:, _abi.AT_AREP] = par.arep[z]
-        at_par[:, _abi.AT_ZEFF] = par.zeff[z]
+        at_par[:, _abi.AT_ZEFF] = 0.0 if "rep" in exclude else par.zeff[z]  # excluded repulsion: zero energy and gradient
         at_par[:, _abi.AT_GAM3] = 0.0 if "es3" in exclude else par.gam3[z]
-        at_par[:, _abi.AT_XBOND] = par.xbond[z]
+        at_par[:, _abi.AT_XBOND] = 0.0 if "hal" in exclude else par.xbond[z]
         at_par[:, _abi.AT_EEQ_CHI] = par.eeq_chi[z]
         at_par[:, _abi.AT_EEQ_ETA] = par.eeq_eta[z]
         at_par[:, _abi.AT_EEQ_KCN] = par.eeq_kcn[z]
@@ -164,6 +164,7 @@ class BatchDescriptor:
         s.nb, s.nat_tot, s.nsh_tot, s.nao_tot = self.nb, self.nat_tot, nsh_tot, nao_tot
         s.nat_max, s.nsh_max, s.nao_max = int(nat.max()), int(nsh.max()), int(nao.max())
         s.nspecies, s.ncgto = int(species.size), int(ukey.size)
+        s.has_xb = int(bool((at_par[:, _abi.AT_XBOND] != 0.0).any()))
         s.mat_total, s.gam_total, s.eeq_total = int(self.mat_off[-1]), int(self.gam_off[-1]), int(self.eeq_off[-1])
         for name, t in self._t.items():
             setattr(s, name, t.data_ptr())

@@ -174,7 +174,6 @@ class _SinglePoint(torch.autograd.Function):
         calc._store(ws, e_pad, nel_ab)
         if need_grad:
             ctx.calc = calc
-            ctx.excl_rep = "rep" in excl
             ctx.d3w = ws.d3w
             ctx.save_for_backward(pos, ws.cn, ws.S, ws.P, ws.W, ws.v_orb, ws.q_sh, ws.gamma)
         return energy
@@ -190,8 +189,6 @@ class _SinglePoint(torch.autograd.Function):
         grad = torch.empty((d.nat_tot, 3), dtype=torch.float64, device=d.device)
         dedcn = torch.empty(d.nat_tot, dtype=torch.float64, device=d.device)
         pairbuf = torch.empty(4 * int(d.struct.gam_total), dtype=torch.float64, device=d.device)
-        if ctx.excl_rep:
-            raise NotImplementedError("analytic gradient with exclude=['rep'] is not implemented")
         _abi.check(
             _abi.lib().xtb_grad_bwd(d.ptr, pos.data_ptr(), cn.data_ptr(), S.data_ptr(), P.data_ptr(), W.data_ptr(), v_orb.data_ptr(),
                                     q_sh.data_ptr(), gamma.data_ptr(), ge.data_ptr(),
@@ -241,6 +238,13 @@ class GFN1Calculator:
         if str(o["guess"]).lower() not in ("eeq", "sad"):
             raise ValueError(f"unknown guess '{o['guess']}'")
         o["guess"] = str(o["guess"]).lower()
+        # labels/integrals.py:45-66: 1 = autograd, 2 = analytical, 3 = legacy loops are the pure-PyTorch drivers this path replaces
+        if str(o["int_driver"]).lower() not in ("autograd", "pytorch", "torch", "dxtb", "1", "analytical", "pytorch2", "torch2",
+                                                "dxtb2", "2", "legacy", "old", "loop", "3"):
+            raise NotImplementedError("only the analytical (pure PyTorch) integral driver of the reference is replaced; "
+                                      f"int_driver={o['int_driver']!r} (libcint) is outside the B200 hot path")
+        if str(o["fermi_partition"]).lower() not in ("equal", "0"):
+            raise NotImplementedError("only fermi_partition='equal' (the reference default) is implemented")
         mixer = str(o["mixer"]).lower()
         if mixer in ("broyden", "anderson"):
             self._mixer = 0
@@ -316,6 +320,23 @@ class GFN1Calculator:
             two = (need[:, 2] <= _SMEM_2CTA) & (mode == 1)
             if 2 * int(two.sum()) >= 3 * _sm_count(self.device):
                 mode[two] = 2
+        # The launch sizes shared memory from the bucket-wide maxima of nao, nsh and nat (not from one molecule's own
+        # triple): a bucket mixing an orbital-rich with a shell- or atom-rich molecule can exceed what each member needs
+        # alone.  Demote the largest-nao members to the next variant until the bucket bound fits.
+        for use_smem, nxt in ((1, 2), (2, 0)):
+            while True:
+                idx = np.flatnonzero(mode == use_smem)
+                if idx.size == 0:
+                    break
+                bound = int(lib.xtb_scf_smem_bytes_mode(use_smem, int(d.nao[idx].max()), int(d.nsh[idx].max()), int(d.nat[idx].max())))
+                if bound <= _SMEM_LIMIT:
+                    break
+                mode[idx[d.nao[idx] == d.nao[idx].max()]] = nxt
+        idx0 = np.flatnonzero(mode == 0)
+        if idx0.size and int(lib.xtb_scf_smem_bytes_mode(0, int(d.nao[idx0].max()), int(d.nsh[idx0].max()), int(d.nat[idx0].max()))) > _SMEM_LIMIT:
+            # per-orbital vectors of the bucket bound no longer fit: the shell/atom-richest members run alone on the device
+            key = np.maximum(d.nsh[idx0], d.nat[idx0])
+            mode[idx0[key == key.max()]] = 3
         buckets = []
         for use_smem in (3, 0, 2, 1):
             idx = np.flatnonzero(mode == use_smem)
@@ -388,9 +409,15 @@ class GFN1Calculator:
         par = torch.remainder(nel.round(), 2)
         if spin is None:
             nuhf = par
-        else:
+        else:  # same checks and messages as get_alpha_beta_occupation (wavefunction/filling.py:78-96)
             uhf = spin.to(nel)
-            nuhf = torch.where(torch.remainder(uhf, 2) == par, uhf, par)
+            if uhf.shape != nel.shape:
+                raise RuntimeError(f"Shape mismatch for unpaired electrons ({uhf.shape}) and number of electrons ({nel.shape}).")
+            if (uhf > nel.round()).any():
+                raise ValueError(f"Number of unpaired electrons ({uhf}) larger than number of electrons ({nel}).")
+            if (torch.remainder(uhf, 2) != par).any():
+                raise ValueError(f"Odd (even) number of unpaired electrons ({uhf}) but even (odd) number of electrons ({nel}) given.")
+            nuhf = uhf
         diff = torch.minimum(nuhf, nel)
         nb_ = (nel - diff) / 2.0
         return torch.stack([nb_ + diff, nb_], dim=-1).round().contiguous()  # scf/base.py:878
@@ -415,6 +442,8 @@ class GFN1Calculator:
             spin_t = torch.as_tensor(spin, dtype=torch.float64, device=self.device).reshape(-1)
             if spin_t.numel() == 1:
                 spin_t = spin_t.expand(nb)
+            if spin_t.numel() != nb:
+                raise RuntimeError(f"Shape mismatch for unpaired electrons ({tuple(spin_t.shape)}) and number of electrons (({nb},)).")
         return chrg_t.contiguous(), spin_t
 
     def _store(self, ws: _Workspace, e_pad: torch.Tensor, nel_ab: torch.Tensor) -> None:

@@ -12,6 +12,7 @@ namespace xtb {
 
 constexpr double kEps = 2.220446049250313e-16;    // torch.finfo(float64).eps
 constexpr double kTiny = 2.2250738585072014e-308;  // torch.finfo(float64).tiny
+constexpr int kMaxGridY = 65535;  // CUDA limit of gridDim.y: launches with the molecule index in y are chunked
 constexpr double kPi = 3.14159265358979323846;
 constexpr double kSqrtPi3 = 5.568327996831707845;  // sqrt(pi)^3
 

@@ -69,8 +69,8 @@ __global__ void k_geometry(const xtb_batch b, const double* __restrict__ pos, do
 // ---------------------------------------------------------------------------------------------
 // shell-resolved Coulomb matrix, harmonic average, gexp = 2 (coulomb/secondorder.py:799-870)
 // ---------------------------------------------------------------------------------------------
-__global__ void k_gamma(const xtb_batch b, const double* __restrict__ pos, double* __restrict__ gamma) {
-  const int m = blockIdx.y;
+__global__ void k_gamma(const xtb_batch b, const double* __restrict__ pos, double* __restrict__ gamma, int mol0) {
+  const int m = mol0 + blockIdx.y;
   const int s0 = b.sh_off[m], ns = b.sh_off[m + 1] - s0;
   const int a0 = b.at_off[m];
   double* g = gamma + b.gam_off[m];
@@ -311,6 +311,73 @@ __global__ void k_eeq_backsub(const double* __restrict__ A, double* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
+// Halogen-bond gradient (derivative of hal.py:318-362; the reference differentiates the energy by autograd,
+// classicals/base.py:118-156, with the triple list (X, J, K) as integer data).  E = xb * lj(a) * (1/2 - cos/4)^6 with
+// a = |R_J - R_X|^2, b = |R_K - R_X|^2, c = |R_K - R_J|^2, cos = (b + a - c) / sqrt(a b).
+// ---------------------------------------------------------------------------------------------
+XTB_DEV bool xb_is_halogen(int z) { return z == 17 || z == 35 || z == 53 || z == 85; }
+XTB_DEV bool xb_is_base(int z) { return z == 7 || z == 8 || z == 15 || z == 16; }
+
+// nearest neighbour of atom x (hal.py:253-266: first atom with the smallest non-zero distance)
+XTB_DEV int xb_nearest(const double* __restrict__ p, int na, int x) {
+  int kb = 0;
+  double dbest = 1.79769313486231570e308;
+  for (int k = 0; k < na; ++k) {
+    const double dx = p[3 * x] - p[3 * k], dy = p[3 * x + 1] - p[3 * k + 1], dz = p[3 * x + 2] - p[3 * k + 2];
+    const double r1 = sqrt(dx * dx + dy * dy + dz * dz);
+    if (r1 > 0.0 && r1 < dbest) { kb = k; dbest = r1; }
+  }
+  return kb;
+}
+
+// dE/d(a, b, c) of one triple
+XTB_DEV void xb_triple_derivs(double a, double bq, double c, double r0, double damp, double xb, double& de_da, double& de_db,
+                              double& de_dc) {
+  const double xy = sqrt(bq * a);
+  const double q = r0 * r0 / a, lj6 = q * q * q, lj12 = lj6 * lj6;
+  const double den = 1.0 / (1.0 + lj12);
+  const double lj = (lj12 - damp * lj6) * den;
+  const double dlj_dlj6 = ((2.0 * lj6 - damp) * (1.0 + lj12) - (lj12 - damp * lj6) * 2.0 * lj6) * den * den;
+  const double dlj_da = dlj_dlj6 * (-3.0 * lj6 / a);
+  const double cosa = (bq + a - c) / xy;
+  const double t = 0.5 - 0.25 * cosa, t2 = t * t, t5 = t2 * t2 * t;
+  const double fd = t5 * t, dfd = -1.5 * t5;
+  de_da = xb * (dlj_da * fd + lj * dfd * (1.0 / xy - 0.5 * cosa / a));
+  de_db = xb * lj * dfd * (1.0 / xy - 0.5 * cosa / bq);
+  de_dc = xb * lj * dfd * (-1.0 / xy);
+}
+
+// Contribution of every triple (X, J, K) that contains atom `at` to dE/dR_at; fixed loop order, single writer.
+XTB_DEV void xb_grad_atom(const xtb_batch& b, const double* __restrict__ p, int a0, int na, int at, double& gx, double& gy,
+                          double& gz) {
+  const bool at_base = xb_is_base(b.at_z[a0 + at]);
+  for (int x = 0; x < na; ++x) {
+    const double xb = b.at_par[(size_t)(a0 + x) * XTB_ATPAR + XTB_AT_XBOND];
+    if (xb == 0.0 || !xb_is_halogen(b.at_z[a0 + x])) continue;
+    const int kb = xb_nearest(p, na, x);
+    if (!(at == x || at == kb || at_base)) continue;
+    const double radx = b.at_par[(size_t)(a0 + x) * XTB_ATPAR + XTB_AT_RAD];
+    const double kx = p[3 * kb] - p[3 * x], ky = p[3 * kb + 1] - p[3 * x + 1], kz = p[3 * kb + 2] - p[3 * x + 2];
+    const double d2xk = kx * kx + ky * ky + kz * kz;
+    const int j0 = (at == x || at == kb) ? 0 : at, j1 = (at == x || at == kb) ? na : at + 1;
+    for (int j = j0; j < j1; ++j) {
+      if (!xb_is_base(b.at_z[a0 + j])) continue;
+      const double jx = p[3 * j] - p[3 * x], jy = p[3 * j + 1] - p[3 * x + 1], jz = p[3 * j + 2] - p[3 * x + 2];
+      const double d2xj = jx * jx + jy * jy + jz * jz;
+      if (sqrt(d2xj) > b.xb_cutoff) continue;
+      const double cx = p[3 * kb] - p[3 * j], cy = p[3 * kb + 1] - p[3 * j + 1], cz = p[3 * kb + 2] - p[3 * j + 2];
+      const double d2kj = cx * cx + cy * cy + cz * cz;
+      const double r0 = (radx + b.at_par[(size_t)(a0 + j) * XTB_ATPAR + XTB_AT_RAD]) * b.xb_rscale;
+      double da, db, dc;
+      xb_triple_derivs(d2xj, d2xk, d2kj, r0, b.xb_damp, xb, da, db, dc);
+      if (at == j) { gx += 2.0 * (da * jx - dc * cx); gy += 2.0 * (da * jy - dc * cy); gz += 2.0 * (da * jz - dc * cz); }
+      if (at == kb) { gx += 2.0 * (db * kx + dc * cx); gy += 2.0 * (db * ky + dc * cy); gz += 2.0 * (db * kz + dc * cz); }
+      if (at == x) { gx -= 2.0 * (da * jx + db * kx); gy -= 2.0 * (da * jy + db * ky); gz -= 2.0 * (da * jz + db * kz); }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Atom-pair part of the analytic gradient: repulsion (repulsion/base.py:337-406), second-order
 // electrostatics with fixed charges (secondorder.py:873-926) and the CN chain rule
 // (ncoord/utils.py:30-52 with the exp-count derivative).  One CTA per molecule.
@@ -395,6 +462,7 @@ __global__ void k_grad_atoms(const xtb_batch b, const double* __restrict__ pos, 
       f += es;
       gx += f * dx; gy += f * dy; gz += f * dz;
     }
+    if (b.has_xb) xb_grad_atom(b, p, a0, na, a, gx, gy, gz);
     // single writer per address: deterministic (grad may already hold the direct dispersion part)
     grad[3 * (size_t)(a0 + a)] += scale * gx;
     grad[3 * (size_t)(a0 + a) + 1] += scale * gy;
@@ -549,7 +617,8 @@ extern "C" int xtb_gamma_fwd(const xtb_batch* b, const double* pos, double* gamm
   const int nt = 256;
   int gx = (b->nsh_max * b->nsh_max + nt - 1) / nt;
   if (gx > 64) gx = 64;
-  k_gamma<<<dim3(gx, b->nb), nt, 0, (cudaStream_t)stream>>>(*b, pos, gamma);
+  for (int m0 = 0; m0 < b->nb; m0 += kMaxGridY)
+    k_gamma<<<dim3(gx, b->nb - m0 < kMaxGridY ? b->nb - m0 : kMaxGridY), nt, 0, (cudaStream_t)stream>>>(*b, pos, gamma, m0);
   return launch_status();
 }
 

@@ -239,8 +239,8 @@ XTB_DEV H0Factors h0_factors(const xtb_batch& b, int m, const PairInfo& pi, cons
 
 template <int LI, int LJ>
 __global__ void __launch_bounds__(128) k_overlap_h0(const xtb_batch b, const double* __restrict__ pos, const double* __restrict__ cn,
-                                                    double* __restrict__ S, double* __restrict__ H0) {
-  const int m = blockIdx.y;
+                                                    double* __restrict__ S, double* __restrict__ H0, int mol0) {
+  const int m = mol0 + blockIdx.y;
   const PairInfo pi = pair_setup<LI, LJ>(b, m, pos);
   if (!pi.valid) return;
   const int s0 = b.sh_off[m];
@@ -268,8 +268,8 @@ __global__ void __launch_bounds__(128) k_overlap_h0(const xtb_batch b, const dou
 }
 
 // diagonal: S = 1 (impls/overlap.py:241-242), H0 = self energy (xtb/base.py:287-292)
-__global__ void k_diag(const xtb_batch b, const double* __restrict__ cn, double* __restrict__ S, double* __restrict__ H0) {
-  const int m = blockIdx.y;
+__global__ void k_diag(const xtb_batch b, const double* __restrict__ cn, double* __restrict__ S, double* __restrict__ H0, int mol0) {
+  const int m = mol0 + blockIdx.y;
   const int o0 = b.ao_off[m], n = b.ao_off[m + 1] - o0;
   const int s0 = b.sh_off[m], a0 = b.at_off[m];
   for (int mu = blockIdx.x * blockDim.x + threadIdx.x; mu < n; mu += gridDim.x * blockDim.x) {
@@ -285,8 +285,8 @@ __global__ void k_diag(const xtb_batch b, const double* __restrict__ cn, double*
 template <int LI, int LJ>
 __global__ void __launch_bounds__(128) k_grad_pair(const xtb_batch b, const double* __restrict__ pos, const double* __restrict__ cn,
                                                    const double* __restrict__ P, const double* __restrict__ W,
-                                                   const double* __restrict__ v_orb, double* __restrict__ pairbuf) {
-  const int m = blockIdx.y;
+                                                   const double* __restrict__ v_orb, double* __restrict__ pairbuf, int mol0) {
+  const int m = mol0 + blockIdx.y;
   const PairInfo pi = pair_setup<LI, LJ>(b, m, pos);
   if (!pi.valid) return;
   const int s0 = b.sh_off[m], a0 = b.at_off[m], o0 = b.ao_off[m];
@@ -336,8 +336,10 @@ __global__ void __launch_bounds__(128) k_grad_pair(const xtb_batch b, const doub
 template <int LI, int LJ> int launch_overlap(const xtb_batch* b, const double* pos, const double* cn, double* S, double* H0, cudaStream_t st) {
   const int nt = 128;
   const int npair = b->nsh_max * b->nsh_max;  // upper bound on n_I * n_J
-  dim3 grid((npair + nt - 1) / nt, b->nb);
-  k_overlap_h0<LI, LJ><<<grid, nt, 0, st>>>(*b, pos, cn, S, H0);
+  for (int m0 = 0; m0 < b->nb; m0 += kMaxGridY) {  // gridDim.y is capped at 65535
+    dim3 grid((npair + nt - 1) / nt, b->nb - m0 < kMaxGridY ? b->nb - m0 : kMaxGridY);
+    k_overlap_h0<LI, LJ><<<grid, nt, 0, st>>>(*b, pos, cn, S, H0, m0);
+  }
   return launch_status();
 }
 template <int LI, int LJ>
@@ -345,8 +347,10 @@ int launch_grad_pair(const xtb_batch* b, const double* pos, const double* cn, co
                      double* pairbuf, cudaStream_t st) {
   const int nt = 128;
   const int npair = b->nsh_max * b->nsh_max;
-  dim3 grid((npair + nt - 1) / nt, b->nb);
-  k_grad_pair<LI, LJ><<<grid, nt, 0, st>>>(*b, pos, cn, P, W, v, pairbuf);
+  for (int m0 = 0; m0 < b->nb; m0 += kMaxGridY) {
+    dim3 grid((npair + nt - 1) / nt, b->nb - m0 < kMaxGridY ? b->nb - m0 : kMaxGridY);
+    k_grad_pair<LI, LJ><<<grid, nt, 0, st>>>(*b, pos, cn, P, W, v, pairbuf, m0);
+  }
   return launch_status();
 }
 
@@ -372,7 +376,8 @@ extern "C" int xtb_overlap_h0_fwd(const xtb_batch* b, const double* pos, const d
   if ((rc = launch_overlap<2, 1>(b, pos, cn, S, H0, st))) return rc;
   if ((rc = launch_overlap<2, 2>(b, pos, cn, S, H0, st))) return rc;
   int gx = (b->nao_max + 127) / 128;
-  k_diag<<<dim3(gx, b->nb), 128, 0, st>>>(*b, cn, S, H0);
+  for (int m0 = 0; m0 < b->nb; m0 += kMaxGridY)
+    k_diag<<<dim3(gx, b->nb - m0 < kMaxGridY ? b->nb - m0 : kMaxGridY), 128, 0, st>>>(*b, cn, S, H0, m0);
   return launch_status();
 }
 

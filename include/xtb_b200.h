@@ -44,7 +44,7 @@ typedef struct xtb_batch {
   int32_t nat_max, nsh_max, nao_max;  /* maxima over the shard */
   int32_t nspecies;                   /* unique elements in the shard */
   int32_t ncgto;                      /* rows of the cgto table */
-  int32_t pad0;
+  int32_t has_xb;                     /* 1: some atom has a non-zero halogen-bond strength (Br, I, At with "hal" not excluded) */
   int64_t mat_total, gam_total, eeq_total; /* host copies of mat_off[nb], gam_off[nb], eeq_off[nb] */
   const int32_t* at_off;  /* [nb+1] */
   const int32_t* sh_off;  /* [nb+1] */

@@ -428,15 +428,20 @@ def repulsion(m: Mol, pos: np.ndarray, grad: bool = False):
     return eat, (g[:, :, None] * rij).sum(1)
 
 
-def halogen(m: Mol, pos: np.ndarray):
-    """components/classicals/halogen/hal.py:209-364 (energy only)."""
+def halogen(m: Mol, pos: np.ndarray, grad: bool = False):
+    """components/classicals/halogen/hal.py:209-364.  With ``grad`` also dE/dR of the triples (X, J, K): the
+    reference differentiates the energy by autograd (classicals/base.py:118-156) with the neighbour list fixed
+    (the index K of the halogen's nearest neighbour is integer data, hal.py:253-266), so the derivative acts on the
+    three squared distances d2xj, d2xk, d2kj only."""
     par = params()
     halogens, bases = (17, 35, 53, 85), (7, 8, 15, 16)
     e = np.zeros(m.nat)
+    g = np.zeros((m.nat, 3)) if grad else None
     rads = par.atomic_rad[m.numbers] * par.xb_rscale
     for x, zx in enumerate(m.numbers):
         if zx not in halogens:
             continue
+        xb = par.elem[int(zx)]["xbond"]
         for j, zj in enumerate(m.numbers):
             if zj not in bases:
                 continue
@@ -450,12 +455,26 @@ def halogen(m: Mol, pos: np.ndarray):
             r0 = rads[x] + rads[j]
             dxj, dxk, dkj = pos[j] - pos[x], pos[kbest] - pos[x], pos[kbest] - pos[j]
             d2xj, d2xk, d2kj = dxj @ dxj, dxk @ dxk, dkj @ dkj
+            xy = math.sqrt(d2xk * d2xj)
             lj6 = (r0 / math.sqrt(d2xj)) ** 6
             lj12 = lj6**2
             lj = (lj12 - par.xb_damp * lj6) / (1.0 + lj12)
-            cosa = (d2xk + d2xj - d2kj) / math.sqrt(d2xk * d2xj)
-            e[x] += lj * (0.5 - 0.25 * cosa) ** 6 * par.elem[int(zx)]["xbond"]
-    return e
+            cosa = (d2xk + d2xj - d2kj) / xy
+            t = 0.5 - 0.25 * cosa
+            fd = t**6
+            e[x] += lj * fd * xb
+            if grad:
+                # chain rule over a = d2xj, b = d2xk, c = d2kj
+                dlj_dlj6 = ((2.0 * lj6 - par.xb_damp) * (1.0 + lj12) - (lj12 - par.xb_damp * lj6) * 2.0 * lj6) / (1.0 + lj12) ** 2
+                dlj_da = dlj_dlj6 * (-3.0 * lj6 / d2xj)
+                dfd = -1.5 * t**5  # d fd / d cosa
+                de_da = xb * (dlj_da * fd + lj * dfd * (1.0 / xy - 0.5 * cosa / d2xj))
+                de_db = xb * lj * dfd * (1.0 / xy - 0.5 * cosa / d2xk)
+                de_dc = xb * lj * dfd * (-1.0 / xy)
+                g[j] += 2.0 * de_da * dxj - 2.0 * de_dc * dkj
+                g[kbest] += 2.0 * de_db * dxk + 2.0 * de_dc * dkj
+                g[x] += -2.0 * de_da * dxj - 2.0 * de_db * dxk
+    return (e, g) if grad else e
 
 
 # --------------------------------------------------------------------------------------
@@ -736,7 +755,10 @@ def singlepoint(numbers, positions, chrg: float = 0.0, opts: dict | None = None,
         if grad:
             g_tot += gr
     if "hal" not in excl:
-        ex = halogen(m, pos)
+        ex = halogen(m, pos, grad=grad)
+        if grad:
+            ex, gx = ex
+            g_tot += gx
         e_at += ex
         res.e_xb = ex.sum()
     if "disp" not in excl and d3_energy is not None:
@@ -879,7 +901,11 @@ def _electronic_gradient(m: Mol, pos, S, dS, P, W, v, cn, dcfdr, q_sh, gam, part
     dedcn_sh = (ps_sh * dhdcn).sum(0)
     dedcn = np.bincount(m.sh_atom, weights=dedcn_sh, minlength=m.nat)
     # dE/dR_A = sum_B (dedcn_A + dedcn_B) dcf_AB/dR_A
-    g += (dcfdr * (dedcn[:, None] + dedcn[None, :])[:, :, None]).sum(1)
+    g_cn = (dcfdr * (dedcn[:, None] + dedcn[None, :])[:, :, None]).sum(1)
+    g += g_cn
+    if parts is not None:
+        parts["h0_dedcn"] = dedcn.copy()  # = dedcn of GFN1Hamiltonian.get_gradient
+        parts["h0_dcn"] = g_cn.copy()  # = ncoord get_dcn(dcndr, dedcn)
     # ES2: E = 1/2 q g q, d gamma/dR_A = -gamma^3 (R_A-R_B) for off-atom shell pairs (gexp = 2)
     offsh = f["offatom"]
     dg = np.where(offsh, -(gam**3), 0.0) * q_sh[:, None] * q_sh[None, :]

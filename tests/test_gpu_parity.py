@@ -531,3 +531,83 @@ def test_bond_orders_vs_reference_literals(mols, energies):
         k = len(mols[n]["numbers"])
         assert np.abs(wbo[i, :k, :k] - np.array(ref["wiberg"]).reshape(k, k)).max() < 1e-8
         assert np.abs(q[i, :k] - np.array(ref["mulliken_charges"])).max() < 6e-6
+
+
+# ---------------------------------------------------------------------------------------------------------
+# halogen-bond correction where it is non-zero (Br / I next to N, O, P, S)
+# ---------------------------------------------------------------------------------------------------------
+HALOGEN = ["CH3Br_NH3", "CH3I_OCH2", "Br2_NH3", "CH2BrI_cluster"]
+
+
+def _halogen_batch(dev, extra=None):
+    from halogen_mols import halogen_mol
+
+    geoms = [halogen_mol(n) for n in HALOGEN] + (extra or [])
+    nat = max(len(z) for z, _ in geoms)
+    numbers = torch.zeros((len(geoms), nat), dtype=torch.long)
+    pos = torch.zeros((len(geoms), nat, 3), dtype=torch.float64)
+    for i, (z, p) in enumerate(geoms):
+        numbers[i, : len(z)] = torch.from_numpy(z)
+        pos[i, : len(z)] = torch.from_numpy(p)
+    return geoms, numbers.to(dev), pos.to(dev)
+
+
+def test_halogen_bond_energy_and_forces_match_oracle(mols):
+    """E_xb != 0 on every molecule of the batch; energy, halogen energy, forces and iteration counts vs the oracle."""
+    from dxtb_b200 import GFN1Calculator
+
+    dev = _dev()
+    caff = (np.array(mols["caffeine"]["numbers"]), np.array(mols["caffeine"]["positions"]))
+    geoms, numbers, pos = _halogen_batch(dev, extra=[caff])
+    calc = GFN1Calculator(numbers, opts=NODISP, device=dev, dtype=torch.float64)
+    p = pos.clone().requires_grad_(True)
+    e = calc.get_energy(p)
+    (g,) = torch.autograd.grad(e.sum(), p)
+    d, ws = calc.desc, calc.cache["ws"]
+    for i, (z, xyz) in enumerate(geoms):
+        r = O.singlepoint(z, xyz, opts={"exclude": ("disp",)}, grad=True)
+        exb = float(ws.e_xb[int(d.at_off[i]) : int(d.at_off[i + 1])].sum())
+        if i < len(HALOGEN):
+            assert abs(r.e_xb) > 1e-4 and abs(exb) > 1e-4
+        assert abs(exb - r.e_xb) < 1e-12
+        assert abs(float(e[i]) - r.energy) < E_TOL
+        assert int(calc.get_iterations()[i]) == r.iterations
+        assert np.abs(g[i, : len(z)].cpu().numpy() - r.gradient).max() < F_TOL
+
+
+def test_halogen_bond_forces_vs_finite_difference_of_cuda_energy():
+    """Forces of the CUDA path against a central finite difference of ITS OWN total energy (tight SCF), on the atoms
+    of the halogen-bond triple (X, J and X's nearest neighbour K)."""
+    from dxtb_b200 import GFN1Calculator
+
+    dev = _dev()
+    geoms, numbers, pos = _halogen_batch(dev)
+    opts = {"exclude": ["disp"], "x_atol": 1e-11, "x_atol_max": 1e-11}
+    calc = GFN1Calculator(numbers, opts=opts, device=dev, dtype=torch.float64)
+    f = calc.get_forces(pos.clone().requires_grad_(True))
+    h = 1e-4
+    probes = {0: [(4, 2), (5, 0), (0, 1)], 1: [(4, 2), (5, 1), (0, 0)], 2: [(0, 2), (1, 0), (2, 1)], 3: [(3, 0), (4, 2), (5, 1), (8, 0), (12, 2)]}
+    for i, lst in probes.items():
+        for a, c in lst:
+            pp, pm = pos.clone(), pos.clone()
+            pp[i, a, c] += h
+            pm[i, a, c] -= h
+            fd = (float(calc.get_energy(pp)[i]) - float(calc.get_energy(pm)[i])) / (2 * h)
+            assert abs(-float(f[i, a, c]) - fd) < 5e-8, (i, a, c)
+
+
+def test_gradient_with_excluded_repulsion_and_halogen():
+    """exclude=['rep'] / ['hal'] drop the term from energy AND forces (reference: the component is not built at all)."""
+    from dxtb_b200 import GFN1Calculator
+
+    dev = _dev()
+    geoms, numbers, pos = _halogen_batch(dev)
+    for excl in (["disp", "rep"], ["disp", "hal"], ["disp", "rep", "hal"]):
+        calc = GFN1Calculator(numbers, opts={"exclude": excl}, device=dev, dtype=torch.float64)
+        p = pos.clone().requires_grad_(True)
+        e = calc.get_energy(p)
+        (g,) = torch.autograd.grad(e.sum(), p)
+        for i, (z, xyz) in enumerate(geoms):
+            r = O.singlepoint(z, xyz, opts={"exclude": tuple(excl)}, grad=True)
+            assert abs(float(e[i]) - r.energy) < E_TOL
+            assert np.abs(g[i, : len(z)].cpu().numpy() - r.gradient).max() < F_TOL

@@ -84,14 +84,19 @@ def test_eeq_guess_known_answer(mols, energies):
     assert abs(q.sum()) < 1e-12
 
 
-def test_cn_derivative_golden(mols, goldens):
-    for name in ["H2O", "CH4", "SiH4", "LYS_xao"]:
-        nums, pos, _ = _geom(mols, name)
-        m = O.make_mol(nums)
-        cn, dcf = O.cn_d3(m, pos, grad=True)
-        assert cn.shape == (len(nums),) and np.isfinite(dcf).all()
-        # antisymmetry of the pair derivative (translational invariance)
-        assert np.abs(dcf + dcf.transpose(1, 0, 2)).max() < 1e-14
+@pytest.mark.parametrize("name,tol", [("H2", 2e-7), ("LiH", 3e-7), ("H2O", 2e-7), ("CH4", 2e-7), ("SiH4", 2e-7),
+                                      ("MB16_43_01", 2e-6), ("LYS_xao", 6e-6)])
+def test_cn_derivative_golden(mols, goldens, name, tol):
+    """dE/dCN of the converged density (`dedcn` of GFN1Hamiltonian.get_gradient, xtb/gfn1.py:185-408) and its CN chain
+    rule term (`get_dcn(cn_d3_gradient, dedcn)`, ncoord/utils.py:30-52) against test/test_hamiltonian/grad_no_overlap.npz
+    (`*_dedcn`, `*_dcn`; float32, generated at x_atol = 1e-6): pins the exp-count derivative and its sign conventions."""
+    nums, pos, chrg = _geom(mols, name)
+    m = O.make_mol(nums)
+    cn, dcf = O.cn_d3(m, pos, grad=True)
+    assert np.abs(dcf + dcf.transpose(1, 0, 2)).max() < 1e-14  # antisymmetry of the pair derivative
+    r = O.singlepoint(nums, pos, float(chrg), opts={"exclude": ("disp",), "x_atol": 1e-6, "x_atol_max": 1e-6}, grad=True)
+    assert np.abs(r.gradient_parts["h0_dedcn"] - goldens[f"dedcn/{name}"]).max() < tol
+    assert np.abs(r.gradient_parts["h0_dcn"] - goldens[f"dcn/{name}"]).max() < tol
 
 
 def test_anderson_matches_simple_for_soft_start():
@@ -272,3 +277,41 @@ def test_h0_gradient_part_vs_reference_goldens(mols, goldens, name, tol):
     r = O.singlepoint(np.array(m["numbers"]), np.array(m["positions"]), float(m["charge"]),
                       opts={"exclude": ("disp",), "x_atol": 1e-6, "x_atol_max": 1e-6}, grad=True)
     assert np.abs(r.gradient_parts["h0_dedr"] - goldens[f"h0_grad/{name}"]).max() < tol
+
+
+@pytest.mark.parametrize("name", ["CH3Br_NH3", "CH3I_OCH2", "Br2_NH3", "CH2BrI_cluster"])
+def test_halogen_gradient_is_derivative_of_energy(name):
+    """Halogen-bond term (hal.py:209-364) on molecules where it is non-zero: analytic dE/dR == central finite
+    difference of the oracle energy (the reference obtains this derivative by autograd, classicals/base.py:118-156)."""
+    from halogen_mols import halogen_mol
+
+    nums, pos = halogen_mol(name)
+    m = O.make_mol(nums)
+    e, g = O.halogen(m, pos, grad=True)
+    assert abs(e.sum()) > 1e-4
+    h = 1e-5
+    fd = np.zeros_like(pos)
+    for a in range(m.nat):
+        for c in range(3):
+            pp, pm = pos.copy(), pos.copy()
+            pp[a, c] += h
+            pm[a, c] -= h
+            fd[a, c] = (O.halogen(m, pp).sum() - O.halogen(m, pm).sum()) / (2 * h)
+    assert np.abs(fd - g).max() < 1e-9
+    assert np.abs(g.sum(0)).max() < 1e-14  # translational invariance
+
+
+def test_total_gradient_with_halogen_bond_vs_finite_difference():
+    """Total oracle gradient (incl. the halogen term) == finite difference of the total energy at tight SCF."""
+    from halogen_mols import halogen_mol
+
+    nums, pos = halogen_mol("CH3Br_NH3")
+    o = {"exclude": ("disp",), "x_atol": 1e-11, "x_atol_max": 1e-11}
+    r = O.singlepoint(nums, pos, opts=o, grad=True)
+    h = 1e-4
+    for a, c in [(4, 2), (5, 0), (0, 2), (4, 1)]:
+        pp, pm = pos.copy(), pos.copy()
+        pp[a, c] += h
+        pm[a, c] -= h
+        fd = (O.singlepoint(nums, pp, opts=o).energy - O.singlepoint(nums, pm, opts=o).energy) / (2 * h)
+        assert abs(fd - r.gradient[a, c]) < 2e-8
