@@ -68,7 +68,9 @@ template <> XTB_DEV void to_sph_left<1>(const double* in, int ncol, double* out)
   for (int c = 0; c < 3 * ncol; ++c) out[c] = in[c];
 }
 template <> XTB_DEV void to_sph_left<2>(const double* in, int ncol, double* out) {
-  const double s3 = 1.7320508075688772935, s34 = 0.86602540378443864676;
+  // md/trafo.py:37-38, 65-75: the reference builds TRAFO with torch.tensor(...) at the default dtype, so sqrt(3) and
+  // sqrt(3)/2 are float32-rounded values cast to fp64 (replicated for parity; see also param.py slater_to_gauss)
+  const double s3 = 1.7320507764816284, s34 = 0.8660253882408142;
   for (int c = 0; c < ncol; ++c) {
     const double xx = in[0 * ncol + c], yy = in[1 * ncol + c], zz = in[2 * ncol + c];
     const double xy = in[3 * ncol + c], xz = in[4 * ncol + c], yz = in[5 * ncol + c];

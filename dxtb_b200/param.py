@@ -128,7 +128,12 @@ class GFN1Param:
         ctab, atab = self._sto[ng]
         alpha = atab[itype] * (zeta * zeta)
         dfact = (1.0, 1.0, 3.0, 15.0, 105.0)[l]
-        coeff = ctab[itype] * (2.0 / math.pi * alpha) ** 0.75 * np.sqrt(4.0 * alpha) ** l / math.sqrt(dfact)
+        # basis/slater.py:52-54, 130-134: the reference keeps its double-factorial table in float32, so sqrt((2l-1)!!) is
+        # taken in float32 before it divides the fp64 coefficients (d shells: sqrt(3) -> 1.7320507764816284).  Together with
+        # the float32 cartesian->spherical matrix (md/trafo.py:37-38, 69-75; XTB_TRAFO_S3 in xtb_integrals.cu) the net effect
+        # is a relative +1.8e-8 on the d(z2) component only: up to 9e-9 on S elements, 5e-10 Eh on MB16_43_01.  Replicated
+        # for parity with dxtb's fp64 path.
+        coeff = ctab[itype] * (2.0 / math.pi * alpha) ** 0.75 * np.sqrt(4.0 * alpha) ** l / float(np.sqrt(np.float32(dfact)))
         return alpha, coeff
 
     def cgto(self, z: int, k: int) -> tuple[np.ndarray, np.ndarray]:

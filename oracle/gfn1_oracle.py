@@ -50,8 +50,10 @@ NLM_CART = (
     np.array([[0, 1, 0], [0, 0, 1], [1, 0, 0]]),  # py, pz, px
     np.array([[2, 0, 0], [0, 2, 0], [0, 0, 2], [1, 1, 0], [1, 0, 1], [0, 1, 1]]),
 )
-_S3 = math.sqrt(3.0)
-_S3_4 = math.sqrt(3.0 / 4.0)
+# trafo.py:37-38, 65-75: TRAFO is built with torch.tensor(...) at the default dtype, i.e. sqrt(3) and sqrt(3)/2 are rounded
+# to float32 before they are cast to the working precision
+_S3 = float(np.float32(math.sqrt(3.0)))
+_S3_4 = float(np.float32(math.sqrt(3.0) * 0.5))
 TRAFO = (
     np.array([[1.0]]),
     np.eye(3),
@@ -114,7 +116,8 @@ class Params:
         coeff_t, alpha_t = self.sto[ng]
         alpha = alpha_t[itype] * zeta**2
         dfact = [1.0, 1.0, 3.0, 15.0, 105.0][l]
-        coeff = coeff_t[itype] * ((2.0 / math.pi * alpha) ** 0.75 * np.sqrt(4 * alpha) ** l / math.sqrt(dfact))
+        # slater.py:52-54: `dfactorial` is a float32 tensor, so its square root is taken in float32 (l = 2: 1.7320507764816284)
+        coeff = coeff_t[itype] * ((2.0 / math.pi * alpha) ** 0.75 * np.sqrt(4 * alpha) ** l / float(np.sqrt(np.float32(dfact))))
         return alpha, coeff
 
     # basis/ortho.py:36-110 and the trigger in basis/bas.py:182-188
