@@ -44,3 +44,21 @@ def gather_results(local: torch.Tensor, n_total: int, group=None) -> torch.Tenso
     bufs = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(bufs, pad, group=group)
     return torch.cat([bufs[r][: b - a] for r, (a, b) in enumerate(sizes)], dim=0)
+
+
+def gather_by_index(local: torch.Tensor, parts, n_total: int, group=None) -> torch.Tensor:
+    """All-gather per-molecule results of arbitrary (e.g. cost-balanced) shards: ``parts[r]`` holds the global molecule
+    ids of rank ``r`` in the order of its local batch.  Returns (n_total, ...) in global order on every rank."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    nmax = max(len(p) for p in parts)
+    pad = local.new_zeros((nmax, *local.shape[1:]))
+    pad[: local.shape[0]] = local
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    out = local.new_zeros((n_total, *local.shape[1:]))
+    for r in range(world):
+        idx = torch.as_tensor(parts[r], dtype=torch.long, device=local.device)
+        out[idx] = bufs[r][: idx.numel()]
+    return out

@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from dxtb_b200.parallel import gather_results, shard_bounds, shard_by_cost
+from dxtb_b200.parallel import gather_by_index, gather_results, shard_bounds, shard_by_cost
 
 
 def test_shard_bounds_cover_everything():
@@ -41,6 +41,13 @@ def _worker(rank, world, port, n_total):
     full = torch.arange(n_total, dtype=torch.float64)
     assert torch.equal(e, -full * 1.5 - 7.0)
     assert f.shape == (n_total, 4, 3) and torch.equal(f[:, 0, 2], 2 * full)
+    # cost-balanced (non-contiguous) shards: the same gather by global molecule id
+    cost = torch.tensor([float((7 * i) % 5 + 1) ** 3 for i in range(n_total)])
+    parts = shard_by_cost(cost, world)
+    mine = parts[rank].to(torch.float64)
+    e2 = gather_by_index(-mine * 1.5 - 7.0, parts, n_total)
+    f2 = gather_by_index(torch.stack([mine, -mine, 2 * mine], dim=-1).unsqueeze(1).expand(-1, 4, -1).contiguous(), parts, n_total)
+    assert torch.equal(e2, e) and torch.equal(f2, f)
     dist.barrier()
     dist.destroy_process_group()
 
