@@ -72,10 +72,10 @@ EXPORTS = {
     "xtb_scf_smem_bytes": (C.c_int64, [_vp]),
     "xtb_scf_smem_bytes_for": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     "xtb_scf_smem_bytes_mode": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
-    "xtb_scf_run": (C.c_int, [_vp] * 21),
+    "xtb_scf_run": (C.c_int, [_vp] * 22),
     "xtb_scf_large_workspace_bytes": (C.c_int64, [C.c_int32] * 4),
-    "xtb_scf_run_large": (C.c_int, [_vp, _vp] + [C.c_int32] * 4 + [_vp] * 18 + [C.c_int64, _vp]),
-    "xtb_grad_bwd": (C.c_int, [_vp] * 15),
+    "xtb_scf_run_large": (C.c_int, [_vp, _vp] + [C.c_int32] * 4 + [_vp] * 19 + [C.c_int64, _vp]),
+    "xtb_grad_bwd": (C.c_int, [_vp] * 16),
     "xtb_d3_fwd": (C.c_int, [_vp] * 6),
 }
 

@@ -51,6 +51,9 @@ DEFAULT_OPTS: dict[str, Any] = {
     "int_driver": "pytorch",
     "force_convergence": False,
     "strict": False,
+    # B200 path only: add the first-order response of the SCF residual to the analytic gradient, so that forces equal the
+    # reference's autograd-through-the-unrolled-SCF forces at ANY convergence threshold (xtb_scf_core.cuh:scf_response)
+    "grad_response": True,
 }
 _IGNORED_OPTS = {"cache_enabled", "cache_charges", "cache_iterations", "cache_density", "cache_potential",
                  "cache_coefficients", "cache_mo_energies", "cache_occupation", "cache_overlap", "cache_hcore",
@@ -93,6 +96,7 @@ class _Workspace:
             self.W = torch.empty(d.struct.mat_total, dtype=f64, device=dev)
         else:
             self.P = self.W = None
+        self.resp = None  # [nao_tot + nsh_tot]: v_out + K y, y_sh (SCF response for the gradient)
 
 
 class _SinglePoint(torch.autograd.Function):
@@ -109,6 +113,9 @@ class _SinglePoint(torch.autograd.Function):
         need_global = calc._use_smem_override in (0, 2) or any(bk["use_smem"] in (0, 2) for bk in calc._buckets)
         ws = _Workspace(d, need_grad, o, need_global)
         excl = calc._exclude
+        response = need_grad and bool(calc.opts["grad_response"]) and not calc._pure_density and int(calc.opts["maxiter"]) > 0
+        if response:
+            ws.resp = torch.zeros(d.nao_tot + d.nsh_tot, dtype=torch.float64, device=d.device)
 
         _abi.check(lib.xtb_geometry_fwd(d.ptr, pos.data_ptr(), ws.cn.data_ptr(), ws.e_rep.data_ptr(), ws.e_xb.data_ptr(), st), "xtb_geometry_fwd")
         if d.has_d3:
@@ -149,13 +156,13 @@ class _SinglePoint(torch.autograd.Function):
                     ws.q0_at.data_ptr(), ws.work.data_ptr(), ws.q_orb.data_ptr(), ws.q_sh.data_ptr(), ws.q_at.data_ptr(),
                     ws.v_orb.data_ptr(), ws.e_atom.data_ptr(), ws.fenergy.data_ptr(), ws.emo.data_ptr(), ws.occ.data_ptr(),
                     ws.iterations.data_ptr(), ws.status.data_ptr(), ws.P.data_ptr() if need_grad else None,
-                    ws.W.data_ptr() if need_grad else None, stream.cuda_stream,
+                    ws.W.data_ptr() if need_grad else None, ws.resp.data_ptr() if response else None, stream.cuda_stream,
                 ),
                 "xtb_scf_run",
             )
         for bk in calc._buckets:
             if bk["use_smem"] == 3:
-                calc._run_large(bk, o, ws, nel_ab, need_grad, st)
+                calc._run_large(bk, o, ws, nel_ab, need_grad, st, response)
         for stream in side:
             if stream is not main:
                 main.wait_stream(stream)
@@ -175,6 +182,7 @@ class _SinglePoint(torch.autograd.Function):
         if need_grad:
             ctx.calc = calc
             ctx.d3w = ws.d3w
+            ctx.resp = ws.resp
             ctx.save_for_backward(pos, ws.cn, ws.S, ws.P, ws.W, ws.v_orb, ws.q_sh, ws.gamma)
         return energy
 
@@ -189,10 +197,13 @@ class _SinglePoint(torch.autograd.Function):
         grad = torch.empty((d.nat_tot, 3), dtype=torch.float64, device=d.device)
         dedcn = torch.empty(d.nat_tot, dtype=torch.float64, device=d.device)
         pairbuf = torch.empty(4 * int(d.struct.gam_total), dtype=torch.float64, device=d.device)
+        resp = ctx.resp
+        v_ptr = resp.data_ptr() if resp is not None else v_orb.data_ptr()
+        y_ptr = resp.data_ptr() + 8 * d.nao_tot if resp is not None else None
         _abi.check(
-            _abi.lib().xtb_grad_bwd(d.ptr, pos.data_ptr(), cn.data_ptr(), S.data_ptr(), P.data_ptr(), W.data_ptr(), v_orb.data_ptr(),
+            _abi.lib().xtb_grad_bwd(d.ptr, pos.data_ptr(), cn.data_ptr(), S.data_ptr(), P.data_ptr(), W.data_ptr(), v_ptr,
                                     q_sh.data_ptr(), gamma.data_ptr(), ge.data_ptr(),
-                                    ctx.d3w.data_ptr() if ctx.d3w is not None else None, pairbuf.data_ptr(), dedcn.data_ptr(),
+                                    ctx.d3w.data_ptr() if ctx.d3w is not None else None, y_ptr, pairbuf.data_ptr(), dedcn.data_ptr(),
                                     grad.data_ptr(),
                                     _stream_ptr(d.device)),
             "xtb_grad_bwd",
@@ -287,6 +298,7 @@ class GFN1Calculator:
         self._large_max_count = int(os.environ.get("DXTB_B200_LARGE_MAX_COUNT", "8"))
         self._buckets = self._make_buckets()
         self._streams: list = []
+        self._pure_density = False  # get_density / get_bond_orders: P without the response density
 
     # ------------------------------------------------------------------------------------------
     def _make_buckets(self) -> list[dict[str, Any]]:
@@ -357,7 +369,7 @@ class GFN1Calculator:
             self._streams.append(torch.cuda.Stream(self.device))
         return self._streams[:n]
 
-    def _run_large(self, bk, o, ws, nel_ab, need_grad: bool, st: int) -> None:
+    def _run_large(self, bk, o, ws, nel_ab, need_grad: bool, st: int, response: bool = False) -> None:
         """Molecules of the large-system bucket, one after the other on the whole device (xtb_scf_run_large)."""
         d, lib = self.desc, _abi.lib()
         nbytes = max(int(lib.xtb_scf_large_workspace_bytes(int(d.nao[m]), int(d.nsh[m]), int(d.nat[m]), int(o.generations)))
@@ -371,7 +383,8 @@ class GFN1Calculator:
                     ws.gamma.data_ptr(), nel_ab.data_ptr(), ws.q0_at.data_ptr(), work.data_ptr(), ws.q_orb.data_ptr(),
                     ws.q_sh.data_ptr(), ws.q_at.data_ptr(), ws.v_orb.data_ptr(), ws.e_atom.data_ptr(), ws.fenergy.data_ptr(),
                     ws.emo.data_ptr(), ws.occ.data_ptr(), ws.iterations.data_ptr(), ws.status.data_ptr(),
-                    ws.P.data_ptr() if need_grad else None, ws.W.data_ptr() if need_grad else None, int(d.mat_off[m]), st,
+                    ws.P.data_ptr() if need_grad else None, ws.W.data_ptr() if need_grad else None,
+                    ws.resp.data_ptr() if response else None, int(d.mat_off[m]), st,
                 ),
                 "xtb_scf_run_large",
             )
@@ -530,7 +543,11 @@ class GFN1Calculator:
     def get_density(self, positions: torch.Tensor, chrg: Any = 0, spin: Any = None, **_: Any) -> torch.Tensor:
         """Density matrix P = C diag(f) C^T of the final solve (calculators/types/abc.py:416-427)."""
         p = positions.detach().clone().requires_grad_(True)  # the kernel writes P, W only when a gradient may follow
-        self.energy(p, chrg, spin)
+        self._pure_density = True
+        try:
+            self.energy(p, chrg, spin)
+        finally:
+            self._pure_density = False
         return self.desc.scatter_matrices(self.cache["ws"].P)
 
     def get_bond_orders(self, positions: torch.Tensor, chrg: Any = 0, spin: Any = None, **_: Any) -> torch.Tensor:

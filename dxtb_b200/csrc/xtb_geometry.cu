@@ -383,7 +383,7 @@ XTB_DEV void xb_grad_atom(const xtb_batch& b, const double* __restrict__ p, int 
 // (ncoord/utils.py:30-52 with the exp-count derivative).  One CTA per molecule.
 // ---------------------------------------------------------------------------------------------
 __global__ void k_grad_atoms(const xtb_batch b, const double* __restrict__ pos, const double* __restrict__ P,
-                             const double* __restrict__ q_sh, const double* __restrict__ gamma,
+                             const double* __restrict__ q_sh, const double* __restrict__ y_sh, const double* __restrict__ gamma,
                              const double* __restrict__ pairbuf, double* __restrict__ dedcn, const double* __restrict__ ge,
                              double* __restrict__ grad) {
   const int m = blockIdx.x;
@@ -457,7 +457,10 @@ __global__ void k_grad_atoms(const xtb_batch b, const double* __restrict__ pos, 
       for (int k = 0; k < nsa; ++k)
         for (int l = 0; l < nsc; ++l) {
           const double gm = g[(size_t)(sa0 + k) * ns + sc0 + l];
-          es -= gm * gm * gm * q_sh[s0 + sa0 + k] * q_sh[s0 + sc0 + l];
+          const double qk = q_sh[s0 + sa0 + k], ql = q_sh[s0 + sc0 + l];
+          double qq = qk * ql;
+          if (y_sh) qq += y_sh[s0 + sa0 + k] * ql + qk * y_sh[s0 + sc0 + l];  // y . dV/dR|_q (SCF response)
+          es -= gm * gm * gm * qq;
         }
       f += es;
       gx += f * dx; gy += f * dy; gz += f * dz;
@@ -640,8 +643,8 @@ int xtb_launch_d3_grad(const xtb_batch* b, const double* pos, const double* d3w,
 }
 
 // used by xtb_grad_bwd (xtb_integrals.cu)
-int xtb_launch_grad_atoms(const xtb_batch* b, const double* pos, const double* P, const double* q_sh, const double* gamma,
-                          const double* pairbuf, double* dedcn, const double* ge, double* grad, cudaStream_t st) {
-  k_grad_atoms<<<b->nb, 128, 0, st>>>(*b, pos, P, q_sh, gamma, pairbuf, dedcn, ge, grad);
+int xtb_launch_grad_atoms(const xtb_batch* b, const double* pos, const double* P, const double* q_sh, const double* y_sh,
+                          const double* gamma, const double* pairbuf, double* dedcn, const double* ge, double* grad, cudaStream_t st) {
+  k_grad_atoms<<<b->nb, 128, 0, st>>>(*b, pos, P, q_sh, y_sh, gamma, pairbuf, dedcn, ge, grad);
   return launch_status();
 }

@@ -358,8 +358,8 @@ int launch_grad_pair(const xtb_batch* b, const double* pos, const double* cn, co
 
 }  // namespace
 
-int xtb_launch_grad_atoms(const xtb_batch* b, const double* pos, const double* P, const double* q_sh, const double* gamma,
-                          const double* pairbuf, double* dedcn, const double* ge, double* grad, cudaStream_t st);
+int xtb_launch_grad_atoms(const xtb_batch* b, const double* pos, const double* P, const double* q_sh, const double* y_sh,
+                          const double* gamma, const double* pairbuf, double* dedcn, const double* ge, double* grad, cudaStream_t st);
 int xtb_launch_d3_grad(const xtb_batch* b, const double* pos, const double* d3w, const double* ge, double* dedcn, double* grad,
                        cudaStream_t st);
 
@@ -385,7 +385,7 @@ extern "C" int xtb_overlap_h0_fwd(const xtb_batch* b, const double* pos, const d
 
 extern "C" int xtb_grad_bwd(const xtb_batch* b, const double* pos, const double* cn, const double* S, const double* P,
                             const double* W, const double* v_orb, const double* q_sh, const double* gamma, const double* ge,
-                            const double* d3w, double* pairbuf, double* dedcn, double* grad, void* stream) {
+                            const double* d3w, const double* y_sh, double* pairbuf, double* dedcn, double* grad, void* stream) {
   (void)S;
   if (!b || !pos || !cn || !P || !W || !v_orb || !q_sh || !gamma || !ge || !pairbuf || !dedcn || !grad) return -1;
   if (b->nb == 0) return 0;
@@ -402,5 +402,5 @@ extern "C" int xtb_grad_bwd(const xtb_batch* b, const double* pos, const double*
   if ((rc = launch_grad_pair<2, 2>(b, pos, cn, P, W, v_orb, pairbuf, st))) return rc;
   // dispersion: direct part into grad, dE/dCN into dedcn (the exp-count CN is shared with H0); one writer per atom
   if (d3w && (rc = xtb_launch_d3_grad(b, pos, d3w, ge, dedcn, grad, st))) return rc;
-  return xtb_launch_grad_atoms(b, pos, P, q_sh, gamma, pairbuf, dedcn, ge, grad, st);
+  return xtb_launch_grad_atoms(b, pos, P, q_sh, y_sh, gamma, pairbuf, dedcn, ge, grad, st);
 }

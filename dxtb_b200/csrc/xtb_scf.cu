@@ -139,7 +139,8 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
       const double* __restrict__ gamma, const double* __restrict__ nel_ab, const double* __restrict__ q0_at, double* __restrict__ work,
       double* __restrict__ q_orb, double* __restrict__ q_sh, double* __restrict__ q_at, double* __restrict__ v_orb,
       double* __restrict__ e_atom, double* __restrict__ fenergy, double* __restrict__ emo, double* __restrict__ occ,
-      int32_t* __restrict__ iterations, int32_t* __restrict__ status, double* __restrict__ Pout, double* __restrict__ Wout) {
+      int32_t* __restrict__ iterations, int32_t* __restrict__ status, double* __restrict__ Pout, double* __restrict__ Wout,
+      double* __restrict__ resp) {
   extern __shared__ double sm[];
   const int m = o.mol_list ? o.mol_list[blockIdx.x] : (int)blockIdx.x;
   const int lnao = o.mol_list ? o.list_nao_max : b.nao_max, lnsh = o.mol_list ? o.list_nsh_max : b.nsh_max,
@@ -276,6 +277,9 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
     }
     __syncthreads();
     gemm_tn<MODE == 1, MODE != 0>(ne, nocc, c.X, c.A, ld, Wm, n, n);
+    // first-order response of the SCF residual (forces of the reference = autograd through the unrolled SCF)
+    if (resp != nullptr && o.maxiter > 0)
+      scf_response<MODE>(c, o, v_orb + c.o0, q_at + c.a0, Pm, Wm, resp + c.o0, resp + b.nao_tot + c.s0, sm_theta);
   }
 }
 
@@ -300,7 +304,7 @@ int64_t mode_smem_bytes(int mode, int64_t nao_max, int64_t nsx, int64_t nax) {
   const xtb_batch *b, const xtb_scf_opts *o, int nblocks, int lnao, int lnsh, int lnat, const double *S, const double *H0,       \
       const double *gamma, const double *nel_ab, const double *q0_at, double *work, double *q_orb, double *q_sh, double *q_at,    \
       double *v_orb, double *e_atom, double *fenergy, double *emo, double *occ, int32_t *iterations, int32_t *status, double *P, \
-      double *W, cudaStream_t st
+      double *W, double *resp, cudaStream_t st
 
 template <int MODE>
 int launch_mode(XTB_SCF_ARGS) {
@@ -315,7 +319,7 @@ int launch_mode(XTB_SCF_ARGS) {
     configured[dev] = smem;
   }
   k_scf<MODE><<<nblocks, NT, (size_t)smem, st>>>(*b, *o, S, H0, gamma, nel_ab, q0_at, work, q_orb, q_sh, q_at, v_orb, e_atom, fenergy, emo,
-                                                  occ, iterations, status, P, W);
+                                                  occ, iterations, status, P, W, resp);
   return launch_status();
 }
 
@@ -326,9 +330,9 @@ int launch_mode(XTB_SCF_ARGS) {
 int xtb_scf_launch_2cta(int mode, XTB_SCF_ARGS) {
   if (mode == 2)
     return launch_mode<2>(b, o, nblocks, lnao, lnsh, lnat, S, H0, gamma, nel_ab, q0_at, work, q_orb, q_sh, q_at, v_orb, e_atom, fenergy,
-                          emo, occ, iterations, status, P, W, st);
+                          emo, occ, iterations, status, P, W, resp, st);
   return launch_mode<0>(b, o, nblocks, lnao, lnsh, lnat, S, H0, gamma, nel_ab, q0_at, work, q_orb, q_sh, q_at, v_orb, e_atom, fenergy, emo,
-                        occ, iterations, status, P, W, st);
+                        occ, iterations, status, P, W, resp, st);
 }
 #else
 int xtb_scf_launch_2cta(int mode, XTB_SCF_ARGS);
@@ -360,7 +364,7 @@ extern "C" int64_t xtb_scf_workspace_bytes(const xtb_batch* b, const xtb_scf_opt
 extern "C" int xtb_scf_run(const xtb_batch* b, const xtb_scf_opts* o, const double* S, const double* H0, const double* gamma,
                            const double* nel_ab, const double* q0_at, void* work, double* q_orb, double* q_sh, double* q_at,
                            double* v_orb, double* e_atom, double* fenergy, double* emo, double* occ, int32_t* iterations,
-                           int32_t* status, double* P, double* W, void* stream) {
+                           int32_t* status, double* P, double* W, double* resp, void* stream) {
   if (!b || !o || !S || !H0 || !gamma || !nel_ab || !q0_at || !work || !q_orb || !q_sh || !q_at || !v_orb || !e_atom || !fenergy ||
       !emo || !occ || !iterations || !status)
     return -1;
@@ -377,7 +381,7 @@ extern "C" int xtb_scf_run(const xtb_batch* b, const xtb_scf_opts* o, const doub
   const int mode = o->use_smem;
   if (mode == 1)
     return launch_mode<1>(b, o, nblocks, lnao, lnsh, lnat, S, H0, gamma, nel_ab, q0_at, wk, q_orb, q_sh, q_at, v_orb, e_atom, fenergy, emo,
-                          occ, iterations, status, P, W, st);
+                          occ, iterations, status, P, W, resp, st);
   // global-memory and hybrid variants: with at least ~1.5 molecules per SM two CTAs per SM (secondary build, 64 registers)
   // overlap one molecule's latency-bound sub-problems with the other's tensor-core passes, if their shared memory fits twice
   static int n_sm = 0;
@@ -389,11 +393,11 @@ extern "C" int xtb_scf_run(const xtb_batch* b, const xtb_scf_opts* o, const doub
   const bool two = 2 * nblocks >= 3 * n_sm && mode_smem_bytes(mode, lnao, lnsh, lnat) <= XTB_SMEM_2CTA;
   if (two)
     return xtb_scf_launch_2cta(mode, b, o, nblocks, lnao, lnsh, lnat, S, H0, gamma, nel_ab, q0_at, wk, q_orb, q_sh, q_at, v_orb, e_atom,
-                               fenergy, emo, occ, iterations, status, P, W, st);
+                               fenergy, emo, occ, iterations, status, P, W, resp, st);
   if (mode == 2)
     return launch_mode<2>(b, o, nblocks, lnao, lnsh, lnat, S, H0, gamma, nel_ab, q0_at, wk, q_orb, q_sh, q_at, v_orb, e_atom, fenergy, emo,
-                          occ, iterations, status, P, W, st);
+                          occ, iterations, status, P, W, resp, st);
   return launch_mode<0>(b, o, nblocks, lnao, lnsh, lnat, S, H0, gamma, nel_ab, q0_at, wk, q_orb, q_sh, q_at, v_orb, e_atom, fenergy, emo,
-                        occ, iterations, status, P, W, st);
+                        occ, iterations, status, P, W, resp, st);
 }
 #endif  // XTB_SECONDARY

@@ -40,6 +40,8 @@ struct Ctx {
   double *xh, *fh;               // Anderson history [gen+1][n] (global)
   int status;
   int sweeps;                    // diagnostic: total Jacobi sweeps of this molecule
+  double ef[2];                  // Fermi level per spin channel of the last fermi_fill (scf_response)
+  bool spin_on[2];               // channel holds electrons
 };
 
 // Address-space hint: lets the compiler emit LDS/STS (32-bit addressing) instead of generic LD/ST.
@@ -515,6 +517,8 @@ __device__ double fermi_fill(Ctx& c, double nel_a, double nel_b, const xtb_scf_o
   __syncthreads();
   double nel[2] = {nel_a, nel_b}, ef[2], ef_used[2], hom[2];
   bool ne_[2];
+  c.spin_on[0] = c.spin_on[1] = false;  // aufbau / empty: no Fermi-function derivative
+  c.ef[0] = c.ef[1] = 0.0;
   if (fabs(nel_a + nel_b) < kEps) {
     for (int k = threadIdx.x; k < n; k += NT) c.focc[k] = 0.0;
     __syncthreads();
@@ -568,6 +572,8 @@ __device__ double fermi_fill(Ctx& c, double nel_a, double nel_b, const xtb_scf_o
     if (fabs(r0) <= o.fermi_thresh && fabs(r1) <= o.fermi_thresh) { conv = true; break; }
   }
   if (!conv) c.status |= XTB_STATUS_FERMI_FAILED;
+  c.ef[0] = ef_used[0]; c.ef[1] = ef_used[1];
+  c.spin_on[0] = ne_[0]; c.spin_on[1] = ne_[1];
   double g = 0.0;
   for (int k = threadIdx.x; k < n; k += NT) {
     double ft = 0.0;
@@ -797,6 +803,204 @@ __device__ bool mix(Ctx& c, Mixer& mx, const xtb_scf_opts& o, double* sm_theta) 
   return conv;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// First-order response of a NOT fully converged SCF state in the nuclear gradient.
+//
+// The reference's forces are autograd through the unrolled SCF (calculators/types/autograd.py:80-201): the exact derivative
+// of E = E[v_in(R), R], v_in being the un-mixed potential that enters the final solve (scf/base.py:497-501) and
+// v_out = V(q_out) the potential of its charges.  With Omega = sum f eps + G stationary in orbitals and occupations,
+//     dE/dR = [Hellmann-Feynman + Pulay terms] + (v_out - v_in) . dq_out/dR ;
+// the last term is first order in the SCF residual (1e-6..1e-5 Eh/bohr at dxtb's default thresholds) and absent from the
+// converged-SCF formula (analytical.py:63-222).  dq_out/dR is expanded with the response of the converged fixed point
+// (coupled-perturbed equations in adjoint form):
+//     y = (1 - chi K)^-1 chi dv,  u = dv + K y,  chi w = -diag(Z_w S),  Z_w = C [(C^T A_w C) o G] C^T,
+//     A_w = -1/2 S o (w (+) w),  G_ij = (f_j - f_i)/(e_j - e_i)  (diagonal: Fermi-function derivative per spin channel with
+//     the Fermi-level shift projected out),  K = dV/dq = gamma + 2 Gamma q_A,
+// and the gradient kernels are fed P + Z_u, W + ZW_u, v_out + K y and y_sh (ES2 cross term).  4 in-CTA GEMMs per
+// application of chi, Anderson-accelerated (same mixer code), <= 12 applications.  Same arithmetic as
+// oracle/gfn1_oracle.py:_scf_response.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kResponseMaxIter = 12;
+constexpr double kResponseTol = 1e-10;
+
+// w = K y: shell/atom sums of y, then gamma y_sh + 2 Gamma q_A y_A (linearised `potential`); leaves y_sh in c.qsh
+__device__ void potential_lin(Ctx& c, const double* __restrict__ y, const double* __restrict__ qat_final, double* __restrict__ wout) {
+  for (int a = threadIdx.x; a < c.na; a += NT) {
+    const int s0 = c.at_sh0[a], nsa = c.at_nsh[a];
+    double ya = 0.0;
+    for (int k = 0; k < nsa; ++k) {
+      double ys = 0.0;
+      const int sh = s0 + k;
+      const int mu0 = c.sh_ao[sh], nmu = 2 * c.sh_l[sh] + 1;
+      for (int mu = mu0; mu < mu0 + nmu; ++mu) ys += y[mu];
+      c.qsh[sh] = ys;
+      ya += ys;
+    }
+    c.qat[a] = ya;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int k = w; k < c.ns; k += NT / 32) {
+    const double* gr = c.gam + (size_t)k * c.ns;
+    double acc = 0.0;
+    for (int l = lane; l < c.ns; l += 32) acc += gr[l] * c.qsh[l];
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      const int a = c.sh_atom[k];
+      c.vsh[k] = acc + 2.0 * c.gam3[(size_t)a * XTB_ATPAR + XTB_AT_GAM3] * qat_final[a] * c.qat[a];
+    }
+  }
+  __syncthreads();
+  for (int mu = threadIdx.x; mu < c.n; mu += NT) wout[mu] = c.vsh[c.ao_sh[mu]];
+  __syncthreads();
+}
+
+// Response density of the Fock perturbation A_w = -1/2 S o (w (+) w):  A <- Z_w (WMAT = false) or ZW_w (WMAT = true).
+// fp0 / fp1: Fermi-function derivatives of the two spin channels.  C is used as scratch and restored.
+template <int MODE, bool WMAT>
+__device__ void response_density(Ctx& c, const double* __restrict__ w, const double* __restrict__ fp0, const double* __restrict__ fp1) {
+  const int n = c.n, ne = c.ne, ld = c.ld;
+  constexpr bool AS = MODE != 0, CS = MODE == 1;
+  for (int t = threadIdx.x; t < ne * ld; t += NT) {
+    const int i = t / ld, j = t - i * ld;
+    c.A[t] = (i < n && j < n) ? -0.5 * c.S[(size_t)i * n + j] * (w[i] + w[j]) : 0.0;
+  }
+  __syncthreads();
+  gemm_tn<AS, CS>(ne, ne, c.A, c.C, ld, c.X, ld, ne);  // X = A_w C
+  gemm_tn<CS, CS>(ne, ne, c.C, c.X, ld, c.A, ld, ne);  // A = C^T A_w C
+  // Fermi-level shift per spin channel: abar_s = sum_k f'_s(k) A_kk / sum_k f'_s(k)
+  double s0 = 0.0, s1 = 0.0, n0 = 0.0, n1 = 0.0;
+  for (int k = threadIdx.x; k < n; k += NT) {
+    const double d = c.A[(size_t)k * ld + k];
+    s0 += fp0[k] * d; n0 += fp0[k];
+    s1 += fp1[k] * d; n1 += fp1[k];
+  }
+  s0 = block_sum(s0, c.red); n0 = block_sum(n0, c.red);
+  s1 = block_sum(s1, c.red); n1 = block_sum(n1, c.red);
+  const double ab0 = fabs(n0) > kTiny ? s0 / n0 : 0.0, ab1 = fabs(n1) > kTiny ? s1 / n1 : 0.0;
+  __syncthreads();
+  for (int t = threadIdx.x; t < ne * ne; t += NT) {
+    const int i = t / ne, j = t - i * ne;
+    if (i > j) continue;
+    double val = 0.0;
+    if (j < n) {
+      const double ei = c.eps[i], ej = c.eps[j], fi = c.focc[i], fj = c.focc[j];
+      const double fpi = fp0[i] + fp1[i], fpj = fp0[j] + fp1[j];
+      if (i == j) {
+        const double d = c.A[(size_t)i * ld + i];
+        const double zd = (d - ab0) * fp0[i] + (d - ab1) * fp1[i];
+        val = WMAT ? d * fi + zd * ei : zd;
+      } else {
+        const double a = 0.5 * (c.A[(size_t)i * ld + j] + c.A[(size_t)j * ld + i]);
+        const double de = ej - ei;
+        const bool close = fabs(de) <= 1e-9;
+        double gf;
+        if (WMAT) gf = close ? 0.5 * ((fi + ei * fpi) + (fj + ej * fpj)) : (fj * ej - fi * ei) / de;
+        else gf = close ? 0.5 * (fpi + fpj) : (fj - fi) / de;
+        val = a * gf;
+      }
+    }
+    c.A[(size_t)i * ld + j] = val;
+    c.A[(size_t)j * ld + i] = val;
+  }
+  // back-transformation Z = C Zt C^T with three buffers: X = C^T, C <- Zt X (= T), A = X^T T, C restored from X
+  for (int t = threadIdx.x; t < ne * ne; t += NT) {
+    const int k = t / ne, i = t - k * ne;
+    c.X[(size_t)k * ld + i] = c.C[(size_t)i * ld + k];
+  }
+  __syncthreads();
+  gemm_tn<AS, CS>(ne, ne, c.A, c.X, ld, c.C, ld, ne);  // T[i][nu] = sum_j Zt[j][i] C^T[j][nu]
+  gemm_tn<CS, CS>(ne, ne, c.X, c.C, ld, c.A, ld, ne);  // Z[mu][nu] = sum_i C^T[i][mu] T[i][nu]
+  for (int t = threadIdx.x; t < ne * ne; t += NT) {
+    const int i = t / ne, k = t - i * ne;
+    c.C[(size_t)i * ld + k] = c.X[(size_t)k * ld + i];
+  }
+  __syncthreads();
+}
+
+// out[mu] = add[mu] - sum_nu Z[mu][nu] S[mu][nu]  (Z in the A buffer): the response charges chi w (+ add)
+__device__ void response_charges(Ctx& c, const double* __restrict__ add, double* __restrict__ out) {
+  const int n = c.n, ld = c.ld;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int mu = w; mu < n; mu += NT / 32) {
+    const double* zr = c.A + (size_t)mu * ld;
+    const double* sr = c.S + (size_t)mu * n;
+    double acc = 0.0;
+    for (int nu = lane; nu < n; nu += 32) acc = fma(zr[nu], sr[nu], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) out[mu] = (add ? add[mu] : 0.0) - acc;
+  }
+  __syncthreads();
+}
+
+// Runs after the final solve and after P, W were written: adds Z_u, ZW_u to Pm, Wm and writes v_out + K y / y_sh.
+// Vector scratch (all free after emit_results): dv -> eorb, z0 -> q, y -> v, w/u -> n0 and vnew, f'_0 -> srt, f'_1 -> cs.
+template <int MODE>
+__device__ void scf_response(Ctx& c, const xtb_scf_opts& o, const double* __restrict__ v_out_g, const double* __restrict__ qat_final,
+                             double* __restrict__ Pm, double* __restrict__ Wm, double* __restrict__ v_grad, double* __restrict__ y_sh,
+                             double* sm_theta) {
+  const int n = c.n, ld = c.ld;
+  double* dv = c.eorb; double* z0 = c.q; double* w = c.n0; double* fp0 = c.srt; double* fp1 = c.cs;
+  for (int k = threadIdx.x; k < n; k += NT) {
+    dv[k] = c.vnew[k] - c.v[k];
+    double f[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      f[s] = 0.0;
+      if (c.spin_on[s] && o.kt >= 3e-7) {
+        const double ex = (c.eps[k] - c.ef[s]) / o.kt;
+        if (ex < 50.0) f[s] = 1.0 / (exp(ex) + 1.0);
+      }
+    }
+    fp0[k] = -(f[0] * (1.0 - f[0])) / o.kt;
+    fp1[k] = -(f[1] * (1.0 - f[1])) / o.kt;
+  }
+  __syncthreads();
+  response_density<MODE, false>(c, dv, fp0, fp1);
+  response_charges(c, nullptr, z0);
+  for (int k = threadIdx.x; k < n; k += NT) c.v[k] = z0[k];
+  __syncthreads();
+  xtb_scf_opts o2 = o;
+  o2.mixer = 0; o2.soft_start = 0; o2.damp = 0.5; o2.damp_init = 0.5; o2.diag_offset = 0.01;
+  o2.x_atol = 0.0; o2.x_atol_max = 0.0;  // the stop test is the max-norm below
+  Mixer mx;
+  mx.step = 0; mx.head = 0;
+  for (int it = 0; it < kResponseMaxIter; ++it) {
+    potential_lin(c, c.v, qat_final, w);
+    response_density<MODE, false>(c, w, fp0, fp1);
+    response_charges(c, z0, c.vnew);  // y_new = z0 + chi K y
+    double res = 0.0;
+    for (int k = threadIdx.x; k < n; k += NT) res = fmax(res, fabs(c.vnew[k] - c.v[k]));
+    res = block_max(res, c.red);
+    __syncthreads();
+    if (res < kResponseTol) {
+      for (int k = threadIdx.x; k < n; k += NT) c.v[k] = c.vnew[k];
+      __syncthreads();
+      break;
+    }
+    mix(c, mx, o2, sm_theta);
+  }
+  potential_lin(c, c.v, qat_final, w);  // w = K y, c.qsh = y_sh
+  for (int k = threadIdx.x; k < c.ns; k += NT) y_sh[k] = c.qsh[k];
+  for (int k = threadIdx.x; k < n; k += NT) {
+    v_grad[k] = v_out_g[k] + w[k];
+    c.vnew[k] = dv[k] + w[k];  // u
+  }
+  __syncthreads();
+  response_density<MODE, false>(c, c.vnew, fp0, fp1);
+  for (int t = threadIdx.x; t < n * n; t += NT) {
+    const int i = t / n, j = t - i * n;
+    Pm[t] += c.A[(size_t)i * ld + j];
+  }
+  __syncthreads();
+  response_density<MODE, true>(c, c.vnew, fp0, fp1);
+  for (int t = threadIdx.x; t < n * n; t += NT) {
+    const int i = t / n, j = t - i * n;
+    Wm[t] += c.A[(size_t)i * ld + j];
+  }
+  __syncthreads();
+}
 
 // Per-molecule results of the converged SCF: charges, potential, orbital energies / occupations, atom-resolved energies.
 __device__ void emit_results(Ctx& c, const xtb_batch& b, int m, double g, int iters, double* __restrict__ q_orb, double* __restrict__ q_sh,

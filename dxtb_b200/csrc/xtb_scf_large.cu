@@ -29,7 +29,10 @@ struct LargeState {  // device-resident scalars of one large-molecule SCF
   double off;        // max |off-diagonal| (Jacobi sweep test), compared as raw bits (non-negative doubles)
   int mixer_step, mixer_head;
   int status, sweeps, nocc, converged;
-  int pad[8];
+  double ef[2];      // Fermi levels of the last solve (SCF response)
+  double abar[2];    // Fermi-level shifts of the current response density
+  int spin_on[2];
+  int pad[2];
 };
 
 struct Layout {  // workspace offsets in doubles
@@ -47,7 +50,7 @@ __host__ __device__ inline Layout layout(int n, int ns, int na, int gen) {
   l.A = p; p += m;
   l.X = p; p += m;
   l.Q = p; p += (size_t)2 * l.nbp * OP * OP;  // accumulated rotations, double buffered by round parity
-  l.vec = p; p += (size_t)8 * (n + 2) + 2 * ns + na + 32 + 36 + (n + 4) / 2 + 2;
+  l.vec = p; p += (size_t)8 * (n + 2) + 2 * ns + na + 32 + 36 + (n + 4) / 2 + 2 + (n + 2);  // + f'_beta of the SCF response
   p += p & 1;
   l.hist = p; p += (size_t)2 * (gen + 1) * n;
   p += p & 1;
@@ -76,8 +79,9 @@ __device__ void large_ctx(Ctx& c, const xtb_batch& b, int m, double* work, int g
   c.qsh = p; p += c.ns; c.vsh = p; p += c.ns; c.qat = p; p += c.na;
   c.red = p; p += 32;
   c.cs = p; p += 36;  // Anderson small system (sm_theta of the batch kernel)
-  c.occl = (int*)p;
-  c.pp = c.qq = nullptr; c.jq = c.jm = c.jr = nullptr;
+  c.occl = (int*)p; p += (c.n + 4) / 2 + 2;
+  c.pp = c.qq = nullptr; c.jq = c.jm = nullptr;
+  c.jr = p;  // f'_beta of the SCF response (the batch kernel keeps it in its Jacobi scratch c.cs)
   c.xh = work + l.hist;
   c.fh = c.xh + (size_t)(gen + 1) * c.n;
   c.S = S + b.mat_off[m];
@@ -503,15 +507,100 @@ kl_jacobi_pass(double* __restrict__ A, double* __restrict__ V, const double* __r
   }
 }
 
+// ---- SCF response of the nuclear gradient (see scf_response in xtb_scf_core.cuh), grid-wide stages ----------------------
+// A = -1/2 S (w_i + w_j), zero padded
+__global__ void kl_resp_fock(double* __restrict__ A, const double* __restrict__ S, const double* __restrict__ w, int n, int ne) {
+  const size_t tot = (size_t)ne * ne;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(t / ne), j = (int)(t - (size_t)i * ne);
+    A[t] = (i < n && j < n) ? -0.5 * S[(size_t)i * n + j] * (w[i] + w[j]) : 0.0;
+  }
+}
+
+// Fermi-level shift per spin channel of the response density: abar_s = sum f'_s(k) At_kk / sum f'_s(k)   (one CTA)
+__global__ void kl_resp_abar(const double* __restrict__ A, const double* __restrict__ fp0, const double* __restrict__ fp1, int n, int ne,
+                             LargeState* st) {
+  __shared__ double red[32];
+  double s0 = 0.0, s1 = 0.0, n0 = 0.0, n1 = 0.0;
+  for (int k = threadIdx.x; k < n; k += blockDim.x) {
+    const double d = A[(size_t)k * ne + k];
+    s0 += fp0[k] * d; n0 += fp0[k];
+    s1 += fp1[k] * d; n1 += fp1[k];
+  }
+  s0 = block_sum(s0, red); n0 = block_sum(n0, red);
+  s1 = block_sum(s1, red); n1 = block_sum(n1, red);
+  if (threadIdx.x == 0) {
+    st->abar[0] = fabs(n0) > kTiny ? s0 / n0 : 0.0;
+    st->abar[1] = fabs(n1) > kTiny ? s1 / n1 : 0.0;
+  }
+}
+
+// At -> Zt = At o G (wmat = 0) or ZWt = At o Ge (wmat = 1), symmetrised, pads zero; same formulas as response_density()
+__global__ void kl_resp_scale(double* __restrict__ A, const double* __restrict__ eps, const double* __restrict__ focc,
+                              const double* __restrict__ fp0, const double* __restrict__ fp1, int n, int ne, int wmat,
+                              const LargeState* st) {
+  const size_t tot = (size_t)ne * ne;
+  const double ab0 = st->abar[0], ab1 = st->abar[1];
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(t / ne), j = (int)(t - (size_t)i * ne);
+    if (i > j) continue;
+    double val = 0.0;
+    if (j < n) {
+      const double ei = eps[i], ej = eps[j], fi = focc[i], fj = focc[j];
+      const double fpi = fp0[i] + fp1[i], fpj = fp0[j] + fp1[j];
+      if (i == j) {
+        const double d = A[t];
+        const double zd = (d - ab0) * fp0[i] + (d - ab1) * fp1[i];
+        val = wmat ? d * fi + zd * ei : zd;
+      } else {
+        const double a = 0.5 * (A[(size_t)i * ne + j] + A[(size_t)j * ne + i]);
+        const double de = ej - ei;
+        const bool close = fabs(de) <= 1e-9;
+        double gf;
+        if (wmat) gf = close ? 0.5 * ((fi + ei * fpi) + (fj + ej * fpj)) : (fj * ej - fi * ei) / de;
+        else gf = close ? 0.5 * (fpi + fpj) : (fj - fi) / de;
+        val = a * gf;
+      }
+    }
+    A[(size_t)i * ne + j] = val;
+    A[(size_t)j * ne + i] = val;
+  }
+}
+
+// out[mu] = add[mu] - sum_nu Z[mu][nu] S[mu][nu]: one warp per row
+__global__ void kl_resp_charges(const double* __restrict__ Z, const double* __restrict__ S, const double* __restrict__ add,
+                                double* __restrict__ out, int n, int ne) {
+  const int lane = threadIdx.x & 31;
+  const int mu = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (mu >= n) return;
+  const double* zr = Z + (size_t)mu * ne;
+  const double* sr = S + (size_t)mu * n;
+  double acc = 0.0;
+  for (int nu = lane; nu < n; nu += 32) acc = fma(zr[nu], sr[nu], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) out[mu] = (add ? add[mu] : 0.0) - acc;
+}
+
+// dst (n x n) += / = src (ne x ne)
+__global__ void kl_pack_add(double* __restrict__ dst, const double* __restrict__ src, int n, int ne, int add) {
+  const size_t tot = (size_t)n * n;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(t / n), j = (int)(t - (size_t)i * n);
+    const double v = src[(size_t)i * ne + j];
+    dst[t] = add ? dst[t] + v : v;
+  }
+}
+
 // ---- single-CTA vector stages (reuse the device functions of the batch kernel) ----------------------------------------
-enum Phase { PH_INIT = 0, PH_FERMI = 1, PH_POT = 2, PH_MIX = 3, PH_COPYV = 4, PH_EMIT = 5 };
+enum Phase { PH_INIT = 0, PH_FERMI = 1, PH_POT = 2, PH_MIX = 3, PH_COPYV = 4, PH_EMIT = 5,
+             PH_RESP_INIT = 6, PH_RESP_Y0 = 7, PH_RESP_KY = 8, PH_RESP_STEP = 9, PH_RESP_FINAL = 10 };
 
 __global__ void __launch_bounds__(NT, 1)
 kl_vec(int phase, const xtb_batch b, const xtb_scf_opts o, int m, const double* __restrict__ S, const double* __restrict__ H0,
        const double* __restrict__ gamma, const double* __restrict__ nel_ab, const double* __restrict__ q0_at, double* __restrict__ work,
        double* __restrict__ q_orb, double* __restrict__ q_sh, double* __restrict__ q_at, double* __restrict__ v_orb,
        double* __restrict__ e_atom, double* __restrict__ fenergy, double* __restrict__ emo, double* __restrict__ occ,
-       int32_t* __restrict__ iterations, int32_t* __restrict__ status, int iters) {
+       int32_t* __restrict__ iterations, int32_t* __restrict__ status, int iters, double* __restrict__ resp) {
   Ctx c;
   large_ctx(c, b, m, work, o.generations, S, H0, gamma);
   const Layout l = layout(c.n, c.ns, c.na, o.generations);
@@ -543,6 +632,8 @@ kl_vec(int phase, const xtb_batch b, const xtb_scf_opts o, int m, const double* 
       st->nocc = no;
       st->g = g;
       st->status |= c.status;
+      st->ef[0] = c.ef[0]; st->ef[1] = c.ef[1];
+      st->spin_on[0] = c.spin_on[0]; st->spin_on[1] = c.spin_on[1];
     }
   } else if (phase == PH_POT) {
     potential(c, c.q, c.vnew);
@@ -563,6 +654,53 @@ kl_vec(int phase, const xtb_batch b, const xtb_scf_opts o, int m, const double* 
     c.status = st->status;
     c.sweeps = st->sweeps;
     emit_results(c, b, m, st->g, iters, q_orb, q_sh, q_at, v_orb, e_atom, fenergy, emo, occ, iterations, status);
+  } else if (phase == PH_RESP_INIT) {
+    // SCF response (xtb_scf_core.cuh:scf_response): dv -> eorb, f'_alpha -> srt, f'_beta -> jr; runs after PH_EMIT
+    for (int k = threadIdx.x; k < n; k += NT) {
+      c.eorb[k] = c.vnew[k] - c.v[k];
+      double f[2];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        f[s] = 0.0;
+        if (st->spin_on[s] && o.kt >= 3e-7) {
+          const double ex = (c.eps[k] - st->ef[s]) / o.kt;
+          if (ex < 50.0) f[s] = 1.0 / (exp(ex) + 1.0);
+        }
+      }
+      c.srt[k] = -(f[0] * (1.0 - f[0])) / o.kt;
+      c.jr[k] = -(f[1] * (1.0 - f[1])) / o.kt;
+    }
+    if (threadIdx.x == 0) { st->mixer_step = 0; st->mixer_head = 0; st->converged = 0; }
+  } else if (phase == PH_RESP_Y0) {
+    for (int k = threadIdx.x; k < n; k += NT) c.v[k] = c.q[k];  // y = z0
+  } else if (phase == PH_RESP_KY) {
+    potential_lin(c, c.v, q_at + c.a0, c.n0);  // w = K y
+  } else if (phase == PH_RESP_STEP) {
+    double res = 0.0;
+    for (int k = threadIdx.x; k < n; k += NT) res = fmax(res, fabs(c.vnew[k] - c.v[k]));
+    res = block_max(res, c.red);
+    __syncthreads();
+    if (res < kResponseTol) {
+      for (int k = threadIdx.x; k < n; k += NT) c.v[k] = c.vnew[k];
+      if (threadIdx.x == 0) st->converged = 1;
+    } else {
+      xtb_scf_opts o2 = o;
+      o2.mixer = 0; o2.soft_start = 0; o2.damp = 0.5; o2.damp_init = 0.5; o2.diag_offset = 0.01;
+      o2.x_atol = 0.0; o2.x_atol_max = 0.0;
+      Mixer mx;
+      mx.step = st->mixer_step;
+      mx.head = st->mixer_head;
+      __syncthreads();
+      mix(c, mx, o2, c.cs);
+      if (threadIdx.x == 0) { st->mixer_step = mx.step; st->mixer_head = mx.head; }
+    }
+  } else if (phase == PH_RESP_FINAL) {
+    potential_lin(c, c.v, q_at + c.a0, c.n0);  // w = K y, qsh = y_sh
+    for (int k = threadIdx.x; k < c.ns; k += NT) resp[b.nao_tot + c.s0 + k] = c.qsh[k];
+    for (int k = threadIdx.x; k < n; k += NT) {
+      resp[c.o0 + k] = v_orb[c.o0 + k] + c.n0[k];
+      c.vnew[k] = c.eorb[k] + c.n0[k];  // u = dv + K y
+    }
   }
 }
 
@@ -584,7 +722,7 @@ extern "C" int xtb_scf_run_large(const xtb_batch* b, const xtb_scf_opts* o, int3
                                  const double* S, const double* H0, const double* gamma, const double* nel_ab, const double* q0_at,
                                  void* work_, double* q_orb, double* q_sh, double* q_at, double* v_orb, double* e_atom, double* fenergy,
                                  double* emo, double* occ, int32_t* iterations, int32_t* status, double* P, double* W,
-                                 int64_t mat_off, void* stream) {
+                                 double* resp, int64_t mat_off, void* stream) {
   if (!b || !o || !S || !H0 || !gamma || !nel_ab || !q0_at || !work_ || !q_orb || !q_sh || !q_at || !v_orb || !e_atom || !fenergy ||
       !emo || !occ || !iterations || !status)
     return -1;
@@ -601,9 +739,10 @@ extern "C" int xtb_scf_run_large(const xtb_batch* b, const xtb_scf_opts* o, int3
   const double* Hm = H0 + mat_off;
   double* vecp = work + l.vec;
   const int nmx = n + 2;
-  double *eps = vecp, *focc = vecp + 2 * (size_t)nmx, *v = vecp + 3 * (size_t)nmx, *q = vecp + 5 * (size_t)nmx, *n0 = vecp + 6 * (size_t)nmx,
-         *eorb = vecp + 7 * (size_t)nmx;
+  double *eps = vecp, *srt = vecp + (size_t)nmx, *focc = vecp + 2 * (size_t)nmx, *v = vecp + 3 * (size_t)nmx, *vnew = vecp + 4 * (size_t)nmx,
+         *q = vecp + 5 * (size_t)nmx, *n0 = vecp + 6 * (size_t)nmx, *eorb = vecp + 7 * (size_t)nmx;
   const int* occl = (const int*)(vecp + 8 * (size_t)nmx + 2 * (size_t)nsh + nat + 32 + 36);
+  double* fp1 = vecp + 8 * (size_t)nmx + 2 * (size_t)nsh + nat + 32 + 36 + (size_t)(n + 4) / 2 + 2;  // large_ctx: c.jr
 
   static bool configured[64] = {};  // function attributes are per device
   {
@@ -650,7 +789,7 @@ extern "C" int xtb_scf_run_large(const xtb_batch* b, const xtb_scf_opts* o, int3
   };
   auto vec = [&](int phase, int iters) {
     kl_vec<<<1, NT, 0, st>>>(phase, *b, *o, mol, S, H0, gamma, nel_ab, q0_at, work, q_orb, q_sh, q_at, v_orb, e_atom, fenergy, emo, occ,
-                             iterations, status, iters);
+                             iterations, status, iters, resp);
   };
   auto gemm = [&](const double* L, const double* R, double* Out, int K) {
     kl_gemm_tn<<<dim3(ne / GT, ne / GT), NT, 4 * GK * GLD * 8, st>>>(L, R, Out, ne, K);
@@ -752,14 +891,47 @@ extern "C" int xtb_scf_run_large(const xtb_batch* b, const xtb_scf_opts* o, int3
   vec(PH_EMIT, iters);
   if (o->want_density) {
     kl_pack<<<ew_grid, 256, 0, st>>>(P + mat_off, A, n, ne);
+    const bool response = resp != nullptr && o->maxiter > 0;
+    if (response) {
+      // First-order response of the SCF residual (xtb_scf_core.cuh:scf_response), every stage grid-wide; C is scratch of
+      // the back-transformation and restored by the second transpose.  Z (or ZW) of the perturbation w ends up in A.
+      auto respond = [&](const double* w, int wmat) {
+        kl_resp_fock<<<ew_grid, 256, 0, st>>>(A, Sm, w, n, ne);
+        gemm(A, C, X, ne);  // X = A_w C
+        gemm(C, X, A, ne);  // A = C^T A_w C
+        kl_resp_abar<<<1, 512, 0, st>>>(A, srt, fp1, n, ne, dst);
+        kl_resp_scale<<<ew_grid, 256, 0, st>>>(A, eps, focc, srt, fp1, n, ne, wmat, dst);
+        kl_transpose<<<dim3(ne / 32, ne / 32), 256, 0, st>>>(X, C, ne);  // X = C^T
+        gemm(A, X, C, ne);                                               // C <- T = Zt C^T
+        gemm(X, C, A, ne);                                               // A = C T = Z
+        kl_transpose<<<dim3(ne / 32, ne / 32), 256, 0, st>>>(C, X, ne);  // C restored
+      };
+      vec(PH_RESP_INIT, 0);
+      respond(eorb, 0);
+      kl_resp_charges<<<(n + 7) / 8, 256, 0, st>>>(A, Sm, nullptr, q, n, ne);  // z0 = chi dv
+      vec(PH_RESP_Y0, 0);
+      for (int it = 0; it < kResponseMaxIter; ++it) {
+        vec(PH_RESP_KY, 0);
+        respond(n0, 0);
+        kl_resp_charges<<<(n + 7) / 8, 256, 0, st>>>(A, Sm, q, vnew, n, ne);  // y_new = z0 + chi K y
+        vec(PH_RESP_STEP, 0);
+        if (int e = read_state()) return e;
+        if (hs.converged) break;
+      }
+      vec(PH_RESP_FINAL, 0);
+      respond(vnew, 0);
+      kl_pack_add<<<ew_grid, 256, 0, st>>>(P + mat_off, A, n, ne, 1);  // P += Z_u
+      respond(vnew, 1);
+      kl_pack_add<<<ew_grid, 256, 0, st>>>(W + mat_off, A, n, ne, 0);  // W = ZW_u (+ the density-weighted part below)
+    }
     const int nocc = hs.nocc, kocc = (nocc + GK - 1) / GK * GK;
     if (kocc > 0) {
       // W = C diag(f eps) C^T = Y1^T Y2 (X, A buffers) -> C buffer (no longer needed)
       kl_build_y<<<dim3(ne / 32, (kocc + 31) / 32), 256, 0, st>>>(X, A, C, focc, eps, occl, n, ne, nocc, kocc, 1);
       // C is read by kl_build_y and overwritten by the GEMM: same stream, ordered
       gemm(X, A, C, kocc);
-      kl_pack<<<ew_grid, 256, 0, st>>>(W + mat_off, C, n, ne);
-    } else {
+      kl_pack_add<<<ew_grid, 256, 0, st>>>(W + mat_off, C, n, ne, response ? 1 : 0);
+    } else if (!response) {
       cudaMemsetAsync(W + mat_off, 0, (size_t)n * n * 8, st);
     }
   }

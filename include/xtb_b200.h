@@ -153,12 +153,13 @@ int xtb_eeq_guess_large(const xtb_batch* b, int32_t mol, int32_t nat, int64_t at
    as a sequence of grid-wide kernels (tensor-core GEMMs + two-level block Jacobi) driven from the host; synchronises
    `stream`.  Same inputs / outputs / status bits as xtb_scf_run; `mat_off` = offset of the molecule in S/H0/P/W (doubles);
    `work` holds xtb_scf_large_workspace_bytes(nao, nsh, nat, generations) bytes.  Replaces the same reference loop as
-   xtb_scf_run (scf/unrolling/default.py:64-137 with scf/base.py:818-907) for systems the one-CTA kernel cannot hold. */
+   xtb_scf_run (scf/unrolling/default.py:64-137 with scf/base.py:818-907) for systems the one-CTA kernel cannot hold.
+   resp: as in xtb_scf_run (whole-batch array [nao_tot + nsh_tot], this molecule's slices are written), or NULL. */
 int64_t xtb_scf_large_workspace_bytes(int32_t nao, int32_t nsh, int32_t nat, int32_t generations);
 int xtb_scf_run_large(const xtb_batch* b, const xtb_scf_opts* o, int32_t mol, int32_t nao, int32_t nsh, int32_t nat, const double* S,
                       const double* H0, const double* gamma, const double* nel_ab, const double* q0_at, void* work, double* q_orb,
                       double* q_sh, double* q_at, double* v_orb, double* e_atom, double* fenergy, double* emo, double* occ,
-                      int32_t* iterations, int32_t* status, double* P, double* W, int64_t mat_off, void* stream);
+                      int32_t* iterations, int32_t* status, double* P, double* W, double* resp, int64_t mat_off, void* stream);
 
 /* Dynamic shared memory the SCF kernel needs with use_smem=1 (host compares with the device limit). */
 int64_t xtb_scf_smem_bytes(const xtb_batch* b);
@@ -173,20 +174,28 @@ int64_t xtb_scf_smem_bytes_mode(int32_t mode, int32_t nao_max, int32_t nsh_max, 
  *   nel_ab [nb][2]  alpha/beta electron numbers; q0_at [nat_tot] guess atomic charges
  *   outputs: q_orb [nao_tot], q_sh [nsh_tot], q_at [nat_tot], v_orb [nao_tot] (potential of the final charges),
  *            e_atom [nat_tot] (electronic + ES2 + ES3 + G/nat), fenergy [nb], emo [nao_tot], occ [nao_tot],
- *            iterations [nb], status [nb]; P, W [mat_off[nb]] if want_density */
+ *            iterations [nb], status [nb]; P, W [mat_off[nb]] if want_density
+ *   resp [nao_tot + nsh_tot] or NULL (needs want_density): first-order response of the SCF residual for the nuclear
+ *            gradient.  The reference's forces are autograd through the unrolled SCF (calculators/types/autograd.py:80-201),
+ *            i.e. they contain (v_out - v_in) . dq/dR of the not fully converged state; with resp != NULL the kernel solves
+ *            the coupled-perturbed equations for it, ADDS the response densities to P and W, and writes
+ *            resp[0..nao_tot) = v_out + K y (potential to hand to xtb_grad_bwd instead of v_orb) and
+ *            resp[nao_tot..) = y_sh (ES2 cross term of xtb_grad_bwd).  See xtb_scf_core.cuh:scf_response. */
 int xtb_scf_run(const xtb_batch* b, const xtb_scf_opts* o, const double* S, const double* H0, const double* gamma,
                 const double* nel_ab, const double* q0_at, void* work, double* q_orb, double* q_sh, double* q_at,
                 double* v_orb, double* e_atom, double* fenergy, double* emo, double* occ, int32_t* iterations,
-                int32_t* status, double* P, double* W, void* stream);
+                int32_t* status, double* P, double* W, double* resp, void* stream);
 
 /* Analytic nuclear gradient of the converged single point (calculators/types/analytical.py:63-222,
  * xtb/gfn1.py:185-408, secondorder.py:873-926, repulsion/base.py:337-406, ncoord/utils.py:30-52):
  * grad[a] = ge[m] * dE_m/dR_a, ge [nb] being the upstream gradient of the molecular energies.
  * dedcn [nat_tot] and pairbuf [4 * gam_off[nb]] are scratch; d3w = weights of xtb_d3_fwd, or NULL when
- * dispersion is excluded.  No atomics: the result is bit-reproducible. */
+ * dispersion is excluded.  y_sh [nsh_tot] = response shell charges of xtb_scf_run (resp + nao_tot), or NULL: adds
+ * y . dV/dR|_q = sum y_s dgamma_st/dR q_t to the second-order term; v_orb is then resp[0..nao_tot) and P, W carry the
+ * response densities.  No atomics: the result is bit-reproducible. */
 int xtb_grad_bwd(const xtb_batch* b, const double* pos, const double* cn, const double* S, const double* P,
                  const double* W, const double* v_orb, const double* q_sh, const double* gamma, const double* ge,
-                 const double* d3w, double* pairbuf, double* dedcn, double* grad, void* stream);
+                 const double* d3w, const double* y_sh, double* pairbuf, double* dedcn, double* grad, void* stream);
 
 /* D3(BJ) two-body dispersion energy (tad-dftd3 dftd3: weight_references, atomic_c6, dispersion with
  * rational_damping; s9 = 0 for GFN1).  cn is the exp-count CN of xtb_geometry_fwd; d3w [nat_tot][14] receives

@@ -699,6 +699,8 @@ DEFAULT_OPTS = dict(
     maxiter=100, mixer="anderson", damp=0.5, damp_init=0.1, damp_generations=5, damp_diagonal_offset=0.01,
     damp_soft_start=True, x_atol=1e-4, x_atol_max=1e-5, fermi_etemp=300.0, fermi_maxiter=200, fermi_thresh=None,
     guess="eeq", exclude=(), int_cutoff=INT_CUTOFF,
+    # gradient: add the first-order response of the not fully converged SCF state (see _scf_response)
+    grad_response=True, response_maxiter=12, response_tol=1e-10,
 )
 
 
@@ -721,6 +723,8 @@ class Result:
     P: np.ndarray = None
     W: np.ndarray = None
     v_orb: np.ndarray = None
+    v_in: np.ndarray = None  # input potential of the final solve (the un-mixed potential of the last iteration)
+    C: np.ndarray = None
     emo: np.ndarray = None
     occ: np.ndarray = None
     cn: np.ndarray = None
@@ -836,12 +840,13 @@ def singlepoint(numbers, positions, chrg: float = 0.0, opts: dict | None = None,
                 break
     # converged_to_charges: one more solve with the un-mixed potential (scf/base.py:497-501)
     fcn(v_new)
+    res.v_in = v_new.copy()
     st = state
     res.iterations, res.converged = iters, converged
     res.q_orb, res.q_sh, res.q_at = st["q"], st["q_sh"], st["q_at"]
     # potential of the FINAL charges: what the reference hands to its analytic gradient (scf/base.py:468)
     v_fin = _potential(m, st["q"], gam, g3)[0]
-    res.P, res.emo, res.occ, res.v_orb = st["P"], st["emo"], st["occ"], v_fin
+    res.P, res.emo, res.occ, res.v_orb, res.C = st["P"], st["emo"], st["occ"], v_fin, st["C"]
 
     # energies (scf/base.py:514-534, 558-607; interactions/base.py:305-360)
     v_es2 = gam @ st["q_sh"]
@@ -863,7 +868,14 @@ def singlepoint(numbers, positions, chrg: float = 0.0, opts: dict | None = None,
         W = (st["C"] * (focc * st["emo"])[None, :]) @ st["C"].T
         res.W = W
         parts: dict = {}
-        g_tot += _electronic_gradient(m, pos, S, dS, st["P"], W, v_fin, cn, dcfdr, st["q_sh"], gam, parts)
+        P_eff, W_eff, v_grad, y_sh = st["P"], W, v_fin, None
+        if o["grad_response"] and o["maxiter"] > 0:
+            Z, ZW, y, Ky = _scf_response(m, S, st["C"], st["emo"], occ, kt, gam, g3, st["q_at"], v_fin - res.v_in,
+                                         o["response_maxiter"], o["response_tol"])
+            P_eff, W_eff, v_grad = st["P"] + Z, W + ZW, v_fin + Ky
+            y_sh = np.bincount(m.ao_sh, weights=y, minlength=m.nsh)
+            parts["response_y"] = y
+        g_tot += _electronic_gradient(m, pos, S, dS, P_eff, W_eff, v_grad, cn, dcfdr, st["q_sh"], gam, parts, y_sh=y_sh)
         res.gradient_parts = parts
         if d3_dedcn is not None:  # CN chain rule of the dispersion energy (same exp-count CN as H0)
             g_tot += (dcfdr * (d3_dedcn[:, None] + d3_dedcn[None, :])[:, :, None]).sum(1)
@@ -871,7 +883,73 @@ def singlepoint(numbers, positions, chrg: float = 0.0, opts: dict | None = None,
     return res
 
 
-def _electronic_gradient(m: Mol, pos, S, dS, P, W, v, cn, dcfdr, q_sh, gam, parts: dict | None = None):
+def _scf_response(m: Mol, S, C, emo, occ, kt, gam, g3, q_at, dv, maxiter=12, tol=1e-10):
+    """First-order correction of the analytic gradient for a NOT fully converged SCF state.
+
+    The reference's forces are autograd through the unrolled SCF (calculators/types/autograd.py:80-201): the exact
+    derivative of the energy it computes, E = E[v_in(R), R], where v_in is the un-mixed potential that enters the final
+    solve (scf/base.py:497-501) and v_out = V(q_out) the potential of the resulting charges.  With Omega = sum f eps + G
+    stationary in the orbitals and occupations,
+        dE/dR = [Hellmann-Feynman + Pulay terms] + (v_out - v_in) . dq_out/dR ,
+    and the last term (first order in the SCF residual dv = v_out - v_in; 1e-6..1e-5 Eh/bohr at dxtb's default thresholds)
+    is what the converged-SCF formula of analytical.py:63-222 leaves out.  dq_out/dR is expanded with the response of the
+    converged fixed point (coupled-perturbed equations in adjoint / Z-vector form):
+        y = (1 - chi K)^-1 chi dv,   u = dv + K y,
+        chi w = -diag(Z_w S),  Z_w = C [ (C^T A_w C) o G ] C^T,  A_w = -1/2 S o (w (+) w),  G_ij = (f_j - f_i)/(e_j - e_i),
+        K = dV/dq = gamma + 2 Gamma q_A  (secondorder.py:414-442, thirdorder.py:303-331),
+    so that the correction is Tr[Z_u dF/dR] - Tr[ZW_u dS/dR] - sum (K y)_mu P_mu,nu dS_mu,nu/dR + y . dV/dR|_q, i.e. the
+    standard gradient evaluated with P + Z_u, W + ZW_u, v_out + K y and the extra ES2 cross term (y_sh).  Diagonal of G:
+    Fermi-function derivative per spin channel with the Fermi-level shift projected out (wavefunction/filling.py:201-366).
+    Returns Z_u, ZW_u, y, K y.  Residual error: (v_out - v_in) . chi . (dv_K/dR - dv*/dR), second order in the residual
+    unless the trajectory's own derivative is unconverged (symmetry-breaking soft modes, e.g. the NO2 radical)."""
+    n = len(emo)
+    f = occ.sum(0)
+    fp_s = -(occ * (1.0 - occ)) / kt if kt >= 3e-7 else np.zeros_like(occ)
+    fp = fp_s.sum(0)
+    de = emo[None, :] - emo[:, None]
+    close = np.abs(de) <= 1e-9
+    den = np.where(close, 1.0, de)
+    G = np.where(close, 0.5 * (fp[None, :] + fp[:, None]), (f[None, :] - f[:, None]) / den)
+    fe = f * emo
+    Ge = np.where(close, 0.5 * ((f + emo * fp)[None, :] + (f + emo * fp)[:, None]), (fe[None, :] - fe[:, None]) / den)
+
+    def kernel(y):  # K y on orbital-resolved vectors
+        y_sh = np.bincount(m.ao_sh, weights=y, minlength=m.nsh)
+        y_at = np.bincount(m.sh_atom, weights=y_sh, minlength=m.nat)
+        return (gam @ y_sh + (2.0 * g3 * q_at * y_at)[m.sh_atom])[m.ao_sh]
+
+    def respond(w, want_w=False):
+        At = C.T @ (-0.5 * S * (w[:, None] + w[None, :])) @ C
+        Zt = At * G
+        d = np.diag(At).copy()
+        zd = np.zeros(n)
+        for s in range(2):
+            norm = fp_s[s].sum()
+            abar = (fp_s[s] * d).sum() / norm if abs(norm) > TINY else 0.0
+            zd += (d - abar) * fp_s[s]
+        np.fill_diagonal(Zt, zd)
+        Z = C @ Zt @ C.T
+        if not want_w:
+            return -np.einsum("ij,ij->i", Z, S)
+        ZWt = At * Ge
+        np.fill_diagonal(ZWt, d * f + zd * emo)
+        return Z, C @ ZWt @ C.T
+
+    z0 = respond(dv)
+    y = z0.copy()
+    mixer = Anderson(n, damp=0.5, damp_init=0.5, generations=5, diagonal_offset=0.01, soft_start=False)
+    for _ in range(maxiter):
+        y_new = z0 + respond(kernel(y))
+        if np.abs(y_new - y).max() < tol:
+            y = y_new
+            break
+        y = mixer.iter(y_new, y)
+    Ky = kernel(y)
+    Z, ZW = respond(dv + Ky, want_w=True)
+    return Z, ZW, y, Ky
+
+
+def _electronic_gradient(m: Mol, pos, S, dS, P, W, v, cn, dcfdr, q_sh, gam, parts: dict | None = None, y_sh=None):
     """calculators/types/analytical.py:63-222 + xtb/gfn1.py:185-408 + secondorder.py:873-926 + ncoord/utils.py:30-52."""
     f = _h0_shell_factors(m, pos, cn)
     a2s = m.ao_sh
@@ -911,7 +989,10 @@ def _electronic_gradient(m: Mol, pos, S, dS, P, W, v, cn, dcfdr, q_sh, gam, part
         parts["h0_dcn"] = g_cn.copy()  # = ncoord get_dcn(dcndr, dedcn)
     # ES2: E = 1/2 q g q, d gamma/dR_A = -gamma^3 (R_A-R_B) for off-atom shell pairs (gexp = 2)
     offsh = f["offatom"]
-    dg = np.where(offsh, -(gam**3), 0.0) * q_sh[:, None] * q_sh[None, :]
+    qq = q_sh[:, None] * q_sh[None, :]
+    if y_sh is not None:  # y . dV/dR at fixed charges (response of the SCF potential, _scf_response)
+        qq = qq + y_sh[:, None] * q_sh[None, :] + q_sh[:, None] * y_sh[None, :]
+    dg = np.where(offsh, -(gam**3), 0.0) * qq
     dg_at = np.zeros((m.nat, m.nat))
     np.add.at(dg_at, (m.sh_atom[:, None], m.sh_atom[None, :]), dg)
     g += (dg_at[:, :, None] * rij).sum(1)

@@ -21,9 +21,15 @@ from oracle import gfn1_oracle as O
 ROOT = Path(__file__).resolve().parent.parent
 E_TOL, Q_TOL, F_TOL = 1e-9, 1e-7, 1e-7
 CASES = {"default": {}, "sad": {"guess": "sad"}, "tight": {"x_atol": 1e-10, "x_atol_max": 1e-10}}
-# analytic converged-SCF gradient vs the reference's autograd-through-the-unrolled-SCF forces at dxtb's DEFAULT thresholds
-# (x_atol 1e-4 / 1e-5): first order in the SCF residual.  Measured max over the fixture molecules: 8.7e-6 Eh/bohr (LYS_xao).
-F_GAP_DEFAULT = 2e-5
+# Forces of the reference = autograd through the unrolled SCF.  At dxtb's DEFAULT thresholds (x_atol 1e-4 / 1e-5) the plain
+# converged-SCF analytic gradient differs from them by up to 8.7e-6 Eh/bohr (first order in the SCF residual); with the
+# first-order response of the residual (oracle _scf_response / CUDA scf_response) the gap is <= 3.1e-8 on every closed-shell
+# fixture molecule.  Exception: the NO2 radical, where the derivative of the reference's own SCF trajectory is not converged
+# in the symmetry-breaking charge mode (dv_K/dR differs from the converged response by 0.2, finite-difference checked); its
+# autograd forces differ from the finite difference of its own energy by 3.6e-7 there.
+F_GAP_DEFAULT = 1e-7
+F_GAP_UNCONVERGED_TRAJECTORY = {"NO2": 5e-6}
+F_GAP_NO_RESPONSE = 2e-5
 
 
 @pytest.fixture(scope="module")
@@ -63,8 +69,11 @@ def test_oracle_reproduces_dxtb(mols, runs, case, name):
         assert gap < F_TOL
     else:
         assert r.iterations == int(runs[f"{case}/{name}/iterations"])
-        assert gap < F_GAP_DEFAULT
-        print(f"{case}/{name}: analytic-vs-autograd force gap at default thresholds {gap:.2e} Eh/bohr")
+        assert gap < F_GAP_UNCONVERGED_TRAJECTORY.get(name, F_GAP_DEFAULT)
+        r0 = O.singlepoint(z, p, c, opts=dict(exclude=("disp",), grad_response=False, **CASES[case]), grad=True)
+        gap0 = np.abs(-r0.gradient - runs[f"{case}/{name}/forces"]).max()
+        assert gap0 < F_GAP_NO_RESPONSE
+        print(f"{case}/{name}: force gap to dxtb autograd at default thresholds {gap0:.2e} (converged-SCF formula) -> {gap:.2e} Eh/bohr")
 
 
 def test_oracle_d3_arithmetic_vs_dxtb_with_shim_table(mols, runs):
@@ -167,7 +176,7 @@ def test_cuda_path_reproduces_dxtb(mols, runs, case):
             assert gap < F_TOL, n
         else:
             assert int(it[i]) == int(runs[f"{case}/{n}/iterations"]), n
-            assert gap < F_GAP_DEFAULT, n
+            assert gap < F_GAP_UNCONVERGED_TRAJECTORY.get(n, F_GAP_DEFAULT), (n, gap)
 
 
 @pytest.mark.gpu
