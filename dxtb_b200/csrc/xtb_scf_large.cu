@@ -593,7 +593,7 @@ __global__ void kl_pack_add(double* __restrict__ dst, const double* __restrict__
 
 // ---- single-CTA vector stages (reuse the device functions of the batch kernel) ----------------------------------------
 enum Phase { PH_INIT = 0, PH_FERMI = 1, PH_POT = 2, PH_MIX = 3, PH_COPYV = 4, PH_EMIT = 5,
-             PH_RESP_INIT = 6, PH_RESP_Y0 = 7, PH_RESP_KY = 8, PH_RESP_STEP = 9, PH_RESP_FINAL = 10 };
+             PH_RESP_INIT = 6, PH_RESP_W0 = 7, PH_RESP_STEP = 8, PH_RESP_FINAL = 9 };
 
 __global__ void __launch_bounds__(NT, 1)
 kl_vec(int phase, const xtb_batch b, const xtb_scf_opts o, int m, const double* __restrict__ S, const double* __restrict__ H0,
@@ -656,8 +656,10 @@ kl_vec(int phase, const xtb_batch b, const xtb_scf_opts o, int m, const double* 
     emit_results(c, b, m, st->g, iters, q_orb, q_sh, q_at, v_orb, e_atom, fenergy, emo, occ, iterations, status);
   } else if (phase == PH_RESP_INIT) {
     // SCF response (xtb_scf_core.cuh:scf_response): dv -> eorb, f'_alpha -> srt, f'_beta -> jr; runs after PH_EMIT
+    double dvmax = 0.0;
     for (int k = threadIdx.x; k < n; k += NT) {
       c.eorb[k] = c.vnew[k] - c.v[k];
+      dvmax = fmax(dvmax, fabs(c.eorb[k]));
       double f[2];
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
@@ -670,12 +672,19 @@ kl_vec(int phase, const xtb_batch b, const xtb_scf_opts o, int m, const double* 
       c.srt[k] = -(f[0] * (1.0 - f[0])) / o.kt;
       c.jr[k] = -(f[1] * (1.0 - f[1])) / o.kt;
     }
-    if (threadIdx.x == 0) { st->mixer_step = 0; st->mixer_head = 0; st->converged = 0; }
-  } else if (phase == PH_RESP_Y0) {
-    for (int k = threadIdx.x; k < n; k += NT) c.v[k] = c.q[k];  // y = z0
-  } else if (phase == PH_RESP_KY) {
-    potential_lin(c, c.v, q_at + c.a0, c.n0);  // w = K y
+    dvmax = block_max(dvmax, c.red);
+    if (dvmax < kResponseTol) {  // nothing to add: hand the plain potential to the gradient
+      for (int k = threadIdx.x; k < n; k += NT) resp[c.o0 + k] = v_orb[c.o0 + k];
+      for (int k = threadIdx.x; k < c.ns; k += NT) resp[b.nao_tot + c.s0 + k] = 0.0;
+    }
+    if (threadIdx.x == 0) st->converged = dvmax < kResponseTol ? 1 : 0;
+  } else if (phase == PH_RESP_W0) {
+    potential_lin(c, c.q, q_at + c.a0, c.v);  // w0 = K z0
   } else if (phase == PH_RESP_STEP) {
+    potential_lin(c, c.n0, q_at + c.a0, c.vnew);  // g(w) = K y, y = z0 + chi w; leaves y_sh in c.qsh
+    Mixer mx;
+    mx.step = iters == 0 ? 0 : st->mixer_step;  // first response step: empty history
+    mx.head = iters == 0 ? 0 : st->mixer_head;
     double res = 0.0;
     for (int k = threadIdx.x; k < n; k += NT) res = fmax(res, fabs(c.vnew[k] - c.v[k]));
     res = block_max(res, c.red);
@@ -687,19 +696,15 @@ kl_vec(int phase, const xtb_batch b, const xtb_scf_opts o, int m, const double* 
       xtb_scf_opts o2 = o;
       o2.mixer = 0; o2.soft_start = 0; o2.damp = 0.5; o2.damp_init = 0.5; o2.diag_offset = 0.01;
       o2.x_atol = 0.0; o2.x_atol_max = 0.0;
-      Mixer mx;
-      mx.step = st->mixer_step;
-      mx.head = st->mixer_head;
-      __syncthreads();
       mix(c, mx, o2, c.cs);
-      if (threadIdx.x == 0) { st->mixer_step = mx.step; st->mixer_head = mx.head; }
+      if (threadIdx.x == 0) st->converged = 0;
     }
+    if (threadIdx.x == 0) { st->mixer_step = mx.step; st->mixer_head = mx.head; }
   } else if (phase == PH_RESP_FINAL) {
-    potential_lin(c, c.v, q_at + c.a0, c.n0);  // w = K y, qsh = y_sh
     for (int k = threadIdx.x; k < c.ns; k += NT) resp[b.nao_tot + c.s0 + k] = c.qsh[k];
     for (int k = threadIdx.x; k < n; k += NT) {
-      resp[c.o0 + k] = v_orb[c.o0 + k] + c.n0[k];
-      c.vnew[k] = c.eorb[k] + c.n0[k];  // u = dv + K y
+      resp[c.o0 + k] = v_orb[c.o0 + k] + c.v[k];
+      c.vnew[k] = c.eorb[k] + c.v[k];  // u = dv + K y
     }
   }
 }
@@ -907,22 +912,26 @@ extern "C" int xtb_scf_run_large(const xtb_batch* b, const xtb_scf_opts* o, int3
         kl_transpose<<<dim3(ne / 32, ne / 32), 256, 0, st>>>(C, X, ne);  // C restored
       };
       vec(PH_RESP_INIT, 0);
-      respond(eorb, 0);
-      kl_resp_charges<<<(n + 7) / 8, 256, 0, st>>>(A, Sm, nullptr, q, n, ne);  // z0 = chi dv
-      vec(PH_RESP_Y0, 0);
-      for (int it = 0; it < kResponseMaxIter; ++it) {
-        vec(PH_RESP_KY, 0);
-        respond(n0, 0);
-        kl_resp_charges<<<(n + 7) / 8, 256, 0, st>>>(A, Sm, q, vnew, n, ne);  // y_new = z0 + chi K y
-        vec(PH_RESP_STEP, 0);
-        if (int e = read_state()) return e;
-        if (hs.converged) break;
+      if (int e = read_state()) return e;
+      if (!hs.converged) {
+        respond(eorb, 0);
+        kl_resp_charges<<<(n + 7) / 8, 256, 0, st>>>(A, Sm, nullptr, q, n, ne);  // z0 = chi dv
+        vec(PH_RESP_W0, 0);
+        for (int it = 0; it < kResponseMaxIter; ++it) {
+          respond(v, 0);
+          kl_resp_charges<<<(n + 7) / 8, 256, 0, st>>>(A, Sm, q, n0, n, ne);  // y = z0 + chi w
+          vec(PH_RESP_STEP, it);
+          if (int e = read_state()) return e;
+          if (hs.converged) break;
+        }
+        vec(PH_RESP_FINAL, 0);
+        respond(vnew, 0);
+        kl_pack_add<<<ew_grid, 256, 0, st>>>(P + mat_off, A, n, ne, 1);  // P += Z_u
+        respond(vnew, 1);
+        kl_pack_add<<<ew_grid, 256, 0, st>>>(W + mat_off, A, n, ne, 0);  // W = ZW_u (+ the density-weighted part below)
+      } else {
+        cudaMemsetAsync(W + mat_off, 0, (size_t)n * n * 8, st);
       }
-      vec(PH_RESP_FINAL, 0);
-      respond(vnew, 0);
-      kl_pack_add<<<ew_grid, 256, 0, st>>>(P + mat_off, A, n, ne, 1);  // P += Z_u
-      respond(vnew, 1);
-      kl_pack_add<<<ew_grid, 256, 0, st>>>(W + mat_off, A, n, ne, 0);  // W = ZW_u (+ the density-weighted part below)
     }
     const int nocc = hs.nocc, kocc = (nocc + GK - 1) / GK * GK;
     if (kocc > 0) {

@@ -700,7 +700,7 @@ DEFAULT_OPTS = dict(
     damp_soft_start=True, x_atol=1e-4, x_atol_max=1e-5, fermi_etemp=300.0, fermi_maxiter=200, fermi_thresh=None,
     guess="eeq", exclude=(), int_cutoff=INT_CUTOFF,
     # gradient: add the first-order response of the not fully converged SCF state (see _scf_response)
-    grad_response=True, response_maxiter=12, response_tol=1e-10,
+    grad_response=True, response_maxiter=12, response_tol=1e-8,
 )
 
 
@@ -883,7 +883,7 @@ def singlepoint(numbers, positions, chrg: float = 0.0, opts: dict | None = None,
     return res
 
 
-def _scf_response(m: Mol, S, C, emo, occ, kt, gam, g3, q_at, dv, maxiter=12, tol=1e-10):
+def _scf_response(m: Mol, S, C, emo, occ, kt, gam, g3, q_at, dv, maxiter=12, tol=1e-8):
     """First-order correction of the analytic gradient for a NOT fully converged SCF state.
 
     The reference's forces are autograd through the unrolled SCF (calculators/types/autograd.py:80-201): the exact
@@ -935,18 +935,21 @@ def _scf_response(m: Mol, S, C, emo, occ, kt, gam, g3, q_at, dv, maxiter=12, tol
         np.fill_diagonal(ZWt, d * f + zd * emo)
         return Z, C @ ZWt @ C.T
 
+    if np.abs(dv).max() < tol:
+        return np.zeros((n, n)), np.zeros((n, n)), np.zeros(n), np.zeros(n)
+    # iterate in potential space, w = K y:  w = K (z0 + chi w); Anderson from an empty history
     z0 = respond(dv)
-    y = z0.copy()
+    w = kernel(z0)
+    y = z0
     mixer = Anderson(n, damp=0.5, damp_init=0.5, generations=5, diagonal_offset=0.01, soft_start=False)
     for _ in range(maxiter):
-        y_new = z0 + respond(kernel(y))
-        if np.abs(y_new - y).max() < tol:
-            y = y_new
+        y = z0 + respond(w)
+        w_new = kernel(y)
+        if np.abs(w_new - w).max() < tol:
+            w = w_new
             break
-        y = mixer.iter(y_new, y)
-    Ky = kernel(y)
-    Z, ZW = respond(dv + Ky, want_w=True)
-    return Z, ZW, y, Ky
+        w = mixer.iter(w_new, w)
+    return (*respond(dv + w, want_w=True), y, w)
 
 
 def _electronic_gradient(m: Mol, pos, S, dS, P, W, v, cn, dcfdr, q_sh, gam, parts: dict | None = None, y_sh=None):
