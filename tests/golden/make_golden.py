@@ -139,6 +139,13 @@ def main():
         if f"{k}_dcn" in gn.files:
             arrays[f"dcn/{name}"] = gn[f"{k}_dcn"]
             arrays[f"dedcn/{name}"] = gn[f"{k}_dedcn"]
+    # total GFN1-xTB gradients INCLUDING D3(BJ) (tblite, float32): test/test_singlepoint/refs/gfn1/grad.npz
+    gt = np.load(REF / "test/test_singlepoint/refs/gfn1/grad.npz")
+    tnames = {"h2": "H2", "h2o": "H2O", "no2": "NO2", "ch4": "CH4", "sih4": "SiH4", "lys_xao": "LYS_xao", "c60": "C60",
+              "vancoh2": "vancoh2", "ad7en": "AD7en+"}
+    for k, name in tnames.items():
+        if k in gt.files:
+            arrays[f"total_grad/{name}"] = gt[k]
     np.savez_compressed(OUT / "reference.npz", **arrays)
 
     def literals(path, key):

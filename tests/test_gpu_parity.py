@@ -611,3 +611,27 @@ def test_gradient_with_excluded_repulsion_and_halogen():
             r = O.singlepoint(z, xyz, opts={"exclude": tuple(excl)}, grad=True)
             assert abs(float(e[i]) - r.energy) < E_TOL
             assert np.abs(g[i, : len(z)].cpu().numpy() - r.gradient).max() < F_TOL
+
+
+def test_config2_full_batch_every_molecule_against_oracle_fixture():
+    """BASELINE config 2 at full size: ALL 1024 perturbed caffeine conformers of bench.py's workload -- energies 1e-9 Eh,
+    atomic charges 1e-7 e, identical SCF iteration counts for every molecule, forces of every 16th (1e-7 Eh/bohr), against
+    the oracle fixture tests/golden/config2_oracle.npz (tests/golden/make_config2_oracle.py)."""
+    from pathlib import Path
+
+    import bench
+    from dxtb_b200 import GFN1Calculator
+
+    dev = _dev()
+    ref = np.load(Path(__file__).resolve().parent / "golden" / "config2_oracle.npz")
+    wl = bench.Workload(2, 1, 1024)
+    pos = wl.positions(0, np.arange(1024))
+    assert abs(float(np.abs(pos).sum()) - float(ref["positions_checksum"])) < 1e-6  # same geometries as the fixture
+    calc = GFN1Calculator(torch.from_numpy(wl.numbers).to(dev), opts=NODISP, device=dev, dtype=torch.float64)
+    p = torch.from_numpy(pos).to(dev).requires_grad_(True)
+    e = calc.get_energy(p)
+    (g,) = torch.autograd.grad(e.sum(), p)
+    assert np.abs(e.detach().cpu().numpy() - ref["energy"]).max() < E_TOL
+    assert np.array_equal(calc.get_iterations().cpu().numpy(), ref["iterations"])
+    assert np.abs(calc.get_atomic_charges().cpu().numpy() - ref["q_at"]).max() < Q_TOL
+    assert np.abs(g[::16].cpu().numpy() - ref["gradient"]).max() < F_TOL
