@@ -285,6 +285,8 @@ class GFN1Calculator:
                 with np.load(d3_table) as f:
                     d3_table = {k: f[k] for k in ("cn", "c6", "r4r2")}
 
+        self._d3_table = d3_table
+        self._disp_calc = None  # calculator over the displaced copies of forces_numerical / hessian_numerical
         self.par = par if isinstance(par, GFN1Param) else gfn1_param()
         self.desc = BatchDescriptor(self.numbers, device, self.par, exclude=tuple(self._exclude), int_cutoff=float(o["int_cutoff"]),
                                     d3_table=d3_table)
@@ -569,6 +571,57 @@ class GFN1Calculator:
         wbo = onehot.mT @ t @ onehot
         wbo.diagonal(dim1=-2, dim2=-1).fill_(0.0)
         return wbo[0] if d.single else wbo
+
+    # ---- numerical derivatives (calculators/types/numerical.py:69-245) -------------------------------------------------
+    # The reference loops over the 3 nat coordinates and runs two single points per step.  Here all 6 nat displaced
+    # geometries of every molecule form ONE batch (one CTA per displaced copy), i.e. one launch sequence for the whole
+    # derivative.
+    def _displaced(self, positions: torch.Tensor, chrg: Any, spin: Any, step_size: float):
+        d = self.desc
+        pos = positions.detach()
+        pos = pos[None] if d.single else pos
+        nb, nat = pos.shape[0], pos.shape[1]
+        ncopy = 6 * nat
+        if getattr(self, "_disp_calc", None) is None:
+            numbers = self.numbers[None] if d.single else self.numbers
+            rep = numbers[:, None, :].expand(nb, ncopy, nat).reshape(nb * ncopy, nat).contiguous()
+            opts = {k: v for k, v in self.opts.items()}
+            kw = {"d3_reference": self._d3_table} if self._d3_table is not None else {}
+            self._disp_calc = GFN1Calculator(rep, self.par, opts=opts, device=self.device, dtype=self.dtype, **kw)
+        shift = torch.zeros((ncopy, nat, 3), dtype=self.dtype, device=self.device)
+        idx = torch.arange(3 * nat, device=self.device)
+        shift.view(2, 3 * nat, nat * 3)[0, idx, idx] = step_size
+        shift.view(2, 3 * nat, nat * 3)[1, idx, idx] = -step_size
+        # padding atoms are displaced too; they are not part of the molecule, so their rows/columns stay zero
+        geoms = (pos[:, None] + shift[None]).reshape(nb * ncopy, nat, 3)
+        chrg_t, spin_t = self._prep(positions, chrg, spin)
+        chrg_r = chrg_t.repeat_interleave(ncopy)
+        spin_r = None if spin_t is None else spin_t.repeat_interleave(ncopy)
+        return geoms, chrg_r, spin_r, nb, nat
+
+    def forces_numerical(self, positions: torch.Tensor, chrg: Any = 0, spin: Any = None, step_size: float = 1.0e-5, **_: Any) -> torch.Tensor:
+        """Central finite differences of the energy (numerical.py:69-152), all displaced geometries in one batch."""
+        geoms, chrg_r, spin_r, nb, nat = self._displaced(positions, chrg, spin, float(step_size))
+        with torch.no_grad():
+            e = self._disp_calc.energy(geoms, chrg_r, spin_r).reshape(nb, 2, nat, 3)
+        f = -(e[:, 0] - e[:, 1]) * (0.5 / float(step_size))
+        mask = (self.numbers > 0).reshape(nb, nat, 1)
+        f = f * mask
+        return f[0] if self.desc.single else f
+
+    def hessian_numerical(self, positions: torch.Tensor, chrg: Any = 0, spin: Any = None, step_size: float = 1.0e-5,
+                          matrix: bool = False, **_: Any) -> torch.Tensor:
+        """Central finite differences of the analytic gradient (numerical.py:154-245): (..., nat, 3, nat, 3), or
+        (..., 3 nat, 3 nat) with ``matrix=True``."""
+        geoms, chrg_r, spin_r, nb, nat = self._displaced(positions, chrg, spin, float(step_size))
+        g = -self._disp_calc.forces_analytical(geoms, chrg_r, spin_r).reshape(nb, 2, nat, 3, nat, 3)  # [.., i, j, a, x] = dE/dR_ax at R_ij +- h
+        h = (g[:, 0] - g[:, 1]) * (0.5 / float(step_size))
+        h = h.permute(0, 3, 4, 1, 2).contiguous()  # deriv[..., a, x, i, j]
+        real = (self.numbers > 0).reshape(nb, nat)
+        h = h * real[:, :, None, None, None] * real[:, None, None, :, None]
+        if matrix:
+            h = h.reshape(nb, 3 * nat, 3 * nat)
+        return h[0] if self.desc.single else h
 
     def reset(self) -> None:
         self.cache = {}

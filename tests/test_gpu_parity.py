@@ -635,3 +635,32 @@ def test_config2_full_batch_every_molecule_against_oracle_fixture():
     assert np.array_equal(calc.get_iterations().cpu().numpy(), ref["iterations"])
     assert np.abs(calc.get_atomic_charges().cpu().numpy() - ref["q_at"]).max() < Q_TOL
     assert np.abs(g[::16].cpu().numpy() - ref["gradient"]).max() < F_TOL
+
+
+def test_numerical_forces_and_hessian_batched(mols):
+    """forces_numerical / hessian_numerical (calculators/types/numerical.py:69-245) with all displaced geometries in one
+    batch: numerical forces == analytic forces, Hessian symmetric, equal to the finite difference of the oracle gradient."""
+    from dxtb_b200 import GFN1Calculator
+
+    dev = _dev()
+    numbers, pos, chrg = _pack(mols, ["H2O", "LiH"], dev)
+    opts = {"exclude": ["disp"], "x_atol": 1e-11, "x_atol_max": 1e-11}
+    calc = GFN1Calculator(numbers, opts=opts, device=dev, dtype=torch.float64)
+    fa = calc.forces_analytical(pos, chrg)
+    fn = calc.forces_numerical(pos, chrg, step_size=1e-4)
+    assert (fa - fn).abs().max() < 1e-7
+    h = calc.hessian_numerical(pos, chrg, step_size=1e-4)
+    assert h.shape == (2, 3, 3, 3, 3)
+    hm = calc.hessian_numerical(pos, chrg, step_size=1e-4, matrix=True)
+    assert (hm - hm.mT).abs().max() < 1e-6
+    assert (hm[1, 6:] == 0).all() and (hm[1, :, 6:] == 0).all()  # LiH is padded to 3 atoms
+    m = mols["H2O"]
+    z, p = np.array(m["numbers"]), np.array(m["positions"])
+    o = {"exclude": ("disp",), "x_atol": 1e-11, "x_atol_max": 1e-11}
+    pp, pm = p.copy(), p.copy()
+    pp[1, 2] += 1e-4
+    pm[1, 2] -= 1e-4
+    col = (O.singlepoint(z, pp, opts=o, grad=True).gradient - O.singlepoint(z, pm, opts=o, grad=True).gradient) / 2e-4
+    assert np.abs(h[0, :, :, 1, 2].cpu().numpy() - col).max() < 1e-6
+    single = GFN1Calculator(numbers[0], opts=opts, device=dev, dtype=torch.float64)
+    assert (single.hessian_numerical(pos[0], matrix=True) - hm[0]).abs().max() < 1e-5
