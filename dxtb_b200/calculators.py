@@ -297,7 +297,12 @@ class GFN1Calculator:
         self._use_smem_override: int | None = None  # tests: force the global-memory variant
         self._prefer_hybrid = os.environ.get("DXTB_B200_PREFER_HYBRID", "0") != "0"
         self._large_min_nao = int(os.environ.get("DXTB_B200_LARGE_MIN_NAO", "1000000"))
-        self._large_max_count = int(os.environ.get("DXTB_B200_LARGE_MAX_COUNT", "8"))
+        # up to this many molecules with nao >= 256 take the large-system path (several at a time, _run_large): measured on a
+        # config-5 shard with 15 vancoh2 (nao 550) 403 ms against 1502 ms with one CTA each (tools/config5_shard.py); the
+        # one-CTA kernel wins from ~45 such molecules on (1.2 s latency for up to 148 of them at once)
+        self._large_max_count = int(os.environ.get("DXTB_B200_LARGE_MAX_COUNT", "40"))
+        self._large_concurrency = int(os.environ.get("DXTB_B200_LARGE_CONCURRENCY", "6"))
+        self._large_streams: list = []
         self._buckets = self._make_buckets()
         self._streams: list = []
         self._pure_density = False  # get_density / get_bond_orders: P without the response density
@@ -325,8 +330,8 @@ class GFN1Calculator:
         # the one-CTA kernel no longer fit in shared memory, or from `large_min_nao` atomic orbitals on
         mode = np.where(need[:, 1] <= _SMEM_LIMIT, 1, np.where(need[:, 2] <= _SMEM_LIMIT, 2, 0))
         mode[(need[:, 0] > _SMEM_LIMIT) | (d.nao >= self._large_min_nao)] = 3
-        # a handful of big molecules cannot fill the device with one CTA each: the large-system path is ~10x faster per
-        # molecule (vancoh2: 0.10 s against 1.1 s latency), the one-CTA kernel only wins from ~a dozen such molecules on
+        # a few dozen big molecules cannot fill the device with one CTA each: the large-system path is ~10x faster per
+        # molecule (vancoh2: 0.10 s alone, ~0.027 s with 6 of them in flight, against 1.1 s latency in one CTA)
         big = (mode == 0) & (d.nao >= 256)
         if 0 < int(big.sum()) <= self._large_max_count:
             mode[big] = 3
@@ -372,24 +377,54 @@ class GFN1Calculator:
         return self._streams[:n]
 
     def _run_large(self, bk, o, ws, nel_ab, need_grad: bool, st: int, response: bool = False) -> None:
-        """Molecules of the large-system bucket, one after the other on the whole device (xtb_scf_run_large)."""
+        """Molecules of the large-system bucket (xtb_scf_run_large).  One molecule alone on the stream when it is big enough
+        to fill the device; otherwise up to DXTB_B200_LARGE_CONCURRENCY of them are driven concurrently by host threads on
+        their own streams and workspaces (a 550-AO molecule fills only 25..155 CTAs per launch; the C call releases the
+        GIL and synchronises only its own stream)."""
         d, lib = self.desc, _abi.lib()
-        nbytes = max(int(lib.xtb_scf_large_workspace_bytes(int(d.nao[m]), int(d.nsh[m]), int(d.nat[m]), int(o.generations)))
-                     for m in bk["mols"])
-        work = torch.empty(nbytes // 8 + 1, dtype=torch.float64, device=d.device)
+        mols = bk["mols"]
+        sizes = [int(lib.xtb_scf_large_workspace_bytes(int(d.nao[m]), int(d.nsh[m]), int(d.nat[m]), int(o.generations))) for m in mols]
+        nthreads = min(len(mols), self._large_concurrency) if max(int(d.nao[m]) for m in mols) <= 1536 else 1
+        main = torch.cuda.current_stream(d.device)
+
+        def run(m: int, work: torch.Tensor, stream_ptr: int, opts) -> int:
+            return lib.xtb_scf_run_large(
+                d.ptr, _abi.C.addressof(opts), int(m), int(d.nao[m]), int(d.nsh[m]), int(d.nat[m]), ws.S.data_ptr(), ws.H0.data_ptr(),
+                ws.gamma.data_ptr(), nel_ab.data_ptr(), ws.q0_at.data_ptr(), work.data_ptr(), ws.q_orb.data_ptr(),
+                ws.q_sh.data_ptr(), ws.q_at.data_ptr(), ws.v_orb.data_ptr(), ws.e_atom.data_ptr(), ws.fenergy.data_ptr(),
+                ws.emo.data_ptr(), ws.occ.data_ptr(), ws.iterations.data_ptr(), ws.status.data_ptr(),
+                ws.P.data_ptr() if need_grad else None, ws.W.data_ptr() if need_grad else None,
+                ws.resp.data_ptr() if response else None, int(d.mat_off[m]), stream_ptr)
+
         o.mol_list, o.list_len = None, 0
-        for m in bk["mols"]:
-            _abi.check(
-                lib.xtb_scf_run_large(
-                    d.ptr, _abi.C.addressof(o), int(m), int(d.nao[m]), int(d.nsh[m]), int(d.nat[m]), ws.S.data_ptr(), ws.H0.data_ptr(),
-                    ws.gamma.data_ptr(), nel_ab.data_ptr(), ws.q0_at.data_ptr(), work.data_ptr(), ws.q_orb.data_ptr(),
-                    ws.q_sh.data_ptr(), ws.q_at.data_ptr(), ws.v_orb.data_ptr(), ws.e_atom.data_ptr(), ws.fenergy.data_ptr(),
-                    ws.emo.data_ptr(), ws.occ.data_ptr(), ws.iterations.data_ptr(), ws.status.data_ptr(),
-                    ws.P.data_ptr() if need_grad else None, ws.W.data_ptr() if need_grad else None,
-                    ws.resp.data_ptr() if response else None, int(d.mat_off[m]), st,
-                ),
-                "xtb_scf_run_large",
-            )
+        if nthreads <= 1:
+            work = torch.empty(max(sizes) // 8 + 1, dtype=torch.float64, device=d.device)
+            for m in mols:
+                _abi.check(run(m, work, st, o), "xtb_scf_run_large")
+            return
+        from concurrent.futures import ThreadPoolExecutor
+
+        if len(self._large_streams) < nthreads:
+            self._large_streams += [torch.cuda.Stream(d.device) for _ in range(nthreads - len(self._large_streams))]
+        works = [torch.empty(max(sizes) // 8 + 1, dtype=torch.float64, device=d.device) for _ in range(nthreads)]
+        fork = torch.cuda.Event()
+        fork.record(main)
+        def worker(t: int) -> int:
+            torch.cuda.set_device(d.device)  # new host threads start on device 0
+            stream = self._large_streams[t]
+            stream.wait_event(fork)
+            opts = type(o).from_buffer_copy(o)  # ctypes structure: private copy per thread
+            rc = 0
+            for m in mols[t::nthreads]:
+                rc = rc or run(m, works[t], stream.cuda_stream, opts)
+            return rc
+
+        with ThreadPoolExecutor(nthreads) as pool:
+            rcs = list(pool.map(worker, range(nthreads)))
+        for t in range(nthreads):
+            main.wait_stream(self._large_streams[t])
+        for rc in rcs:
+            _abi.check(rc, "xtb_scf_run_large")
 
     @property
     def _variants(self) -> list[int]:

@@ -14,6 +14,9 @@
 // eigendecomposition S = U s U^T (any S-orthonormal basis gives the same SCF trajectory up to round-off).
 #include "xtb_scf_core.cuh"
 
+#include <mutex>
+#include <vector>
+
 namespace {
 
 constexpr int OB = 32;       // outer Jacobi block
@@ -709,6 +712,32 @@ kl_vec(int phase, const xtb_batch b, const xtb_scf_opts o, int m, const double* 
   }
 }
 
+struct SideStream {
+  int dev;
+  cudaStream_t main, side;
+  cudaEvent_t ev_a, ev_s;
+};
+
+// thread-safe lookup / creation of the helper stream of (device, caller stream)
+SideStream* side_stream_for(int dev, cudaStream_t main) {
+  static std::mutex mtx;
+  static std::vector<SideStream*> all;
+  std::lock_guard<std::mutex> lock(mtx);
+  for (SideStream* s : all)
+    if (s->dev == dev && s->main == main) return s;
+  SideStream* s = new SideStream{dev, main, nullptr, nullptr, nullptr};
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  if (cudaStreamCreateWithPriority(&s->side, cudaStreamNonBlocking, hi) != cudaSuccess ||
+      cudaEventCreateWithFlags(&s->ev_a, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&s->ev_s, cudaEventDisableTiming) != cudaSuccess) {
+    delete s;
+    return nullptr;
+  }
+  all.push_back(s);
+  return s;
+}
+
 template <typename F>
 int set_smem(F f, int bytes) {
   cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -751,6 +780,8 @@ extern "C" int xtb_scf_run_large(const xtb_batch* b, const xtb_scf_opts* o, int3
 
   static bool configured[64] = {};  // function attributes are per device
   {
+    static std::mutex cfg_mtx;
+    std::lock_guard<std::mutex> lock(cfg_mtx);
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) return -5;
@@ -768,22 +799,15 @@ extern "C" int xtb_scf_run_large(const xtb_batch* b, const xtb_scf_opts* o, int3
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   }
-  // second stream (highest priority) and events for the sub-problem / pass overlap of the Jacobi rounds, per device
-  constexpr int kMaxDev = 64;
-  static cudaStream_t side_s[kMaxDev] = {};
-  static cudaEvent_t ev_a_s[kMaxDev] = {}, ev_s_s[kMaxDev] = {};
+  // second stream (highest priority) and events for the sub-problem / pass overlap of the Jacobi rounds: one set per
+  // (device, caller stream), so that several large molecules can be driven concurrently from different host threads on
+  // different streams (a 550-AO molecule fills only 25..155 CTAs per launch)
   int cur_dev = 0;
   cudaGetDevice(&cur_dev);
-  if (cur_dev < 0 || cur_dev >= kMaxDev) return -5;
-  if (!side_s[cur_dev]) {
-    int lo = 0, hi = 0;
-    cudaDeviceGetStreamPriorityRange(&lo, &hi);
-    if (cudaStreamCreateWithPriority(&side_s[cur_dev], cudaStreamNonBlocking, hi) != cudaSuccess) return -5;
-    if (cudaEventCreateWithFlags(&ev_a_s[cur_dev], cudaEventDisableTiming) != cudaSuccess) return -5;
-    if (cudaEventCreateWithFlags(&ev_s_s[cur_dev], cudaEventDisableTiming) != cudaSuccess) return -5;
-  }
-  cudaStream_t side = side_s[cur_dev];
-  cudaEvent_t ev_a = ev_a_s[cur_dev], ev_s = ev_s_s[cur_dev];
+  SideStream* ss = side_stream_for(cur_dev, st);
+  if (!ss) return -5;
+  cudaStream_t side = ss->side;
+  cudaEvent_t ev_a = ss->ev_a, ev_s = ss->ev_s;
   const int ew_grid = 4 * n_sm;  // elementwise kernels: grid-stride
   LargeState hs;
   auto read_state = [&]() -> int {

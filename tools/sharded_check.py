@@ -6,8 +6,10 @@
 Every rank computes its shard of ONE fixed batch (config-3-like drug-like conformers with contiguous shards, and a ragged
 config-5-like batch with cost-balanced shards), the per-molecule energies / forces / iteration counts are gathered with
 dxtb_b200.parallel, and rank 0 recomputes the whole batch on its own GPU and compares: bit-for-bit for the uniform batch
-(every molecule runs the same kernel variant regardless of the sharding), 1e-10 for the ragged one (the size buckets, and
-with them the kernel variant of a molecule, depend on what else is in the shard).  Prints one JSON line; exit code 1 on mismatch.
+(every molecule runs the same kernel variant regardless of the sharding); for the ragged one the parity tolerances
+(1e-9 Eh, 1e-7 Eh/bohr, equal iteration counts), because the size buckets -- and with them the kernel variant of a molecule,
+e.g. one-CTA kernel vs large-system path for the few 550-AO molecules of a shard -- depend on what else is in the shard
+(different eigensolver round-off, response solver stopped at 1e-8).  Prints one JSON line; exit code 1 on mismatch.
 """
 import json
 import os
@@ -42,7 +44,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     report, ok = {}, True
-    for config, n, tol in ((3, 64 * world, 0.0), (5, 48 * world, 1e-10)):
+    for config, n, tol, ftol in ((3, 64 * world, 0.0, 0.0), (5, 48 * world, 1e-9, 1e-7)):
         wl = bench.Workload(config, world, n)
         parts = [wl.shard(r) for r in range(world)]
         e, g, it = single_points(wl, parts[rank], dev)
@@ -54,8 +56,8 @@ def main():
             de, dg = float((e_all - e1).abs().max()), float((g_all - g1).abs().max())
             same_it = bool(torch.equal(it_all, it1))
             report[f"config{config}"] = {"n": wl.n_total, "world": world, "max_abs_dE": de, "max_abs_dF": dg, "iterations_equal": same_it,
-                                         "tolerance": tol, "shard_sizes": [len(p) for p in parts]}
-            ok = ok and de <= tol and dg <= tol and same_it
+                                         "tolerance": [tol, ftol], "shard_sizes": [len(p) for p in parts]}
+            ok = ok and de <= tol and dg <= ftol and same_it
     if rank == 0:
         report["ok"] = ok
         print(json.dumps(report), flush=True)
