@@ -664,3 +664,26 @@ def test_numerical_forces_and_hessian_batched(mols):
     assert np.abs(h[0, :, :, 1, 2].cpu().numpy() - col).max() < 1e-6
     single = GFN1Calculator(numbers[0], opts=opts, device=dev, dtype=torch.float64)
     assert (single.hessian_numerical(pos[0], matrix=True) - hm[0]).abs().max() < 1e-5
+
+
+def test_large_system_path_concurrent_molecules(mols, monkeypatch):
+    """Several medium-large molecules in flight on the large-system path (host threads, own streams and workspaces):
+    bit-identical to driving them one after the other."""
+    from dxtb_b200 import GFN1Calculator
+
+    dev = _dev()
+    numbers, pos, chrg = _pack(mols, ["vancoh2", "H2O", "C60", "vancoh2", "caffeine", "vancoh2", "C60"], dev)
+    pos = pos + 0.01 * torch.arange(7, device=dev, dtype=torch.float64)[:, None, None] * (numbers > 0)[..., None]
+    monkeypatch.setenv("DXTB_B200_LARGE_MIN_NAO", "200")  # C60 (nao 240) and vancoh2 (550) take the large path
+    out = []
+    for conc in ("1", "3"):
+        monkeypatch.setenv("DXTB_B200_LARGE_CONCURRENCY", conc)
+        calc = GFN1Calculator(numbers, opts=NODISP, device=dev, dtype=torch.float64)
+        assert 3 in calc._variants
+        p = pos.clone().requires_grad_(True)
+        e = calc.get_energy(p, chrg)
+        (g,) = torch.autograd.grad(e.sum(), p)
+        out.append((e.detach().clone(), g.clone(), calc.get_iterations().clone()))
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1]) and torch.equal(out[0][2], out[1][2])
+    r = O.singlepoint(np.array(mols["C60"]["numbers"]), pos[2, :60].cpu().numpy(), opts={"exclude": ("disp",)}, grad=True)
+    assert abs(float(out[1][0][2]) - r.energy) < E_TOL and np.abs(out[1][1][2, :60].cpu().numpy() - r.gradient).max() < F_TOL
