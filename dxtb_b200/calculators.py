@@ -109,11 +109,13 @@ class _SinglePoint(torch.autograd.Function):
         st = _stream_ptr(d.device)
         need_grad = bool(ctx.needs_input_grad[0])
         pos = d.gather_atoms(positions.detach())
+        response = need_grad and bool(calc.opts["grad_response"]) and not calc._pure_density and int(calc.opts["maxiter"]) > 0
         o = calc._scf_struct(want_density=need_grad)
+        if response:
+            o.want_density = 2  # sizes the workspace for the response solver
         need_global = calc._use_smem_override in (0, 2) or any(bk["use_smem"] in (0, 2) for bk in calc._buckets)
         ws = _Workspace(d, need_grad, o, need_global)
         excl = calc._exclude
-        response = need_grad and bool(calc.opts["grad_response"]) and not calc._pure_density and int(calc.opts["maxiter"]) > 0
         if response:
             ws.resp = torch.zeros(d.nao_tot + d.nsh_tot, dtype=torch.float64, device=d.device)
 

@@ -186,12 +186,16 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
   p += ((p - sm) & 1);
   c.smem = MODE == 1;
   const size_t msz = (size_t)ne * ld;
+  // workspace: [Anderson history][2 response matrices per molecule if want_density == 2][3 matrices per molecule, MODE != 1]
+  const size_t mat_bound = (size_t)b.mat_total + 34 * (size_t)b.nao_tot + 285 * (size_t)b.nb;
+  const size_t resp_region = o.want_density == 2 ? 2 * mat_bound : 0;
   if (MODE == 1) {
     const size_t nex = (size_t)((lnao + 15) & ~15);
     const size_t mszx = nex * (nex + 4);
     c.C = p; c.A = p + mszx; c.X = p + 2 * mszx;
   } else {
-    double* wm = work + (size_t)(o.generations + 1) * 2 * b.nao_tot + 3 * ((size_t)b.mat_off[m] + 34 * (size_t)c.o0 + 285 * (size_t)m);  // sum of (n+15)(n+19) bounds ne*ld
+    double* wm = work + (size_t)(o.generations + 1) * 2 * b.nao_tot + resp_region +
+                 3 * ((size_t)b.mat_off[m] + 34 * (size_t)c.o0 + 285 * (size_t)m);  // sum of (n+15)(n+19) bounds ne*ld
     c.C = wm; c.A = wm + msz; c.X = wm + 2 * msz;
     if (MODE == 2) c.A = p;  // hybrid: the Fock / A / density buffer (sub-problem gathers, two-sided updates) in shared memory
   }
@@ -278,8 +282,12 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
     __syncthreads();
     gemm_tn<MODE == 1, MODE != 0>(ne, nocc, c.X, c.A, ld, Wm, n, n);
     // first-order response of the SCF residual (forces of the reference = autograd through the unrolled SCF)
-    if (resp != nullptr && o.maxiter > 0)
-      scf_response<MODE>(c, o, v_orb + c.o0, q_at + c.a0, Pm, Wm, resp + c.o0, resp + b.nao_tot + c.s0, sm_theta);
+    if (resp != nullptr && o.maxiter > 0 && o.want_density == 2) {
+      RespBuf rb;
+      rb.SC = work + (size_t)(o.generations + 1) * 2 * b.nao_tot + 2 * ((size_t)b.mat_off[m] + 34 * (size_t)c.o0 + 285 * (size_t)m);
+      rb.G2 = rb.SC + msz;
+      scf_response<MODE>(c, o, rb, v_orb + c.o0, q_at + c.a0, Pm, Wm, resp + c.o0, resp + b.nao_tot + c.s0, sm_theta);
+    }
   }
 }
 
@@ -354,6 +362,7 @@ extern "C" int64_t xtb_scf_smem_bytes(const xtb_batch* b) {
 extern "C" int64_t xtb_scf_workspace_bytes(const xtb_batch* b, const xtb_scf_opts* o) {
   if (!b || !o) return -1;
   int64_t d = (int64_t)(o->generations + 1) * 2 * b->nao_tot;
+  if (o->want_density == 2) d += 2 * (b->mat_total + 34 * (int64_t)b->nao_tot + 285 * (int64_t)b->nb);  // SCF response: S C and a GEMM output
   if (o->use_smem != 1) {
     // 3 matrices of at most (n+15)(n+19) per molecule: 3 (sum n^2 + 34 sum n + 285 nb)
     d += 3 * (b->mat_total + 34 * (int64_t)b->nao_tot + 285 * (int64_t)b->nb);
@@ -369,6 +378,7 @@ extern "C" int xtb_scf_run(const xtb_batch* b, const xtb_scf_opts* o, const doub
       !emo || !occ || !iterations || !status)
     return -1;
   if (o->want_density && (!P || !W)) return -1;
+  if (resp && o->want_density != 2) return -1;  // the workspace must have been sized for the response (want_density = 2)
   if (o->generations > 5 || o->generations < 1) return -3;
   if (o->use_smem < 0 || o->use_smem > 2) return -4;
   if (b->nb == 0) return 0;

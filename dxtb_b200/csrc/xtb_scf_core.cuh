@@ -59,9 +59,10 @@ XTB_DEV void dmma884(double& d0, double& d1, double a, double b) {
 // Out[i][j] = sum_{k<K} L[k*ld+i] * R[k*ld+j], i,j < ne (ne % 16 == 0), on the fp64 tensor cores:
 // one warp per 16x16 output tile (2x2 DMMA tiles), K consumed 4 at a time.  With ld == 4 (mod 16) both
 // fragment loads (4 consecutive k rows x 8 consecutive columns per half-warp) are bank-conflict free.
-template <bool LS, bool RS>
+// WK: row k of L is scaled by wk[k] (weighted inner product over k).
+template <bool LS, bool RS, bool WK = false>
 __device__ void gemm_tn(int ne, int K, const double* __restrict__ L, const double* __restrict__ R, int ld, double* __restrict__ Out,
-                        int ldo, int nout) {
+                        int ldo, int nout, const double* __restrict__ wk = nullptr) {
   if (LS) XTB_ASSUME_SHARED(L);
   if (RS) XTB_ASSUME_SHARED(R);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -79,8 +80,13 @@ __device__ void gemm_tn(int ne, int K, const double* __restrict__ L, const doubl
       const bool kv = k0 + tg < K;
       const double* lr = L + (size_t)(k0 + tg) * ld + i0 + g;
       const double* rr = R + (size_t)(k0 + tg) * ld + j0 + g;
-      const double a0 = kv ? lr[0] : 0.0, a1 = kv ? lr[8] : 0.0;
+      double a0 = kv ? lr[0] : 0.0, a1 = kv ? lr[8] : 0.0;
       const double b0 = kv ? rr[0] : 0.0, b1 = kv ? rr[8] : 0.0;
+      if (WK) {
+        const double wv = kv ? wk[k0 + tg] : 0.0;
+        a0 *= wv;
+        a1 *= wv;
+      }
       dmma884(d[0][0][0], d[0][0][1], a0, b0);
       dmma884(d[0][1][0], d[0][1][1], a0, b1);
       dmma884(d[1][0][0], d[1][0][1], a1, b0);
@@ -104,7 +110,10 @@ __device__ void gemm_tn(int ne, int K, const double* __restrict__ L, const doubl
 #define XTB_DEFER_NBP_MAX 16
 #endif
 constexpr int XTB_DEFER_NBP = XTB_DEFER_NBP_MAX;  // up to this many block pairs (nao <= 256) the accumulated rotations are double buffered
-constexpr int NGRP = 16;  // upper bound of sub-problems solved concurrently (one warp each with its own 16x16 copy; Ctx::ng)
+#ifndef XTB_NGRP
+#define XTB_NGRP 16
+#endif
+constexpr int NGRP = XTB_NGRP;  // upper bound of sub-problems solved concurrently (one warp each with its own 16x16 copy; Ctx::ng)
 
 #ifndef XTB_JACOBI_SMALL_SIN
 #define XTB_JACOBI_SMALL_SIN 0.1  // sub-problems whose rotations all have |sin| below this take the small-angle shortcut
@@ -859,23 +868,28 @@ __device__ void potential_lin(Ctx& c, const double* __restrict__ y, const double
   __syncthreads();
 }
 
-// Response density of the Fock perturbation A_w = -1/2 S o (w (+) w):  A <- Z_w (WMAT = false) or ZW_w (WMAT = true).
-// fp0 / fp1: Fermi-function derivatives of the two spin channels.  C is used as scratch and restored.
+// Buffers of the response solver: C (eigenvectors, untouched), X = C^T (set up once), A (work), and two matrices in the
+// global workspace: SC = S C (set up once) and G2 (GEMM output).  With A_w = -1/2 (diag(w) S + S diag(w)):
+//     At = C^T A_w C = -1/2 (M + M^T),   M = C^T diag(w) (S C)                       -- ONE weighted GEMM
+//     chi w = -diag(Z S) = -rowdot(C Zt, S C)                                         -- ONE GEMM (X^T-contraction) + row dots
+// i.e. 2 GEMMs per application of chi instead of 4 GEMMs + 2 transposes; the full Z / ZW matrices (2 more GEMMs each) are
+// only formed once at the end.
+struct RespBuf {
+  double* SC;  // [mu][q]  (global workspace)
+  double* G2;  // GEMM output (global workspace)
+};
+
+// A <- Zt (WMAT = false) or ZWt (WMAT = true) of the perturbation w, in the eigenvector basis
 template <int MODE, bool WMAT>
-__device__ void response_density(Ctx& c, const double* __restrict__ w, const double* __restrict__ fp0, const double* __restrict__ fp1) {
+__device__ void response_zt(Ctx& c, const RespBuf& rb, const double* __restrict__ w, const double* __restrict__ fp0,
+                            const double* __restrict__ fp1) {
   const int n = c.n, ne = c.ne, ld = c.ld;
   constexpr bool AS = MODE != 0, CS = MODE == 1;
-  for (int t = threadIdx.x; t < ne * ld; t += NT) {
-    const int i = t / ld, j = t - i * ld;
-    c.A[t] = (i < n && j < n) ? -0.5 * c.S[(size_t)i * n + j] * (w[i] + w[j]) : 0.0;
-  }
-  __syncthreads();
-  gemm_tn<AS, CS>(ne, ne, c.A, c.C, ld, c.X, ld, ne);  // X = A_w C
-  gemm_tn<CS, CS>(ne, ne, c.C, c.X, ld, c.A, ld, ne);  // A = C^T A_w C
-  // Fermi-level shift per spin channel: abar_s = sum_k f'_s(k) A_kk / sum_k f'_s(k)
+  gemm_tn<CS, false, true>(ne, n, c.C, rb.SC, ld, c.A, ld, ne, w);  // M[i][j] = sum_{mu < n} w_mu C[mu][i] SC[mu][j]
+  // Fermi-level shift per spin channel: abar_s = sum_k f'_s(k) At_kk / sum_k f'_s(k),  At_kk = -M_kk
   double s0 = 0.0, s1 = 0.0, n0 = 0.0, n1 = 0.0;
   for (int k = threadIdx.x; k < n; k += NT) {
-    const double d = c.A[(size_t)k * ld + k];
+    const double d = -c.A[(size_t)k * ld + k];
     s0 += fp0[k] * d; n0 += fp0[k];
     s1 += fp1[k] * d; n1 += fp1[k];
   }
@@ -891,11 +905,11 @@ __device__ void response_density(Ctx& c, const double* __restrict__ w, const dou
       const double ei = c.eps[i], ej = c.eps[j], fi = c.focc[i], fj = c.focc[j];
       const double fpi = fp0[i] + fp1[i], fpj = fp0[j] + fp1[j];
       if (i == j) {
-        const double d = c.A[(size_t)i * ld + i];
+        const double d = -c.A[(size_t)i * ld + i];
         const double zd = (d - ab0) * fp0[i] + (d - ab1) * fp1[i];
         val = WMAT ? d * fi + zd * ei : zd;
       } else {
-        const double a = 0.5 * (c.A[(size_t)i * ld + j] + c.A[(size_t)j * ld + i]);
+        const double a = -0.5 * (c.A[(size_t)i * ld + j] + c.A[(size_t)j * ld + i]);
         const double de = ej - ei;
         const bool close = fabs(de) <= 1e-9;
         double gf;
@@ -907,46 +921,52 @@ __device__ void response_density(Ctx& c, const double* __restrict__ w, const dou
     c.A[(size_t)i * ld + j] = val;
     c.A[(size_t)j * ld + i] = val;
   }
-  // back-transformation Z = C Zt C^T with three buffers: X = C^T, C <- Zt X (= T), A = X^T T, C restored from X
-  for (int t = threadIdx.x; t < ne * ne; t += NT) {
-    const int k = t / ne, i = t - k * ne;
-    c.X[(size_t)k * ld + i] = c.C[(size_t)i * ld + k];
-  }
   __syncthreads();
-  gemm_tn<AS, CS>(ne, ne, c.A, c.X, ld, c.C, ld, ne);  // T[i][nu] = sum_j Zt[j][i] C^T[j][nu]
-  gemm_tn<CS, CS>(ne, ne, c.X, c.C, ld, c.A, ld, ne);  // Z[mu][nu] = sum_i C^T[i][mu] T[i][nu]
-  for (int t = threadIdx.x; t < ne * ne; t += NT) {
-    const int i = t / ne, k = t - i * ne;
-    c.C[(size_t)i * ld + k] = c.X[(size_t)k * ld + i];
-  }
-  __syncthreads();
+  (void)AS;
 }
 
-// out[mu] = add[mu] - sum_nu Z[mu][nu] S[mu][nu]  (Z in the A buffer): the response charges chi w (+ add)
-__device__ void response_charges(Ctx& c, const double* __restrict__ add, double* __restrict__ out) {
-  const int n = c.n, ld = c.ld;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int mu = w; mu < n; mu += NT / 32) {
-    const double* zr = c.A + (size_t)mu * ld;
-    const double* sr = c.S + (size_t)mu * n;
+// out[mu] = add[mu] + chi w = add[mu] - sum_q (C Zt)[mu][q] SC[mu][q]
+template <int MODE>
+__device__ void response_charges(Ctx& c, const RespBuf& rb, const double* __restrict__ w, const double* __restrict__ fp0,
+                                 const double* __restrict__ fp1, const double* __restrict__ add, double* __restrict__ out) {
+  const int n = c.n, ne = c.ne, ld = c.ld;
+  constexpr bool AS = MODE != 0, CS = MODE == 1;
+  response_zt<MODE, false>(c, rb, w, fp0, fp1);
+  gemm_tn<CS, AS>(ne, ne, c.X, c.A, ld, rb.G2, ld, ne);  // G2[mu][q] = sum_p C^T[p][mu] Zt[p][q]
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  for (int mu = wp; mu < n; mu += NT / 32) {
+    const double* gr = rb.G2 + (size_t)mu * ld;
+    const double* sr = rb.SC + (size_t)mu * ld;
     double acc = 0.0;
-    for (int nu = lane; nu < n; nu += 32) acc = fma(zr[nu], sr[nu], acc);
+    for (int q = lane; q < n; q += 32) acc = fma(gr[q], sr[q], acc);
     acc = warp_sum(acc);
     if (lane == 0) out[mu] = (add ? add[mu] : 0.0) - acc;
   }
   __syncthreads();
 }
 
+// A <- Z_w (or ZW_w) in the AO basis: Z = C Zt C^T
+template <int MODE, bool WMAT>
+__device__ void response_density(Ctx& c, const RespBuf& rb, const double* __restrict__ w, const double* __restrict__ fp0,
+                                 const double* __restrict__ fp1) {
+  const int ne = c.ne, ld = c.ld;
+  constexpr bool AS = MODE != 0, CS = MODE == 1;
+  response_zt<MODE, WMAT>(c, rb, w, fp0, fp1);
+  gemm_tn<AS, CS>(ne, ne, c.A, c.X, ld, rb.G2, ld, ne);     // G2[q][mu] = sum_p Zt[p][q] C^T[p][mu]
+  gemm_tn<false, CS>(ne, ne, rb.G2, c.X, ld, c.A, ld, ne);  // Z[mu][nu] = sum_q G2[q][mu] C^T[q][nu]
+}
+
+// Runs after the final solve and after P, W were written: adds Z_u, ZW_u to Pm, Wm and writes v_out + K y / y_sh.
+// Vector scratch (all free after emit_results): dv -> eorb, z0 -> q, w -> v, g(w) -> vnew, y -> n0, f'_0 -> srt, f'_1 -> cs.
 // The coupled-perturbed equations are iterated in potential space, w = K y:  w = g(w) = K (z0 + chi w), Anderson-accelerated
 // from an empty history (re-using the SCF's own Anderson history as search directions was measured SLOWER: 12 instead of 8
 // applications of chi to 1e-9, its differences carry the non-linearity of the early SCF iterations).
-// Runs after the final solve and after P, W were written: adds Z_u, ZW_u to Pm, Wm and writes v_out + K y / y_sh.
-// Vector scratch (all free after emit_results): dv -> eorb, z0 -> q, w -> v, g(w) -> vnew, y -> n0, f'_0 -> srt, f'_1 -> cs.
 template <int MODE>
-__device__ void scf_response(Ctx& c, const xtb_scf_opts& o, const double* __restrict__ v_out_g,
+__device__ void scf_response(Ctx& c, const xtb_scf_opts& o, const RespBuf& rb, const double* __restrict__ v_out_g,
                              const double* __restrict__ qat_final, double* __restrict__ Pm, double* __restrict__ Wm,
                              double* __restrict__ v_grad, double* __restrict__ y_sh, double* sm_theta) {
-  const int n = c.n, ld = c.ld;
+  const int n = c.n, ne = c.ne, ld = c.ld;
+  constexpr bool AS = MODE != 0, CS = MODE == 1;
   double* dv = c.eorb; double* z0 = c.q; double* y = c.n0; double* fp0 = c.srt; double* fp1 = c.cs;
   double dvmax = 0.0;
   for (int k = threadIdx.x; k < n; k += NT) {
@@ -975,8 +995,19 @@ __device__ void scf_response(Ctx& c, const xtb_scf_opts& o, const double* __rest
   const long long tr0 = clock64();
   int nit = 0;
 #endif
-  response_density<MODE, false>(c, dv, fp0, fp1);
-  response_charges(c, nullptr, z0);
+  // set-up: SC = S C (global), X = C^T
+  for (int t = threadIdx.x; t < ne * ld; t += NT) {
+    const int i = t / ld, j = t - i * ld;
+    c.A[t] = (i < n && j < n) ? c.S[(size_t)i * n + j] : 0.0;
+  }
+  for (int t = threadIdx.x; t < ne * ne; t += NT) {
+    const int k = t / ne, i = t - k * ne;
+    c.X[(size_t)k * ld + i] = c.C[(size_t)i * ld + k];
+  }
+  __syncthreads();
+  gemm_tn<AS, CS>(ne, ne, c.A, c.C, ld, rb.SC, ld, ne);  // SC[mu][q] = sum_nu S[nu][mu] C[nu][q]
+
+  response_charges<MODE>(c, rb, dv, fp0, fp1, nullptr, z0);
   potential_lin(c, z0, qat_final, c.v);  // w0 = K z0
   xtb_scf_opts o2 = o;
   o2.mixer = 0; o2.soft_start = 0; o2.damp = 0.5; o2.damp_init = 0.5; o2.diag_offset = 0.01;
@@ -984,16 +1015,15 @@ __device__ void scf_response(Ctx& c, const xtb_scf_opts& o, const double* __rest
   Mixer mx;
   mx.step = 0; mx.head = 0;
   for (int it = 0; it < kResponseMaxIter; ++it) {
-    response_density<MODE, false>(c, c.v, fp0, fp1);
-    response_charges(c, z0, y);                 // y = z0 + chi w
-    potential_lin(c, y, qat_final, c.vnew);     // g(w) = K y; leaves y_sh in c.qsh
+    response_charges<MODE>(c, rb, c.v, fp0, fp1, z0, y);  // y = z0 + chi w
+    potential_lin(c, y, qat_final, c.vnew);               // g(w) = K y; leaves y_sh in c.qsh
     double res = 0.0;
     for (int k = threadIdx.x; k < n; k += NT) res = fmax(res, fabs(c.vnew[k] - c.v[k]));
     res = block_max(res, c.red);
     __syncthreads();
 #ifdef XTB_PROFILE_PHASES
     ++nit;
-    if (threadIdx.x == 0 && blockIdx.x == 0) printf("  response it %d: residual %.3e (history %d)\n", it, res, mx.step);
+    if (threadIdx.x == 0 && blockIdx.x == 0) printf("  response it %d: residual %.3e\n", it, res);
 #endif
     if (res < kResponseTol) {
       for (int k = threadIdx.x; k < n; k += NT) c.v[k] = c.vnew[k];
@@ -1011,18 +1041,21 @@ __device__ void scf_response(Ctx& c, const xtb_scf_opts& o, const double* __rest
     c.vnew[k] = dv[k] + c.v[k];  // u = dv + K y
   }
   __syncthreads();
-  response_density<MODE, false>(c, c.vnew, fp0, fp1);
+  response_density<MODE, false>(c, rb, c.vnew, fp0, fp1);
   for (int t = threadIdx.x; t < n * n; t += NT) {
     const int i = t / n, j = t - i * n;
     Pm[t] += c.A[(size_t)i * ld + j];
   }
   __syncthreads();
-  response_density<MODE, true>(c, c.vnew, fp0, fp1);
+  response_density<MODE, true>(c, rb, c.vnew, fp0, fp1);
   for (int t = threadIdx.x; t < n * n; t += NT) {
     const int i = t / n, j = t - i * n;
     Wm[t] += c.A[(size_t)i * ld + j];
   }
   __syncthreads();
+#ifdef XTB_PROFILE_PHASES
+  if (threadIdx.x == 0 && blockIdx.x == 0) printf("  response total %lld cycles\n", clock64() - tr0);
+#endif
 }
 
 // Per-molecule results of the converged SCF: charges, potential, orbital energies / occupations, atom-resolved energies.

@@ -88,7 +88,7 @@ typedef struct xtb_scf_opts {
   int32_t generations;      /* 5 */
   int32_t soft_start;       /* 1 */
   int32_t fermi_maxiter;    /* 200 */
-  int32_t want_density;     /* 1: write P, W (needed by xtb_grad_bwd) */
+  int32_t want_density;     /* 1: write P, W (needed by xtb_grad_bwd); 2: the same + workspace for the SCF response (resp != NULL) */
   int32_t use_smem;         /* kernel variant: 1 = C, A, X matrices in shared memory; 2 = hybrid (A in shared memory, C and X in the
                                workspace); 0 = all in the workspace.  The host checks capacity (xtb_scf_smem_bytes_mode) */
   int32_t jacobi_max_sweeps;/* 30 */
