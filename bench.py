@@ -567,15 +567,18 @@ def run_ours(args) -> None:
                 e_ref = np.concatenate([o[0].reshape(-1) for o in out])
                 f_ref = np.concatenate([o[1].reshape(-1, *o[1].shape[-2:]) for o in out])
                 cpu_de = float(np.abs(e_last[: len(e_ref)].detach().cpu().numpy() - e_ref).max())
-                cpu_df = float(np.abs(-g_last[: len(f_ref)].cpu().numpy() - f_ref).max())
+                gaps = np.abs(-g_last[: len(f_ref)].cpu().numpy() - f_ref).reshape(len(f_ref), -1).max(1)
+                cpu_df = float(gaps.max())
+                cpu_df_stats = {"median": float(np.median(gaps)), "fraction_within_1e-7": float((gaps < 1e-7).mean())}
             else:
-                cpu_de = cpu_df = None
+                cpu_de = cpu_df = cpu_df_stats = None
             arm.close()
             cpu = {"value": n / dt, "unit": UNIT, "cores": arm.cores, "per_core": n / dt / arm.cores, "kind": arm.kind,
                    "sample": f"{n} systems of the last batch, energy+forces, {arm.what}, {arm.cores} worker processes x 1 thread ({dt:.1f} s)",
-                   "max_abs_dE_vs_cuda_Eh": cpu_de, "max_abs_dF_vs_cuda_Eh_per_bohr": cpu_df,
-                   "note": "forces of dxtb are autograd through the unrolled SCF at default thresholds; the analytic converged-SCF "
-                           "gradient differs from them by O(SCF residual) (DESIGN.md section 5)"}
+                   "max_abs_dE_vs_cuda_Eh": cpu_de, "max_abs_dF_vs_cuda_Eh_per_bohr": cpu_df, "dF_vs_cuda": cpu_df_stats,
+                   "note": "forces of dxtb are autograd through the unrolled SCF at default thresholds; the CUDA forces are the "
+                           "analytic gradient + first-order response of the SCF residual; what remains is second order "
+                           "(derivative of the reference's own unconverged trajectory), see DESIGN.md section 5"}
 
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
