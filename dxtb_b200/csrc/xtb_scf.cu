@@ -13,6 +13,8 @@
 // 2 = only A in shared memory, C and X in the L2-resident workspace (nao <= ~128), 0 = all three in the workspace.
 // Leading dimension ld = ne + 4 (== 4 mod 16): every DMMA fragment load is bank-conflict free.
 #include "xtb_scf_core.cuh"
+
+#include <cstdlib>
 #ifdef XTB_PROFILE_PHASES
 #include <cstdio>
 #endif
@@ -392,15 +394,18 @@ extern "C" int xtb_scf_run(const xtb_batch* b, const xtb_scf_opts* o, const doub
   if (mode == 1)
     return launch_mode<1>(b, o, nblocks, lnao, lnsh, lnat, S, H0, gamma, nel_ab, q0_at, wk, q_orb, q_sh, q_at, v_orb, e_atom, fenergy, emo,
                           occ, iterations, status, P, W, resp, st);
-  // global-memory and hybrid variants: with at least ~1.5 molecules per SM two CTAs per SM (secondary build, 64 registers)
-  // overlap one molecule's latency-bound sub-problems with the other's tensor-core passes, if their shared memory fits twice
+  // global-memory and hybrid variants at two CTAs per SM (secondary build, 64 registers): one molecule's latency-bound
+  // sub-problems overlap the other's tensor-core passes.  Round 2 measurement (tools/ab_variants.py, 1024 capsaicin
+  // conformers, nao 142): 4.50 k SP/s at 2 CTAs/SM against 5.52 k at 1 CTA/SM (128 registers, no spills, the matrices of 148
+  // instead of 296 molecules in L2) -- so it is off unless DXTB_B200_2CTA is set.
   static int n_sm = 0;
   if (n_sm == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   }
-  const bool two = 2 * nblocks >= 3 * n_sm && mode_smem_bytes(mode, lnao, lnsh, lnat) <= XTB_SMEM_2CTA;
+  static const bool want_2cta = getenv("DXTB_B200_2CTA") != nullptr;  // developer A/B knob
+  const bool two = want_2cta && 2 * nblocks >= 3 * n_sm && mode_smem_bytes(mode, lnao, lnsh, lnat) <= XTB_SMEM_2CTA;
   if (two)
     return xtb_scf_launch_2cta(mode, b, o, nblocks, lnao, lnsh, lnat, S, H0, gamma, nel_ab, q0_at, wk, q_orb, q_sh, q_at, v_orb, e_atom,
                                fenergy, emo, occ, iterations, status, P, W, resp, st);

@@ -164,8 +164,8 @@ int xtb_scf_run_large(const xtb_batch* b, const xtb_scf_opts* o, int32_t mol, in
 /* Dynamic shared memory the SCF kernel needs with use_smem=1 (host compares with the device limit). */
 int64_t xtb_scf_smem_bytes(const xtb_batch* b);
 int64_t xtb_scf_smem_bytes_for(int32_t nao_max, int32_t nsh_max, int32_t nat_max);
-/* Same for kernel variant `mode` (the use_smem values).  Variants 0 and 2 run two CTAs per SM when the launch has at
-   least 1.5 molecules per SM and this is at most XTB_SMEM_2CTA. */
+/* Same for kernel variant `mode` (the use_smem values).  With DXTB_B200_2CTA set, variants 0 and 2 run two CTAs per SM when the
+   launch has at least 1.5 molecules per SM and this is at most XTB_SMEM_2CTA (measured slower in round 2; off by default). */
 int64_t xtb_scf_smem_bytes_mode(int32_t mode, int32_t nao_max, int32_t nsh_max, int32_t nat_max);
 #define XTB_SMEM_2CTA (113 * 1024)
 
