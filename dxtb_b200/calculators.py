@@ -77,17 +77,18 @@ class _Workspace:
 
     def __init__(self, d: BatchDescriptor, want_density: bool, scf_opts: _abi.XtbScfOpts, need_global: bool = True):
         dev, f64 = d.device, torch.float64
-        z = lambda n, dt=f64: torch.zeros(int(n), dtype=dt, device=dev)  # noqa: E731
-        self.cn, self.e_rep, self.e_xb = z(d.nat_tot), z(d.nat_tot), z(d.nat_tot)
-        self.e_disp = z(d.nat_tot) if d.has_d3 else None
+        # all zero-initialised fp64 outputs are views of ONE buffer (one fill launch instead of fourteen)
+        sizes = [d.nat_tot] * 3 + [d.nat_tot if d.has_d3 else 0, d.nat_tot, int(d.struct.gam_total)] + [d.nao_tot] * 4 + \
+                [d.nsh_tot, d.nat_tot, d.nat_tot, d.nb]
+        flat = torch.zeros(int(sum(sizes)), dtype=f64, device=dev)
+        views = torch.split(flat, [int(x) for x in sizes])
+        (self.cn, self.e_rep, self.e_xb, e_disp, self.q0_at, self.gamma, self.q_orb, self.v_orb, self.emo, self.occ,
+         self.q_sh, self.q_at, self.e_atom, self.fenergy) = views
+        self.e_disp = e_disp if d.has_d3 else None
         self.d3w = torch.empty((d.nat_tot, 14), dtype=f64, device=dev) if d.has_d3 else None
-        self.q0_at = z(d.nat_tot)
-        self.gamma = z(d.struct.gam_total)
         self.S, self.H0 = torch.empty(d.struct.mat_total, dtype=f64, device=dev), torch.empty(d.struct.mat_total, dtype=f64, device=dev)
-        self.q_orb, self.v_orb, self.emo, self.occ = z(d.nao_tot), z(d.nao_tot), z(d.nao_tot), z(d.nao_tot)
-        self.q_sh, self.q_at, self.e_atom = z(d.nsh_tot), z(d.nat_tot), z(d.nat_tot)
-        self.fenergy = z(d.nb)
-        self.iterations, self.status = z(d.nb, torch.int32), z(d.nb, torch.int32)
+        ints = torch.zeros(2 * d.nb, dtype=torch.int32, device=dev)
+        self.iterations, self.status = ints[: d.nb], ints[d.nb:]
         scf_opts.use_smem = 0 if need_global else 1  # sizes the matrix workspace of variants 0 and 2
         nbytes = _abi.lib().xtb_scf_workspace_bytes(d.ptr, _abi.C.addressof(scf_opts))
         self.work = torch.empty(int(nbytes) // 8 + 1, dtype=f64, device=dev)

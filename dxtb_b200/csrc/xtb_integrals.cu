@@ -239,15 +239,29 @@ XTB_DEV H0Factors h0_factors(const xtb_batch& b, int m, const PairInfo& pi, cons
   return f;
 }
 
+// Basis data staged in shared memory: the contracted-Gaussian table of the batch (one 16-double row per unique (element,
+// shell): nprim, exponents, coefficients) is copied once per CTA; every thread then reads its two rows from there in the
+// primitive double loop.  Falls back to the global table if the batch has more than kCgtoSmemRows unique shells.
+constexpr int kCgtoSmemRows = 96;  // 12 kB
+
+XTB_DEV const double* stage_cgto(const xtb_batch& b, double* s_cgto) {
+  if (b.ncgto > kCgtoSmemRows) return b.cgto;
+  for (int t = threadIdx.x; t < b.ncgto * XTB_CGTO; t += blockDim.x) s_cgto[t] = b.cgto[t];
+  __syncthreads();
+  return s_cgto;
+}
+
 template <int LI, int LJ>
 __global__ void __launch_bounds__(128) k_overlap_h0(const xtb_batch b, const double* __restrict__ pos, const double* __restrict__ cn,
                                                     double* __restrict__ S, double* __restrict__ H0, int mol0) {
+  __shared__ double s_cgto[kCgtoSmemRows * XTB_CGTO];
+  const double* cgto = stage_cgto(b, s_cgto);
   const int m = mol0 + blockIdx.y;
   const PairInfo pi = pair_setup<LI, LJ>(b, m, pos);
   if (!pi.valid) return;
   const int s0 = b.sh_off[m];
-  const double* gi = b.cgto + (size_t)b.sh_cgto[s0 + pi.I] * XTB_CGTO;
-  const double* gj = b.cgto + (size_t)b.sh_cgto[s0 + pi.J] * XTB_CGTO;
+  const double* gi = cgto + (size_t)b.sh_cgto[s0 + pi.I] * XTB_CGTO;
+  const double* gj = cgto + (size_t)b.sh_cgto[s0 + pi.J] * XTB_CGTO;
   double s[2 * LI + 1][2 * LJ + 1];
   double dummy[1][2 * LI + 1][2 * LJ + 1];
   shell_pair_overlap<LI, LJ, false>(gi, gj, pi.vx, pi.vy, pi.vz, s, dummy);
@@ -288,12 +302,14 @@ template <int LI, int LJ>
 __global__ void __launch_bounds__(128) k_grad_pair(const xtb_batch b, const double* __restrict__ pos, const double* __restrict__ cn,
                                                    const double* __restrict__ P, const double* __restrict__ W,
                                                    const double* __restrict__ v_orb, double* __restrict__ pairbuf, int mol0) {
+  __shared__ double s_cgto[kCgtoSmemRows * XTB_CGTO];
+  const double* cgto = stage_cgto(b, s_cgto);
   const int m = mol0 + blockIdx.y;
   const PairInfo pi = pair_setup<LI, LJ>(b, m, pos);
   if (!pi.valid) return;
   const int s0 = b.sh_off[m], a0 = b.at_off[m], o0 = b.ao_off[m];
-  const double* gi = b.cgto + (size_t)b.sh_cgto[s0 + pi.I] * XTB_CGTO;
-  const double* gj = b.cgto + (size_t)b.sh_cgto[s0 + pi.J] * XTB_CGTO;
+  const double* gi = cgto + (size_t)b.sh_cgto[s0 + pi.I] * XTB_CGTO;
+  const double* gj = cgto + (size_t)b.sh_cgto[s0 + pi.J] * XTB_CGTO;
   double s[2 * LI + 1][2 * LJ + 1];
   double ds[3][2 * LI + 1][2 * LJ + 1];
   shell_pair_overlap<LI, LJ, true>(gi, gj, pi.vx, pi.vy, pi.vz, s, ds);
