@@ -40,4 +40,16 @@ if which in ("all", "hybrid"):
 if which in ("all", "global"):
     run(["nicotine", "H2O"], override=0)                            # variant 0 (forced)
 if which in ("all", "large"):
-    run(["H2O", "caffeine"], DXTB_B200_LARGE_MIN_NAO=1)            # variant 3
+    run(["H2O", "caffeine"], DXTB_B200_LARGE_MIN_NAO=1)            # variant 3 (two molecules in flight on host threads)
+if which in ("all", "halogen"):
+    # halogen-bond energy + gradient, SCF response on a converged-enough state (round 2)
+    sys.path.insert(0, str(ROOT / "tests"))
+    from halogen_mols import halogen_mol
+    z, xyz = halogen_mol("CH3Br_NH3")
+    os.environ["DXTB_B200_LARGE_MIN_NAO"] = "1000000"
+    calc = GFN1Calculator(torch.tensor(z, device=dev), opts={"exclude": ["disp"]}, device=dev, dtype=torch.float64)
+    p = torch.tensor(xyz, device=dev, requires_grad=True)
+    e = calc.get_energy(p)
+    (g,) = torch.autograd.grad(e, p)
+    torch.cuda.synchronize()
+    print("CH3Br_NH3", calc._variants, float(e), float(g.abs().max()))
