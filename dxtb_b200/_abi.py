@@ -50,9 +50,10 @@ class XtbScfOpts(C.Structure):
     _fields_ = [
         ("maxiter", C.c_int32), ("mixer", C.c_int32), ("generations", C.c_int32), ("soft_start", C.c_int32),
         ("fermi_maxiter", C.c_int32), ("want_density", C.c_int32), ("use_smem", C.c_int32), ("jacobi_max_sweeps", C.c_int32),
+        ("subspace", C.c_int32), ("subspace_maxiter", C.c_int32),
         ("damp", C.c_double), ("damp_init", C.c_double), ("diag_offset", C.c_double),
         ("x_atol", C.c_double), ("x_atol_max", C.c_double), ("kt", C.c_double), ("fermi_thresh", C.c_double),
-        ("jacobi_tol", C.c_double), ("jacobi_tol_iter", C.c_double),
+        ("jacobi_tol", C.c_double), ("jacobi_tol_iter", C.c_double), ("subspace_tol", C.c_double), ("subspace_gap", C.c_double),
         ("mol_list", _vp), ("list_len", C.c_int32), ("list_nao_max", C.c_int32), ("list_nsh_max", C.c_int32),
         ("list_nat_max", C.c_int32),
     ]

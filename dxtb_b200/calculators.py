@@ -54,6 +54,10 @@ DEFAULT_OPTS: dict[str, Any] = {
     # B200 path only: add the first-order response of the SCF residual to the analytic gradient, so that forces equal the
     # reference's autograd-through-the-unrolled-SCF forces at ANY convergence threshold (xtb_scf_core.cuh:scf_response)
     "grad_response": True,
+    # B200 path only: intermediate SCF iterations of closed-shell molecules with a certified gap >= 60 kT solve for the
+    # occupied subspace (Riccati fixed point, xtb_scf_subspace.cuh) instead of diagonalising; the final solve is always the
+    # full eigendecomposition.  False: every iteration diagonalises (as the reference does).
+    "scf_subspace": True,
 }
 _IGNORED_OPTS = {"cache_enabled", "cache_charges", "cache_iterations", "cache_density", "cache_potential",
                  "cache_coefficients", "cache_mo_energies", "cache_occupation", "cache_overlap", "cache_hcore",
@@ -452,6 +456,11 @@ class GFN1Calculator:
         s.jacobi_tol = 1e-13
         # intermediate map evaluations: eigensolver residual 4 orders below the SCF convergence threshold
         s.jacobi_tol_iter = min(2e-9, max(s.jacobi_tol, 1e-4 * min(s.x_atol, s.x_atol_max)))
+        # occupied-subspace solve of the intermediate iterations (DXTB_B200_SUBSPACE=0: developer A/B switch)
+        s.subspace = 1 if o["scf_subspace"] and os.environ.get("DXTB_B200_SUBSPACE", "1") != "0" else 0
+        s.subspace_maxiter = 16
+        s.subspace_tol = min(1e-10, 0.05 * s.jacobi_tol_iter)
+        s.subspace_gap = 60.0
         return s
 
     def _electrons(self, chrg: torch.Tensor, spin: torch.Tensor | None) -> torch.Tensor:

@@ -13,6 +13,7 @@
 // 2 = only A in shared memory, C and X in the L2-resident workspace (nao <= ~128), 0 = all three in the workspace.
 // Leading dimension ld = ne + 4 (== 4 mod 16): every DMMA fragment load is bank-conflict free.
 #include "xtb_scf_core.cuh"
+#include "xtb_scf_subspace.cuh"
 
 #include <cstdlib>
 #ifdef XTB_PROFILE_PHASES
@@ -52,10 +53,9 @@ __device__ void reorthonormalize(Ctx& c) {
   gemm_tn<CS, AS>(ne, ne, c.X, c.A, ld, c.C, ld, ne);  // C = C M
 }
 
-// One SCF map evaluation v -> q -> vnew (scf/base.py:651-675, 818-907, 765-792).
-// Returns the electronic free energy of this solve.
+// A = C^T F C with F = H0 - 1/2 S o (v_i + v_j), symmetrised, pad rows / columns exactly zero (X buffer: F C).
 template <int MODE>
-__device__ double fcn(Ctx& c, const double* __restrict__ v, const xtb_scf_opts& o, double nel_a, double nel_b, double jtol) {
+__device__ void build_projected_fock(Ctx& c, const double* __restrict__ v) {
   const int n = c.n, ne = c.ne, ld = c.ld;
   constexpr bool AS = MODE != 0, CS = MODE == 1;  // address space of the A buffer / of the C and X buffers
   // F = H0 - 1/2 S (v_i + v_j)   -> A buffer (symmetric, zero padded)
@@ -81,40 +81,124 @@ __device__ double fcn(Ctx& c, const double* __restrict__ v, const xtb_scf_opts& 
     }
   }
   __syncthreads();
+}
+
+template <int MODE>
+__device__ int jacobi_mode(Ctx& c, double tol, int maxsweeps) {
+  constexpr bool AS = MODE != 0, CS = MODE == 1;
 #ifdef XTB_PROFILE_PHASES
   const long long tj0 = clock64();
 #endif
-  const int sw = (MODE != 1 && c.defer) ? jacobi<AS, CS, MODE != 1>(c, c.A, c.C, ne, jtol, o.jacobi_max_sweeps)
-                                        : jacobi<AS, CS, false>(c, c.A, c.C, ne, jtol, o.jacobi_max_sweeps);
+  c.sub.xvalid = false;  // the basis changes (and X may live in the Jacobi scratch)
+  const int sw = (MODE != 1 && c.defer) ? jacobi<AS, CS, MODE != 1>(c, c.A, c.C, c.ne, tol, maxsweeps)
+                                        : jacobi<AS, CS, false>(c, c.A, c.C, c.ne, tol, maxsweeps);
 #ifdef XTB_PROFILE_PHASES
   c.tjac += clock64() - tj0;
 #endif
-  if (sw < 0) c.status |= XTB_STATUS_JACOBI_NOT_CONVERGED;
   c.sweeps += sw < 0 ? -sw : sw;
-  for (int k = threadIdx.x; k < n; k += NT) c.eps[k] = c.A[(size_t)k * ld + k];
-  __syncthreads();
-  const double g = fermi_fill(c, nel_a, nel_b, o);
-  // compact list of occupied orbitals
-  if (threadIdx.x == 0) {
-    int no = 0;
-    for (int k = 0; k < n; ++k)
-      if (c.focc[k] > 0.0) c.occl[no++] = k;
-    c.occl[n] = no;
+  return sw;
+}
+
+// One SCF map evaluation v -> q -> vnew (scf/base.py:651-675, 818-907, 765-792).
+// Returns the electronic free energy of this solve (0 on the occupied-subspace path, whose occupations are integer).
+// final_solve: the solve that defines the results -- always the full eigendecomposition.
+template <int MODE>
+__device__ double fcn(Ctx& c, const double* __restrict__ v, const xtb_scf_opts& o, double nel_a, double nel_b, double jtol,
+                      bool final_solve) {
+  const int n = c.n, ne = c.ne, ld = c.ld;
+  constexpr bool CS = MODE == 1;
+#ifdef XTB_PROFILE_PHASES
+  const long long tf0 = clock64();
+#endif
+  build_projected_fock<MODE>(c, v);
+#ifdef XTB_PROFILE_PHASES
+  c.tfock += clock64() - tf0;
+#endif
+  const double* Pb = c.A;  // buffer that holds the density after the solve
+  bool fast = false, diagonal = false;
+  double g = 0.0;
+  if (!final_solve && c.sub.eligible) {
+    // occupied-subspace path (xtb_scf_subspace.cuh): Jacobi sweeps only until the gap between the two diagonal blocks is
+    // certified, then the Riccati fixed point for the occupied subspace
+    int sweeps_here = 0;
+    for (;;) {
+      bool needs_perm;
+#ifdef XTB_PROFILE_PHASES
+      const long long tc0 = clock64();
+#endif
+      const double gapc = subspace_certify(c, c.A, needs_perm);
+#ifdef XTB_PROFILE_PHASES
+      c.tcert += clock64() - tc0;
+#endif
+#ifdef XTB_DEBUG_SUBSPACE
+      if (threadIdx.x == 0 && blockIdx.x == 0) printf("  certified gap %.4f (need %.4f) permute %d sweeps so far %d\n", gapc, c.sub.gapmin, (int)needs_perm, c.sweeps);
+#endif
+      if (gapc >= c.sub.gapmin) {
+        if (needs_perm) {
+          subspace_permute(c);
+          c.sub.xvalid = false;
+        }
+#ifdef XTB_PROFILE_PHASES
+        const long long ts0 = clock64();
+#endif
+        double* pb = nullptr;
+        const bool ok = subspace_riccati<MODE>(c, o);
+#ifdef XTB_PROFILE_PHASES
+        const long long ts1 = clock64();
+        c.tric += ts1 - ts0;
+#endif
+        if (ok) pb = subspace_density<MODE>(c);
+#ifdef XTB_PROFILE_PHASES
+        c.tsub += clock64() - ts0;
+        c.tden += clock64() - ts1;
+#endif
+        if (pb != nullptr) {
+          Pb = pb;
+          fast = true;
+          ++c.sub.nfast;
+          break;
+        }
+        if (ok) build_projected_fock<MODE>(c, v);  // the density step overwrote A before it failed
+      }
+      if (sweeps_here >= o.jacobi_max_sweeps) break;  // the full solve below reports the failure
+      const int sw = jacobi_mode<MODE>(c, jtol, 1);
+      sweeps_here += sw < 0 ? -sw : sw;
+      if (sw >= 0) { diagonal = true; break; }  // converged: finish on the standard path
+    }
   }
-  __syncthreads();
-  const int nocc = c.occl[n];
-  // Y[kk][i] = sqrt(f_k) C[i][k]  -> X buffer;  P = Y^T Y -> A buffer
-  for (int t = threadIdx.x; t < nocc * ld; t += NT) {
-    const int kk = t / ld, i = t - kk * ld;
-    const int k = c.occl[kk];
-    c.X[t] = (i < n) ? sqrt(c.focc[k]) * c.C[(size_t)i * ld + k] : 0.0;
+  if (!fast) {
+    if (!diagonal) {
+      const int sw = jacobi_mode<MODE>(c, jtol, o.jacobi_max_sweeps);
+      if (sw < 0) c.status |= XTB_STATUS_JACOBI_NOT_CONVERGED;
+    }
+    for (int k = threadIdx.x; k < n; k += NT) c.eps[k] = c.A[(size_t)k * ld + k];
+    __syncthreads();
+    g = fermi_fill(c, nel_a, nel_b, o);
+    // compact list of occupied orbitals
+    if (threadIdx.x == 0) {
+      int no = 0;
+      for (int k = 0; k < n; ++k)
+        if (c.focc[k] > 0.0) c.occl[no++] = k;
+      c.occl[n] = no;
+    }
+    __syncthreads();
+    const int nocc = c.occl[n];
+    // Y[kk][i] = sqrt(f_k) C[i][k]  -> X buffer;  P = Y^T Y -> A buffer
+    for (int t = threadIdx.x; t < nocc * ld; t += NT) {
+      const int kk = t / ld, i = t - kk * ld;
+      const int k = c.occl[kk];
+      c.X[t] = (i < n) ? sqrt(c.focc[k]) * c.C[(size_t)i * ld + k] : 0.0;
+    }
+    __syncthreads();
+    gemm_tn<CS, CS>(ne, nocc, c.X, c.X, ld, c.A, ld, ne);
   }
-  __syncthreads();
-  gemm_tn<CS, CS>(ne, nocc, c.X, c.X, ld, c.A, ld, ne);
   // Mulliken populations and orbital-resolved H0 energies: one warp per row
+#ifdef XTB_PROFILE_PHASES
+  const long long tm0 = clock64();
+#endif
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   for (int mu = w; mu < n; mu += NT / 32) {
-    const double* pr = c.A + (size_t)mu * ld;
+    const double* pr = Pb + (size_t)mu * ld;
     const double* sr = c.S + (size_t)mu * n;
     const double* hr = c.H0 + (size_t)mu * n;
     double pop = 0.0, e = 0.0;
@@ -132,6 +216,9 @@ __device__ double fcn(Ctx& c, const double* __restrict__ v, const xtb_scf_opts& 
   }
   __syncthreads();
   potential(c, c.q, c.vnew);
+#ifdef XTB_PROFILE_PHASES
+  c.tmull += clock64() - tm0;
+#endif
   return g;
 }
 
@@ -157,7 +244,10 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
   c.np = c.ne / 2;
   c.status = 0;
   c.sweeps = 0;
-  c.tp1 = c.tp2 = c.tjac = 0;
+  c.tp1 = c.tp2 = c.tjac = c.tsub = 0;
+#ifdef XTB_PROFILE_PHASES
+  c.tcert = c.tric = c.tden = c.tfock = c.tmull = 0;
+#endif
 #ifdef XTB_PROFILE_PHASES
   const long long tk0 = clock64();
 #endif
@@ -175,6 +265,7 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
   double* sm_theta = p; p += 36;
   c.occl = (int*)p; p += (nmx + 2) / 2 + 1;
   p += ((p - sm) & 1);  // 16-byte alignment for the double2 / int2 scratch and the matrices
+  int jcap = 0;  // doubles of block-Jacobi scratch (free between sweeps: home of the occupied-subspace X, MODE 1)
   {
     // block-Jacobi scratch, always in shared memory: accumulated rotations Q per block pair, sub-problem copy and
     // rotation parameters per concurrently working thread group
@@ -184,20 +275,23 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
     c.ng = nbpx < NGRP ? nbpx : NGRP;
     c.jm = p; p += c.ng * JB2 * MLD;
     c.jr = nullptr;
+    jcap = (int)(p - c.jq);
   }
   p += ((p - sm) & 1);
   c.smem = MODE == 1;
   const size_t msz = (size_t)ne * ld;
-  // workspace: [Anderson history][2 response matrices per molecule if want_density == 2][3 matrices per molecule, MODE != 1]
+  // workspace: [Anderson history][2 response matrices per molecule if want_density == 2][occupied-subspace X, Z: 1 matrix
+  // bound per molecule][3 matrices per molecule, MODE != 1]
   const size_t mat_bound = (size_t)b.mat_total + 34 * (size_t)b.nao_tot + 285 * (size_t)b.nb;
   const size_t resp_region = o.want_density == 2 ? 2 * mat_bound : 0;
+  const size_t mol_bound = (size_t)b.mat_off[m] + 34 * (size_t)c.o0 + 285 * (size_t)m;  // sum of (n+15)(n+19) over the molecules before m
+  double* persist = work + (size_t)(o.generations + 1) * 2 * b.nao_tot + resp_region + mol_bound;
   if (MODE == 1) {
     const size_t nex = (size_t)((lnao + 15) & ~15);
     const size_t mszx = nex * (nex + 4);
     c.C = p; c.A = p + mszx; c.X = p + 2 * mszx;
   } else {
-    double* wm = work + (size_t)(o.generations + 1) * 2 * b.nao_tot + resp_region +
-                 3 * ((size_t)b.mat_off[m] + 34 * (size_t)c.o0 + 285 * (size_t)m);  // sum of (n+15)(n+19) bounds ne*ld
+    double* wm = work + (size_t)(o.generations + 1) * 2 * b.nao_tot + resp_region + mat_bound + 3 * mol_bound;  // (n+15)(n+19) bounds ne*ld
     c.C = wm; c.A = wm + msz; c.X = wm + 2 * msz;
     if (MODE == 2) c.A = p;  // hybrid: the Fock / A / density buffer (sub-problem gathers, two-sided updates) in shared memory
   }
@@ -214,6 +308,26 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
   c.at_nsh = b.at_nsh + c.a0;
   c.gam3 = b.at_par + (size_t)c.a0 * XTB_ATPAR;
   const double nel_a = nel_ab[2 * m], nel_b = nel_ab[2 * m + 1];
+  {
+    // occupied-subspace path of the intermediate map evaluations (xtb_scf_subspace.cuh): closed shell, integer occupation,
+    // Y^T and (Y Z)^T side by side in the A buffer (2 no <= ne); not below 33 AOs, where a Jacobi sweep is one or two block
+    // rounds and costs less than the barriers of the fixed point (measured: H2O 0.77x, SiH4 0.99x, MB16_43_01 1.45x)
+    Subspace& sb = c.sub;
+    sb.no = (int)rint(nel_a);
+    sb.nv = c.n - sb.no;
+    sb.lds = ((sb.no + 15) & ~15) + 4;
+    sb.xvalid = sb.zvalid = false;
+    sb.nfast = sb.nric = sb.nnewt = 0;
+    sb.gapmin = fmax(o.subspace_gap * o.kt, 0.02);
+    sb.eligible = o.subspace != 0 && o.maxiter > 0 && nel_a == nel_b && fabs(nel_a - (double)sb.no) < 1e-9 && sb.no >= 1 && sb.nv >= 1 &&
+                  2 * sb.no <= c.ne && c.ne >= 48;
+    sb.Zg = persist;                                // [no][lds]
+    sb.X = persist + (size_t)sb.no * sb.lds;        // [nv][lds];  (no + nv) lds <= n (n + 19)
+    if (MODE == 1) {
+      if (sb.nv * sb.lds <= jcap) sb.X = c.jq;      // shared memory: the Jacobi scratch is free between sweeps
+      else sb.eligible = false;
+    }
+  }
 
   // reference occupation per AO (scf/iterator.py:147-170)
   for (int mu = threadIdx.x; mu < n; mu += NT) {
@@ -241,12 +355,12 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
   bool converged = true;
   // intermediate map evaluations only steer the SCF trajectory: a looser eigensolver tolerance saves the last
   // (verification) sweep; the final solve that defines charges / energies / P / W uses the tight one
-  double g = fcn<MODE>(c, c.v, o, nel_a, nel_b, o.maxiter > 0 ? o.jacobi_tol_iter : o.jacobi_tol);  // outside the loop (unrolling/default.py:81)
+  double g = fcn<MODE>(c, c.v, o, nel_a, nel_b, o.maxiter > 0 ? o.jacobi_tol_iter : o.jacobi_tol, o.maxiter <= 0);  // outside the loop (unrolling/default.py:81)
   if (o.maxiter > 0) {
     converged = false;
     mix(c, mx, o, sm_theta);  // mix_guess (unrolling/default.py:93-94); convergence is not tested here
     for (int it = 0; it < o.maxiter; ++it) {
-      g = fcn<MODE>(c, c.v, o, nel_a, nel_b, o.jacobi_tol_iter);
+      g = fcn<MODE>(c, c.v, o, nel_a, nel_b, o.jacobi_tol_iter, false);
       ++iters;
       if (mix(c, mx, o, sm_theta)) { converged = true; break; }
     }
@@ -254,15 +368,18 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
     for (int k = threadIdx.x; k < n; k += NT) c.v[k] = c.vnew[k];
     __syncthreads();
     reorthonormalize<MODE>(c);  // remove the drift of the accumulated rotations before the solve that defines the results
-    g = fcn<MODE>(c, c.v, o, nel_a, nel_b, o.jacobi_tol);
+    g = fcn<MODE>(c, c.v, o, nel_a, nel_b, o.jacobi_tol, true);
   }
   if (!converged) c.status |= XTB_STATUS_SCF_NOT_CONVERGED;
 
   emit_results(c, b, m, g, iters, q_orb, q_sh, q_at, v_orb, e_atom, fenergy, emo, occ, iterations, status);
 #ifdef XTB_PROFILE_PHASES
   if (threadIdx.x == 0 && blockIdx.x == 0)
-    printf("k_scf phases (cycles): total %lld  jacobi %lld  sub-problems %lld  pass %lld  sweeps %d\n", clock64() - tk0, c.tjac, c.tp1, c.tp2,
-           c.sweeps);
+    printf("k_scf phases (cycles): total %lld  jacobi %lld  sub-problems %lld  pass %lld  sweeps %d  subspace %lld (%d map evaluations of %d, %d fixed-point, %d Newton iterations)\n",
+           clock64() - tk0, c.tjac, c.tp1, c.tp2, c.sweeps, c.tsub, c.sub.nfast, iters, c.sub.nric, c.sub.nnewt);
+  if (threadIdx.x == 0 && blockIdx.x == 0)
+    printf("   certify %lld  fixed point %lld  density %lld  | projected Fock (all map evaluations) %lld  Mulliken + potential %lld\n", c.tcert, c.tric, c.tden,
+           c.tfock, c.tmull);
 #endif
   if (o.want_density) {
     double* Pm = Pout + b.mat_off[m];
@@ -364,6 +481,7 @@ extern "C" int64_t xtb_scf_smem_bytes(const xtb_batch* b) {
 extern "C" int64_t xtb_scf_workspace_bytes(const xtb_batch* b, const xtb_scf_opts* o) {
   if (!b || !o) return -1;
   int64_t d = (int64_t)(o->generations + 1) * 2 * b->nao_tot;
+  d += b->mat_total + 34 * (int64_t)b->nao_tot + 285 * (int64_t)b->nb;  // occupied-subspace X and Z per molecule
   if (o->want_density == 2) d += 2 * (b->mat_total + 34 * (int64_t)b->nao_tot + 285 * (int64_t)b->nb);  // SCF response: S C and a GEMM output
   if (o->use_smem != 1) {
     // 3 matrices of at most (n+15)(n+19) per molecule: 3 (sum n^2 + 34 sum n + 285 nb)

@@ -26,8 +26,21 @@ namespace {
 #endif
 constexpr int NT = XTB_NT;  // threads per CTA
 
+// State of the occupied-subspace solve of the intermediate SCF map evaluations (see subspace_* below).
+struct Subspace {
+  bool eligible;   // closed shell with an integer number of doubly occupied orbitals and room for the scratch layout
+  bool xvalid;     // X belongs to the current basis C (reset by every Jacobi sweep / permutation)
+  bool zvalid;     // Zg holds (1 + X^T X)^-1 of an earlier X in the same basis (warm start of the Newton iteration)
+  int no, nv, lds; // occupied / virtual orbitals, leading dimension of the no-column matrices (== 4 mod 16)
+  double gapmin;   // certified HOMO-LUMO gap required for integer occupations
+  double* X;       // [nv][lds] graph of the occupied subspace in the basis C (shared Jacobi scratch or workspace)
+  double* Zg;      // [no][lds] workspace copy of Z
+  int nfast, nric, nnewt;  // diagnostics: map evaluations on this path, fixed-point / Newton iterations
+};
+
 struct Ctx {
   int n, ne, ld, ns, na, np;
+  Subspace sub;
   int o0, s0, a0;
   double *C, *A, *X;             // ne x ld matrices (shared or global)
   const double *S, *H0, *gam;    // global, n x n / ns x ns
@@ -37,7 +50,10 @@ struct Ctx {
   bool smem;                     // matrices live in shared memory
   int ng;                        // Jacobi: number of 16x16 sub-problem copies = warps that solve sub-problems concurrently
   bool defer;                    // Jacobi: Q double buffered, V pass deferred into the next round's sub-problem phase
-  long long tp1, tp2, tjac;      // XTB_PROFILE_PHASES: cycles in the sub-problem phase / rotation pass / whole eigensolver
+#ifdef XTB_PROFILE_PHASES
+  long long tcert, tric, tden, tfock, tmull;
+#endif
+  long long tp1, tp2, tjac, tsub;  // XTB_PROFILE_PHASES: cycles in the sub-problem phase / rotation pass / whole eigensolver / subspace solve
   const int *ao_sh, *sh_atom, *at_sh0, *at_nsh, *sh_ao, *sh_l;
   const double* gam3;            // at_par base (stride XTB_ATPAR)
   double *xh, *fh;               // Anderson history [gen+1][n] (global)

@@ -1,0 +1,293 @@
+// Occupied-subspace solve for the INTERMEDIATE SCF map evaluations of the one-CTA kernel (xtb_scf.cu).
+//
+// The reference diagonalises the Fock matrix in every iteration (scf/unrolling/base.py:141-175) although the iteration only
+// needs the charges of the density it defines (scf/base.py:651-675).  For a closed-shell molecule whose HOMO-LUMO gap is
+// many kT wide the Fermi occupations (wavefunction/filling.py:201-366) are 2 / 0 to round-off, so the density is the projector
+// onto the occupied subspace and no individual eigenvector is needed.  In the basis C of an earlier (partial) diagonalisation
+// the projected Fock matrix A = C^T F C = [[Aoo, Aov], [Avo, Avv]] is nearly block diagonal; the occupied subspace is the
+// graph span([1; X]) of the solution of the algebraic Riccati equation
+//     R(X) = Avo + Avv X - X (Aoo + Aov X) = 0,
+// which the diagonally preconditioned fixed point X <- X - R(X) / (d_a - d_i) reaches in 3-9 iterations of two small
+// tensor-core GEMMs (a Jacobi sweep costs ~10x as much), warm-started from the previous map evaluation.  Then
+//     P = 2 Y (1 + X^T X)^-1 Y^T,   Y = C_o + C_v X,
+// with the inverse by Newton's iteration Z <- Z (2 - G Z), also warm-started.  Everything is GEMM-shaped (DMMA).
+//
+// Safeguards (each falls back to a Jacobi sweep, i.e. to the path that was there before):
+//  * integer occupations are CERTIFIED per map evaluation: with Gershgorin discs inside the two diagonal blocks and Cauchy
+//    interlacing, gap(A) >= min_a (d_a - sum_{b != a} |A_ab|) - max_i (d_i + sum_{j != i} |A_ij|); the path is taken only if
+//    that bound is >= subspace_gap * kT (60 kT: occupation error exp(-30) ~ 1e-13);
+//  * the o / v classification follows the ranks of the current diagonal; a change permutes C and restarts X;
+//  * a stalled, diverging or large (|X| >= 1) fixed point, or a failed Newton iteration, triggers a sweep.
+// The final solve that defines energies, charges, P, W and the orbital energies is always the full Jacobi solve.
+#pragma once
+#include "xtb_scf_core.cuh"
+
+namespace {
+
+// Out(i, j) = sum_{k < K} la(i, k) rb(k, j) for i < M, j < N on the fp64 tensor cores: one warp per (8 TM) x (8 TN) tile,
+// out-of-range operand elements are zero, results are handed to st(i, j, value).  With leading dimensions == 4 (mod 16)
+// row-major operands are bank-conflict free in both orientations ([k][i] and [i][k]).  No trailing barrier.
+template <int TM, int TN, class LA, class RB, class ST>
+__device__ __forceinline__ void gemm_small(int M, int N, int K, LA la, RB rb, ST st) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, tg = lane & 3;
+  const int mt = (M + 8 * TM - 1) / (8 * TM), nt = (N + 8 * TN - 1) / (8 * TN);
+  for (int t = warp; t < mt * nt; t += NT / 32) {
+    const int ti = t / nt, tj = t - ti * nt;
+    const int i0 = ti * 8 * TM, j0 = tj * 8 * TN;
+    double d[TM][TN][2];
+#pragma unroll
+    for (int x = 0; x < TM; ++x)
+#pragma unroll
+      for (int y = 0; y < TN; ++y) d[x][y][0] = d[x][y][1] = 0.0;
+#pragma unroll 4
+    for (int k0 = 0; k0 < K; k0 += 4) {  // unrolled: the operand loads of four steps are in flight together (L2 latency in MODE 0 / 2)
+      const int k = k0 + tg;
+      const bool kv = k < K;
+      double a[TM], b[TN];
+#pragma unroll
+      for (int x = 0; x < TM; ++x) {
+        const int i = i0 + 8 * x + g;
+        a[x] = (kv && i < M) ? la(i, k) : 0.0;
+      }
+#pragma unroll
+      for (int y = 0; y < TN; ++y) {
+        const int j = j0 + 8 * y + g;
+        b[y] = (kv && j < N) ? rb(k, j) : 0.0;
+      }
+#pragma unroll
+      for (int x = 0; x < TM; ++x)
+#pragma unroll
+        for (int y = 0; y < TN; ++y) dmma884(d[x][y][0], d[x][y][1], a[x], b[y]);
+    }
+#pragma unroll
+    for (int x = 0; x < TM; ++x)
+#pragma unroll
+      for (int y = 0; y < TN; ++y) {
+        const int i = i0 + 8 * x + g, j = j0 + 8 * y + 2 * tg;
+        if (i < M) {
+          if (j < N) st(i, j, d[x][y][0]);
+          if (j + 1 < N) st(i, j + 1, d[x][y][1]);
+        }
+      }
+  }
+}
+
+// Block-wide maxima of two values with one pair of barriers (NT = 512: 16 warps; `red` holds 32 doubles).
+__device__ __forceinline__ void block_max2(double& a, double& b, double* red) {
+  static_assert(NT == 512, "block_max2 assumes 16 warps");
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  a = warp_max(a);
+  b = warp_max(b);
+  __syncthreads();
+  if (lane == 0) { red[w] = a; red[16 + w] = b; }
+  __syncthreads();
+  double r = red[lane];  // lanes 0-15: a of the 16 warps, lanes 16-31: b
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) r = fmax(r, __shfl_xor_sync(0xffffffffu, r, o));
+  a = __shfl_sync(0xffffffffu, r, 0);
+  b = __shfl_sync(0xffffffffu, r, 16);
+}
+
+// Ranks of the diagonal of A (-> c.occl, diagonal -> c.eps) and the certified gap between the `no` lowest diagonal entries
+// and the rest (header comment).  needs_perm: the occupied class is not the first `no` columns.
+__device__ double subspace_certify(Ctx& c, const double* __restrict__ A, bool& needs_perm) {
+  const int n = c.n, ld = c.ld, no = c.sub.no;
+  int* rank = c.occl;
+  for (int k = threadIdx.x; k < n; k += NT) c.eps[k] = A[(size_t)k * ld + k];
+  __syncthreads();
+  int bad = 0;
+  for (int k = threadIdx.x; k < n; k += NT) {
+    const double e = c.eps[k];
+    int rk = 0;
+    for (int j = 0; j < n; ++j) {
+      const double ej = c.eps[j];
+      rk += (ej < e) || (ej == e && j < k);
+    }
+    rank[k] = rk;
+    bad |= (rk < no) != (k < no);
+  }
+  needs_perm = __syncthreads_or(bad) != 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double hi = -1.0e300, nlo = -1.0e300;  // max over occupied rows of d + r;  max over virtual rows of -(d - r)
+  for (int i = warp; i < n; i += NT / 32) {
+    const double* row = A + (size_t)i * ld;
+    const bool oi = rank[i] < no;
+    double s = 0.0;
+    for (int j = lane; j < n; j += 32)
+      if (j != i && (rank[j] < no) == oi) s += fabs(row[j]);
+    s = warp_sum(s);
+    if (oi) hi = fmax(hi, c.eps[i] + s);
+    else nlo = fmax(nlo, s - c.eps[i]);
+  }
+  block_max2(hi, nlo, c.red);
+  return -nlo - hi;
+}
+
+// Sort the basis by the ranks in c.occl: column k of C -> column rank[k], A permuted on both sides, c.eps alike.
+// Uses the X buffer as the copy target.
+__device__ void subspace_permute(Ctx& c) {
+  const int n = c.n, ne = c.ne, ld = c.ld;
+  const int* rank = c.occl;
+  for (int t = threadIdx.x; t < ne * ne; t += NT) {
+    const int mu = t / ne, k = t - mu * ne;
+    c.X[(size_t)mu * ld + (k < n ? rank[k] : k)] = c.C[(size_t)mu * ld + k];
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < ne * ne; t += NT) {
+    const int mu = t / ne, k = t - mu * ne;
+    c.C[(size_t)mu * ld + k] = c.X[(size_t)mu * ld + k];
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < ne * ne; t += NT) {
+    const int i = t / ne, j = t - i * ne;
+    c.X[(size_t)(i < n ? rank[i] : i) * ld + (j < n ? rank[j] : j)] = c.A[(size_t)i * ld + j];
+  }
+  for (int k = threadIdx.x; k < n; k += NT) c.srt[rank[k]] = c.eps[k];
+  __syncthreads();
+  for (int t = threadIdx.x; t < ne * ne; t += NT) {
+    const int i = t / ne, j = t - i * ne;
+    c.A[(size_t)i * ld + j] = c.X[(size_t)i * ld + j];
+  }
+  for (int k = threadIdx.x; k < n; k += NT) c.eps[k] = c.srt[k];
+  __syncthreads();
+}
+
+// Fixed-point iteration of the Riccati equation in the occupied-first basis (A in the A buffer, its diagonal in c.eps,
+// T = A(:, v) X with Lambda = Aoo + Aov X in its first `no` rows in the X buffer).  Returns true when max |R| <= tol.
+template <int MODE>
+__device__ bool subspace_riccati(Ctx& c, const xtb_scf_opts& o) {
+  const int n = c.n, ld = c.ld, no = c.sub.no, nv = c.sub.nv, lds = c.sub.lds;
+  const double* __restrict__ A = c.A;
+  double* __restrict__ T = c.X;
+  double* __restrict__ X = c.sub.X;
+  const double* __restrict__ dg = c.eps;
+  if (MODE != 0) XTB_ASSUME_SHARED(A);
+  if (MODE == 1) { XTB_ASSUME_SHARED(T); XTB_ASSUME_SHARED(X); }
+  XTB_ASSUME_SHARED(dg);
+  if (!c.sub.xvalid) {
+    for (int t = threadIdx.x; t < nv * lds; t += NT) X[t] = 0.0;
+    c.sub.xvalid = true;
+    c.sub.zvalid = false;
+    __syncthreads();
+  }
+  double rprev = 1.0e300;
+  for (int it = 0; it < o.subspace_maxiter; ++it) {
+    // T[r][i] = sum_b A[no + b][r] X[b][i]  (A symmetric);  rows r < no: + Aoo -> Lambda
+    gemm_small<2, 1>(
+        n, no, nv, [&](int r, int b) { return A[(size_t)(no + b) * ld + r]; }, [&](int b, int i) { return X[b * lds + i]; },
+        [&](int r, int i, double v) { T[r * lds + i] = (r < no) ? v + A[(size_t)r * ld + i] : v; });
+    __syncthreads();
+    // R = Avo + T1 - X Lambda;  X_new = X - R / (d_a - d_i) -> written over T1 (every element has one owner)
+    double rmax = 0.0, xmax = 0.0;
+    gemm_small<1, 1>(
+        nv, no, no, [&](int a, int j) { return X[a * lds + j]; }, [&](int j, int i) { return T[j * lds + i]; },
+        [&](int a, int i, double t3) {
+          const double r = A[(size_t)(no + a) * ld + i] + T[(no + a) * lds + i] - t3;
+          const double xn = X[a * lds + i] - r / (dg[no + a] - dg[i]);
+          T[(no + a) * lds + i] = xn;
+          rmax = fmax(rmax, fabs(r));
+          xmax = fmax(xmax, fabs(xn));
+        });
+    block_max2(rmax, xmax, c.red);  // its barriers also order the X_new stores before the copy
+    for (int t = threadIdx.x; t < nv * no; t += NT) {
+      const int a = t / no, i = t - a * no;
+      X[a * lds + i] = T[(no + a) * lds + i];
+    }
+    __syncthreads();
+    ++c.sub.nric;
+#ifdef XTB_DEBUG_SUBSPACE
+    if (threadIdx.x == 0 && blockIdx.x == 0) printf("    riccati it %d: max|R| %.3e max|X| %.3e\n", it, rmax, xmax);
+#endif
+    if (!(xmax < 1.0) || !(rmax < 1.0e300)) return false;  // large rotation / NaN: not the regime of this path
+    if (rmax <= o.subspace_tol) return true;
+    if (it >= 2 && rmax > 2.0 * rprev) return false;  // diverging
+    rprev = rmax;
+  }
+  return false;
+}
+
+// P = 2 Y Z Y^T with Y = C_o + C_v X and Z = (1 + X^T X)^-1; overwrites the A and X buffers and returns the buffer that
+// holds P (row stride ld), or nullptr if the Newton iteration for Z failed (A is lost then: the caller rebuilds it).
+//   A buffer: G, E (no x lds each) during the Newton iteration, then Y^T and W^T = (Y Z)^T ([k][mu], no x ld each);
+//   X buffer: Z, Z' (ping-pong), then P.
+// No XTB_ASSUME_SHARED hints in here: with them on G / E / Z nvcc 12.9 treated the whole function as unreachable for the
+// shared-memory variants (and dropped the `return true` of subspace_riccati with it) -- found in the PTX, not understood.
+template <int MODE>
+__device__ double* subspace_density(Ctx& c) {
+  const int n = c.n, ld = c.ld, no = c.sub.no, nv = c.sub.nv, lds = c.sub.lds;
+  const double* __restrict__ C = c.C;
+  const double* __restrict__ X = c.sub.X;
+  double* G = c.A;
+  double* E = c.A + (size_t)no * lds;
+  double* Zc = c.X;
+  double* Zn = c.X + (size_t)no * lds;
+  // G = 1 + X^T X
+  gemm_small<1, 1>(
+      no, no, nv, [&](int i, int b) { return X[b * lds + i]; }, [&](int b, int j) { return X[b * lds + j]; },
+      [&](int i, int j, double v) { G[i * lds + j] = (i == j) ? 1.0 + v : v; });
+  if (c.sub.zvalid)
+    for (int t = threadIdx.x; t < no * lds; t += NT) Zc[t] = c.sub.Zg[t];
+  __syncthreads();
+  bool ok = false;
+  for (int it = 0; it < 12; ++it) {
+    if (!c.sub.zvalid) {  // Z0 = 2 - G = 1 - X^T X: residual (X^T X)^2
+      for (int t = threadIdx.x; t < no * no; t += NT) {
+        const int i = t / no, j = t - i * no;
+        Zc[i * lds + j] = (i == j ? 2.0 : 0.0) - G[i * lds + j];
+      }
+      c.sub.zvalid = true;
+      __syncthreads();
+    }
+    double emax = 0.0;
+    gemm_small<1, 1>(
+        no, no, no, [&](int i, int k) { return G[i * lds + k]; }, [&](int k, int j) { return Zc[k * lds + j]; },
+        [&](int i, int j, double v) {
+          const double e = (i == j ? 1.0 : 0.0) - v;
+          E[i * lds + j] = e;
+          emax = fmax(emax, fabs(e));
+        });
+    emax = block_max(emax, c.red);  // (its barriers order the E stores before the next GEMM)
+    if (emax <= 1e-12) { ok = true; break; }
+    if (!(emax < 0.5)) {
+      if (it > 0) break;       // the cold start does not contract either: give up
+      c.sub.zvalid = false;    // warm start too far off: restart from Z0
+      continue;
+    }
+    gemm_small<1, 1>(
+        no, no, no, [&](int i, int k) { return Zc[i * lds + k]; }, [&](int k, int j) { return E[k * lds + j]; },
+        [&](int i, int j, double v) { Zn[i * lds + j] = Zc[i * lds + j] + v; });
+    __syncthreads();
+    double* t = Zc; Zc = Zn; Zn = t;
+    ++c.sub.nnewt;
+  }
+  if (!ok) {
+    c.sub.zvalid = false;
+    return nullptr;
+  }
+  for (int t = threadIdx.x; t < no * no; t += NT) {
+    const int i = t / no, j = t - i * no;
+    c.sub.Zg[i * lds + j] = Zc[i * lds + j];
+  }
+  // Yt[k][mu] = C[mu][k] + sum_b X[b][k] C[mu][no + b]
+  double* Yt = c.A;
+  double* Wt = c.A + (size_t)no * ld;
+  gemm_small<1, 2>(
+      no, n, nv, [&](int k, int b) { return X[b * lds + k]; }, [&](int b, int mu) { return C[(size_t)mu * ld + no + b]; },
+      [&](int k, int mu, double v) { Yt[(size_t)k * ld + mu] = v + C[(size_t)mu * ld + k]; });
+  __syncthreads();
+  // Wt[k][mu] = sum_j Z[j][k] Yt[j][mu]
+  gemm_small<1, 2>(
+      no, n, no, [&](int k, int j) { return Zc[j * lds + k]; }, [&](int j, int mu) { return Yt[(size_t)j * ld + mu]; },
+      [&](int k, int mu, double v) { Wt[(size_t)k * ld + mu] = v; });
+  __syncthreads();
+  // P[mu][nu] = 2 sum_k Wt[k][mu] Yt[k][nu]  -> X buffer (Z is dead)
+  double* Pb = c.X;
+  gemm_small<2, 2>(
+      n, n, no, [&](int mu, int k) { return Wt[(size_t)k * ld + mu]; }, [&](int k, int nu) { return Yt[(size_t)k * ld + nu]; },
+      [&](int mu, int nu, double v) { Pb[(size_t)mu * ld + nu] = 2.0 * v; });
+  __syncthreads();
+  return Pb;
+}
+
+}  // namespace

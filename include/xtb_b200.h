@@ -92,6 +92,9 @@ typedef struct xtb_scf_opts {
   int32_t use_smem;         /* kernel variant: 1 = C, A, X matrices in shared memory; 2 = hybrid (A in shared memory, C and X in the
                                workspace); 0 = all in the workspace.  The host checks capacity (xtb_scf_smem_bytes_mode) */
   int32_t jacobi_max_sweeps;/* 30 */
+  int32_t subspace;         /* 1: intermediate SCF map evaluations of closed-shell molecules with a certified gap >= subspace_gap kT
+                               take the occupied-subspace (Riccati) solve instead of the full eigendecomposition; 0: always full */
+  int32_t subspace_maxiter; /* 16: fixed-point iterations before falling back to a Jacobi sweep */
   double damp;              /* 0.5 */
   double damp_init;         /* 0.1 */
   double diag_offset;       /* 0.01 */
@@ -101,6 +104,8 @@ typedef struct xtb_scf_opts {
   double fermi_thresh;      /* sqrt(eps) */
   double jacobi_tol;        /* 1e-13: max |off-diagonal| of the final solve */
   double jacobi_tol_iter;   /* 2e-9: the same for intermediate SCF map evaluations */
+  double subspace_tol;      /* 1e-10: max |Riccati residual| (Eh) of the occupied-subspace solve */
+  double subspace_gap;      /* 60: certified HOMO-LUMO gap in units of kT below which occupations are not taken as integer */
   /* optional size bucket: this launch handles molecules mol_list[0..list_len) only (device pointer; NULL = all).
    * list_*_max are the maxima over the bucket (they size the shared-memory layout). */
   const int32_t* mol_list;
