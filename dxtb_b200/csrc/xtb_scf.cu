@@ -26,7 +26,7 @@ namespace {
 // is S-orthonormal only to cond(S) eps and the Jacobi rotations accumulated over the SCF let it drift further; the defect
 // d enters the energy as sum_k f_k eps_k d_kk (3e-10 Eh for the 550-AO vancoh2, 1e-8 Eh for 3104 AOs).  Uses A and X.
 template <int MODE>
-__device__ void reorthonormalize(Ctx& c) {
+XTB_CTX_FN void reorthonormalize(Ctx& c) {
   const int n = c.n, ne = c.ne, ld = c.ld;
   constexpr bool AS = MODE != 0, CS = MODE == 1;
   for (int t = threadIdx.x; t < ne * ld; t += NT) {
@@ -53,9 +53,9 @@ __device__ void reorthonormalize(Ctx& c) {
   gemm_tn<CS, AS>(ne, ne, c.X, c.A, ld, c.C, ld, ne);  // C = C M
 }
 
-// A = C^T F C with F = H0 - 1/2 S o (v_i + v_j), symmetrised, pad rows / columns exactly zero (X buffer: F C).
+// A = C^T F C with F = H0 - 1/2 S o (v_i + v_j), exactly symmetric, pad rows / columns exactly zero (X buffer: F C).
 template <int MODE>
-__device__ void build_projected_fock(Ctx& c, const double* __restrict__ v) {
+XTB_CTX_FN void build_projected_fock(Ctx& c, const double* __restrict__ v) {
   const int n = c.n, ne = c.ne, ld = c.ld;
   constexpr bool AS = MODE != 0, CS = MODE == 1;  // address space of the A buffer / of the C and X buffers
   // F = H0 - 1/2 S (v_i + v_j)   -> A buffer (symmetric, zero padded)
@@ -70,21 +70,11 @@ __device__ void build_projected_fock(Ctx& c, const double* __restrict__ v) {
   }
   __syncthreads();
   gemm_tn<AS, CS>(ne, ne, c.A, c.C, ld, c.X, ld, ne);  // X = F C   (F symmetric)
-  gemm_tn<CS, CS>(ne, ne, c.C, c.X, ld, c.A, ld, ne);  // A = C^T X
-  // symmetrise (round-off) and keep the pad row/column exactly zero
-  for (int t = threadIdx.x; t < ne * ne; t += NT) {
-    const int i = t / ne, j = t - i * ne;
-    if (i < j) {
-      const double a = (i < n && j < n) ? 0.5 * (c.A[(size_t)i * ld + j] + c.A[(size_t)j * ld + i]) : 0.0;
-      c.A[(size_t)i * ld + j] = a;
-      c.A[(size_t)j * ld + i] = a;
-    }
-  }
-  __syncthreads();
+  gemm_tn_sym<CS, CS, AS>(ne, n, c.C, c.X, ld, c.A);   // A = C^T X: lower tiles computed and mirrored, padding exactly zero
 }
 
 template <int MODE>
-__device__ int jacobi_mode(Ctx& c, double tol, int maxsweeps) {
+XTB_CTX_FN int jacobi_mode(Ctx& c, double tol, int maxsweeps) {
   constexpr bool AS = MODE != 0, CS = MODE == 1;
 #ifdef XTB_PROFILE_PHASES
   const long long tj0 = clock64();
@@ -103,30 +93,36 @@ __device__ int jacobi_mode(Ctx& c, double tol, int maxsweeps) {
 // Returns the electronic free energy of this solve (0 on the occupied-subspace path, whose occupations are integer).
 // final_solve: the solve that defines the results -- always the full eigendecomposition.
 template <int MODE>
-__device__ double fcn(Ctx& c, const double* __restrict__ v, const xtb_scf_opts& o, double nel_a, double nel_b, double jtol,
+XTB_CTX_FN double fcn(Ctx& c, const double* __restrict__ v, const xtb_scf_opts& o, double nel_a, double nel_b, double jtol,
                       bool final_solve) {
   const int n = c.n, ne = c.ne, ld = c.ld;
   constexpr bool CS = MODE == 1;
-#ifdef XTB_PROFILE_PHASES
-  const long long tf0 = clock64();
-#endif
-  build_projected_fock<MODE>(c, v);
-#ifdef XTB_PROFILE_PHASES
-  c.tfock += clock64() - tf0;
-#endif
   const double* Pb = c.A;  // buffer that holds the density after the solve
-  bool fast = false, diagonal = false;
+  bool fast = false;
   double g = 0.0;
-  if (!final_solve && c.sub.eligible) {
-    // occupied-subspace path (xtb_scf_subspace.cuh): Jacobi sweeps only until the gap between the two diagonal blocks is
-    // certified, then the Riccati fixed point for the occupied subspace
-    int sweeps_here = 0;
-    for (;;) {
+  // Occupied-subspace path (xtb_scf_subspace.cuh): Jacobi sweeps only until the gap between the two diagonal blocks is
+  // certified, then the Riccati fixed point for the occupied subspace.  Otherwise (final solve, open shell, small gap):
+  // sweeps until A is diagonal.  One loop, so that the projected Fock build and the Jacobi solver have ONE call site each.
+  bool try_sub = !final_solve && c.sub.eligible, rebuild = true;
+  int sweeps_here = 0;
+  for (;;) {
+    if (rebuild) {
+#ifdef XTB_PROFILE_PHASES
+      const long long tf0 = clock64();
+#endif
+      build_projected_fock<MODE>(c, v);
+#ifdef XTB_PROFILE_PHASES
+      c.tfock += clock64() - tf0;
+#endif
+      rebuild = false;
+    }
+    if (try_sub) {
       bool needs_perm;
 #ifdef XTB_PROFILE_PHASES
       const long long tc0 = clock64();
 #endif
-      const double gapc = subspace_certify(c, c.A, needs_perm);
+      double gapc = c.sub.layout ? subspace_certify<false>(c, c.A, needs_perm) : -1.0;
+      if (gapc < c.sub.gapmin) gapc = subspace_certify<true>(c, c.A, needs_perm);  // (re)classify by the ranks of the diagonal
 #ifdef XTB_PROFILE_PHASES
       c.tcert += clock64() - tc0;
 #endif
@@ -138,6 +134,7 @@ __device__ double fcn(Ctx& c, const double* __restrict__ v, const xtb_scf_opts& 
           subspace_permute(c);
           c.sub.xvalid = false;
         }
+        c.sub.layout = true;
 #ifdef XTB_PROFILE_PHASES
         const long long ts0 = clock64();
 #endif
@@ -158,19 +155,22 @@ __device__ double fcn(Ctx& c, const double* __restrict__ v, const xtb_scf_opts& 
           ++c.sub.nfast;
           break;
         }
-        if (ok) build_projected_fock<MODE>(c, v);  // the density step overwrote A before it failed
+        if (ok) {  // the density step overwrote A before it failed (not seen in practice): this molecule diagonalises from now on
+          c.sub.eligible = try_sub = false;
+          rebuild = true;
+          continue;
+        }
       }
-      if (sweeps_here >= o.jacobi_max_sweeps) break;  // the full solve below reports the failure
-      const int sw = jacobi_mode<MODE>(c, jtol, 1);
-      sweeps_here += sw < 0 ? -sw : sw;
-      if (sw >= 0) { diagonal = true; break; }  // converged: finish on the standard path
+    }
+    const int sw = jacobi_mode<MODE>(c, jtol, try_sub ? 1 : o.jacobi_max_sweeps);
+    sweeps_here += sw < 0 ? -sw : sw;
+    if (sw >= 0) break;  // A is diagonal: finish on the standard path
+    if (!try_sub || sweeps_here >= o.jacobi_max_sweeps) {
+      c.status |= XTB_STATUS_JACOBI_NOT_CONVERGED;
+      break;
     }
   }
   if (!fast) {
-    if (!diagonal) {
-      const int sw = jacobi_mode<MODE>(c, jtol, o.jacobi_max_sweeps);
-      if (sw < 0) c.status |= XTB_STATUS_JACOBI_NOT_CONVERGED;
-    }
     for (int k = threadIdx.x; k < n; k += NT) c.eps[k] = c.A[(size_t)k * ld + k];
     __syncthreads();
     g = fermi_fill(c, nel_a, nel_b, o);
@@ -202,13 +202,17 @@ __device__ double fcn(Ctx& c, const double* __restrict__ v, const xtb_scf_opts& 
     const double* sr = c.S + (size_t)mu * n;
     const double* hr = c.H0 + (size_t)mu * n;
     double pop = 0.0, e = 0.0;
-    for (int nu = lane; nu < n; nu += 32) {
-      const double p = pr[nu];
-      pop = fma(p, sr[nu], pop);
-      e = fma(p, hr[nu], e);
+    if (final_solve) {
+      for (int nu = lane; nu < n; nu += 32) {
+        const double p = pr[nu];
+        pop = fma(p, sr[nu], pop);
+        e = fma(p, hr[nu], e);
+      }
+      e = warp_sum(e);
+    } else {  // the energies of intermediate iterations are never used
+      for (int nu = lane; nu < n; nu += 32) pop = fma(pr[nu], sr[nu], pop);
     }
     pop = warp_sum(pop);
-    e = warp_sum(e);
     if (lane == 0) {
       c.q[mu] = c.n0[mu] - pop;
       c.eorb[mu] = e;
@@ -316,16 +320,21 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
     sb.no = (int)rint(nel_a);
     sb.nv = c.n - sb.no;
     sb.lds = ((sb.no + 15) & ~15) + 4;
-    sb.xvalid = sb.zvalid = false;
+    sb.xvalid = sb.zvalid = sb.layout = false;
     sb.nfast = sb.nric = sb.nnewt = 0;
     sb.gapmin = fmax(o.subspace_gap * o.kt, 0.02);
     sb.eligible = o.subspace != 0 && o.maxiter > 0 && nel_a == nel_b && fabs(nel_a - (double)sb.no) < 1e-9 && sb.no >= 1 && sb.nv >= 1 &&
                   2 * sb.no <= c.ne && c.ne >= 48;
-    sb.Zg = persist;                                // [no][lds]
-    sb.X = persist + (size_t)sb.no * sb.lds;        // [nv][lds];  (no + nv) lds <= n (n + 19)
+    sb.Zg = persist;  // [no][lds]
+    // X [nv][lds]: in the shared-memory variant the Jacobi scratch (free between sweeps), else the workspace
+    // ((no + nv) lds <= n (n + 19)).  MODE 1 must never see the workspace pointer here: XTB_ASSUME_SHARED(X) in
+    // subspace_riccati propagates the address space to EVERY source of the pointer (a select between the two made nvcc
+    // treat the whole workspace region, Zg included, as shared memory: memcheck "invalid __shared__ write").
     if (MODE == 1) {
-      if (sb.nv * sb.lds <= jcap) sb.X = c.jq;      // shared memory: the Jacobi scratch is free between sweeps
-      else sb.eligible = false;
+      sb.X = c.jq;
+      if (sb.nv * sb.lds > jcap) sb.eligible = false;
+    } else {
+      sb.X = persist + (size_t)sb.no * sb.lds;
     }
   }
 
@@ -336,8 +345,13 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
   }
   // S-orthonormal start basis C0 = L^{-T} from the Cholesky factor S = L L^T (done once; the reference
   // re-factorises S in every iteration inside storch.eighb, scf/unrolling/base.py:141-175)
+#ifdef XTB_PROFILE_PHASES
+  const long long tc0 = clock64();
+#endif
   if (!cholesky_start_basis<MODE>(c)) c.status |= XTB_STATUS_S_NOT_POSDEF;
-  reorthonormalize<MODE>(c);
+#ifdef XTB_PROFILE_PHASES
+  if (threadIdx.x == 0 && blockIdx.x == 0) printf("   Cholesky start basis %lld\n", clock64() - tc0);
+#endif
 
   // guess: atomic charges spread equally over shells, then over the AOs of a shell (scf/guess.py:122-182)
   for (int mu = threadIdx.x; mu < n; mu += NT) {
@@ -351,24 +365,36 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
   Mixer mx;
   mx.step = 0;
   mx.head = 0;
-  int iters = 1;
-  bool converged = true;
-  // intermediate map evaluations only steer the SCF trajectory: a looser eigensolver tolerance saves the last
-  // (verification) sweep; the final solve that defines charges / energies / P / W uses the tight one
-  double g = fcn<MODE>(c, c.v, o, nel_a, nel_b, o.maxiter > 0 ? o.jacobi_tol_iter : o.jacobi_tol, o.maxiter <= 0);  // outside the loop (unrolling/default.py:81)
-  if (o.maxiter > 0) {
-    converged = false;
-    mix(c, mx, o, sm_theta);  // mix_guess (unrolling/default.py:93-94); convergence is not tested here
-    for (int it = 0; it < o.maxiter; ++it) {
-      g = fcn<MODE>(c, c.v, o, nel_a, nel_b, o.jacobi_tol_iter, false);
-      ++iters;
-      if (mix(c, mx, o, sm_theta)) { converged = true; break; }
+  int iters = 0;
+  bool converged = o.maxiter <= 0;
+  double g = 0.0;
+  // scf/unrolling/default.py:71-136 as ONE loop (the map evaluation, the mixer and the re-orthonormalisation have a single call
+  // site each, see XTB_CTX_FN): stage 0 = the evaluation outside the reference's loop (default.py:81) followed by mix_guess
+  // (default.py:93-94, convergence not tested), stage 1 = the iterations, stage 2 = converged_to_charges: one more solve with
+  // the UN-MIXED potential (scf/base.py:497-501, default.py:111-114), which defines the results.
+  // Intermediate map evaluations only steer the SCF trajectory: a looser eigensolver tolerance saves the last (verification)
+  // sweep; the final solve that defines charges / energies / P / W uses the tight one.
+  for (int stage = 0, it = 0;;) {
+    const bool final_solve = stage == 2 || o.maxiter <= 0;
+    if (stage == 2) {
+      for (int k = threadIdx.x; k < n; k += NT) c.v[k] = c.vnew[k];
+      __syncthreads();
     }
-    // converged_to_charges: one more solve with the UN-MIXED potential (scf/base.py:497-501, default.py:111-114)
-    for (int k = threadIdx.x; k < n; k += NT) c.v[k] = c.vnew[k];
-    __syncthreads();
-    reorthonormalize<MODE>(c);  // remove the drift of the accumulated rotations before the solve that defines the results
-    g = fcn<MODE>(c, c.v, o, nel_a, nel_b, o.jacobi_tol, true);
+    // one Newton-Schulz step on the Cholesky start basis, and again before the solve that defines the results (removes the
+    // drift of the accumulated rotations)
+    if (stage != 1) reorthonormalize<MODE>(c);
+    g = fcn<MODE>(c, c.v, o, nel_a, nel_b, final_solve ? o.jacobi_tol : o.jacobi_tol_iter, final_solve);
+    if (stage != 2) ++iters;
+    if (final_solve) break;
+    const bool conv = mix(c, mx, o, sm_theta);
+    if (stage == 0) {
+      stage = 1;
+    } else if (conv) {
+      converged = true;
+      stage = 2;
+    } else if (++it >= o.maxiter) {
+      stage = 2;
+    }
   }
   if (!converged) c.status |= XTB_STATUS_SCF_NOT_CONVERGED;
 

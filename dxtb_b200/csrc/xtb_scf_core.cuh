@@ -30,6 +30,7 @@ constexpr int NT = XTB_NT;  // threads per CTA
 struct Subspace {
   bool eligible;   // closed shell with an integer number of doubly occupied orbitals and room for the scratch layout
   bool xvalid;     // X belongs to the current basis C (reset by every Jacobi sweep / permutation)
+  bool layout;     // the basis has been put in occupied-first order at least once (cheap certificate first)
   bool zvalid;     // Zg holds (1 + X^T X)^-1 of an earlier X in the same basis (warm start of the Newton iteration)
   int no, nv, lds; // occupied / virtual orbitals, leading dimension of the no-column matrices (== 4 mod 16)
   double gapmin;   // certified HOMO-LUMO gap required for integer occupations
@@ -62,6 +63,11 @@ struct Ctx {
   double ef[2];                  // Fermi level per spin channel of the last fermi_fill (scf_response)
   bool spin_on[2];               // channel holds electrons
 };
+
+// Every function that takes the per-molecule context is force-inlined: one call that is not inlined puts the whole Ctx (60
+// pointers) into local memory and every c.xyz access of the kernel becomes a stack load (seen in the SASS when fcn<> stopped
+// being inlined at its three call sites).  The big ones (fcn, jacobi) have a single call site.
+#define XTB_CTX_FN __device__ __forceinline__
 
 // Address-space hint: lets the compiler emit LDS/STS (32-bit addressing) instead of generic LD/ST.
 #define XTB_ASSUME_SHARED(ptr) __builtin_assume(__isShared(ptr))
@@ -122,6 +128,55 @@ __device__ void gemm_tn(int ne, int K, const double* __restrict__ L, const doubl
   __syncthreads();
 }
 
+// Symmetric product Out = L^T R for operands with L^T R == (L^T R)^T in exact arithmetic (A = C^T (F C)): only the tiles on and
+// below the diagonal are computed (15 instead of 25 for ne = 80: one round of the 16 warps instead of two) and mirrored, so Out
+// is EXACTLY symmetric; rows / columns >= n (padding) are written as exact zeros.
+template <bool LS, bool RS, bool OS>
+__device__ void gemm_tn_sym(int ne, int n, const double* __restrict__ L, const double* __restrict__ R, int ld, double* __restrict__ Out) {
+  if (LS) XTB_ASSUME_SHARED(L);
+  if (RS) XTB_ASSUME_SHARED(R);
+  if (OS) XTB_ASSUME_SHARED(Out);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, tg = lane & 3;
+  const int nt = ne >> 4;
+  for (int t = warp; t < nt * (nt + 1) / 2; t += NT / 32) {
+    int ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+    while (ti * (ti + 1) / 2 > t) --ti;
+    const int tj = t - ti * (ti + 1) / 2;  // tj <= ti
+    const int i0 = ti << 4, j0 = tj << 4;
+    double d[2][2][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) d[a][b][0] = d[a][b][1] = 0.0;
+    for (int k0 = 0; k0 < ne; k0 += 4) {
+      const double* lr = L + (size_t)(k0 + tg) * ld + i0 + g;
+      const double* rr = R + (size_t)(k0 + tg) * ld + j0 + g;
+      const double a0 = lr[0], a1 = lr[8];
+      const double b0 = rr[0], b1 = rr[8];
+      dmma884(d[0][0][0], d[0][0][1], a0, b0);
+      dmma884(d[0][1][0], d[0][1][1], a0, b1);
+      dmma884(d[1][0][0], d[1][0][1], a1, b0);
+      dmma884(d[1][1][0], d[1][1][1], a1, b1);
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int i = i0 + 8 * a + g, j = j0 + 8 * b + 2 * tg + e;
+          if (ti != tj || i >= j) {
+            const double v = (i < n && j < n) ? d[a][b][e] : 0.0;
+            Out[(size_t)i * ld + j] = v;
+            Out[(size_t)j * ld + i] = v;
+          }
+        }
+  }
+  __syncthreads();
+}
+
 #ifndef XTB_DEFER_NBP_MAX
 #define XTB_DEFER_NBP_MAX 16
 #endif
@@ -164,7 +219,7 @@ XTB_DEV int bp_index(int I, int J, int l) { return (l < JB ? I * JB : J * JB - J
 // Compared with rotating the full matrix after every scalar rotation round this moves A and V through
 // shared memory ~10x instead of ~80x per sweep.  Returns the number of sweeps, or -sweeps if not converged.
 template <bool AS, bool VS, bool DEFER = false>
-__device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, int nrow, double tol, int maxsweeps) {
+XTB_CTX_FN int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, int nrow, double tol, int maxsweeps) {
   const int ne = c.ne, ld = c.ld;
   const int nblk = ne / JB, nbp = nblk / 2, ntile = ne / 8;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -530,7 +585,7 @@ __device__ int jacobi(Ctx& c, double* __restrict__ A, double* __restrict__ V, in
 
 // Fermi smearing, both spin channels in lockstep (wavefunction/filling.py:201-366).
 // focc[k] = f_alpha + f_beta; returns G = kT sum ln(f^f (1-f)^(1-f)) (scf/base.py:586-594).
-__device__ double fermi_fill(Ctx& c, double nel_a, double nel_b, const xtb_scf_opts& o) {
+XTB_CTX_FN double fermi_fill(Ctx& c, double nel_a, double nel_b, const xtb_scf_opts& o) {
   const int n = c.n;
   // rank sort of the eigenvalues (ascending; ties broken by index)
   for (int k = threadIdx.x; k < n; k += NT) {
@@ -624,7 +679,7 @@ __device__ double fermi_fill(Ctx& c, double nel_a, double nel_b, const xtb_scf_o
 }
 
 // q (orbital charges) -> shell/atom charges -> potential vout (scf/base.py:702-727, interactions/base.py:134-181)
-__device__ void potential(Ctx& c, const double* __restrict__ q, double* __restrict__ vout) {
+XTB_CTX_FN void potential(Ctx& c, const double* __restrict__ q, double* __restrict__ vout) {
   for (int a = threadIdx.x; a < c.na; a += NT) {
     const int s0 = c.at_sh0[a], nsa = c.at_nsh[a];
     double qa = 0.0;
@@ -659,7 +714,7 @@ __device__ void potential(Ctx& c, const double* __restrict__ q, double* __restri
 // In-CTA right-looking Cholesky S = L L^T (lower triangle, in the A buffer), X = L^{-1} by forward substitution
 // (thread per column, X buffer), C = X^T.  Returns false if S is not positive definite.
 template <int MODE>
-__device__ bool cholesky_start_basis(Ctx& c) {
+XTB_CTX_FN bool cholesky_start_basis(Ctx& c) {
   const int n = c.n, ne = c.ne, ld = c.ld;
   double* A = c.A; double* X = c.X; double* C = c.C; double* lk = c.srt;
   if (MODE != 0) XTB_ASSUME_SHARED(A);
@@ -746,7 +801,7 @@ struct Mixer {
 
 // Anderson / simple mixing (mixer/anderson.py:163-317, mixer/simple.py:88-151).  x_old is in c.v, x_new in
 // c.vnew; the mixed vector is written to c.v.  Returns true if converged (mixer/base.py:229-256).
-__device__ bool mix(Ctx& c, Mixer& mx, const xtb_scf_opts& o, double* sm_theta) {
+XTB_CTX_FN bool mix(Ctx& c, Mixer& mx, const xtb_scf_opts& o, double* sm_theta) {
   const int n = c.n, G1 = o.generations + 1;
   auto slot = [&](int i) { return (mx.head + i) % G1; };
   double* f0 = c.fh + (size_t)slot(0) * n;
@@ -853,7 +908,7 @@ constexpr int kResponseMaxIter = 12;
 constexpr double kResponseTol = 1e-8;  // max-norm of the potential-space residual (the accepted iterate is ~4x better); force error of that size
 
 // w = K y: shell/atom sums of y, then gamma y_sh + 2 Gamma q_A y_A (linearised `potential`); leaves y_sh in c.qsh
-__device__ void potential_lin(Ctx& c, const double* __restrict__ y, const double* __restrict__ qat_final, double* __restrict__ wout) {
+XTB_CTX_FN void potential_lin(Ctx& c, const double* __restrict__ y, const double* __restrict__ qat_final, double* __restrict__ wout) {
   for (int a = threadIdx.x; a < c.na; a += NT) {
     const int s0 = c.at_sh0[a], nsa = c.at_nsh[a];
     double ya = 0.0;
@@ -897,7 +952,7 @@ struct RespBuf {
 
 // A <- Zt (WMAT = false) or ZWt (WMAT = true) of the perturbation w, in the eigenvector basis
 template <int MODE, bool WMAT>
-__device__ void response_zt(Ctx& c, const RespBuf& rb, const double* __restrict__ w, const double* __restrict__ fp0,
+XTB_CTX_FN void response_zt(Ctx& c, const RespBuf& rb, const double* __restrict__ w, const double* __restrict__ fp0,
                             const double* __restrict__ fp1) {
   const int n = c.n, ne = c.ne, ld = c.ld;
   constexpr bool AS = MODE != 0, CS = MODE == 1;
@@ -943,7 +998,7 @@ __device__ void response_zt(Ctx& c, const RespBuf& rb, const double* __restrict_
 
 // out[mu] = add[mu] + chi w = add[mu] - sum_q (C Zt)[mu][q] SC[mu][q]
 template <int MODE>
-__device__ void response_charges(Ctx& c, const RespBuf& rb, const double* __restrict__ w, const double* __restrict__ fp0,
+XTB_CTX_FN void response_charges(Ctx& c, const RespBuf& rb, const double* __restrict__ w, const double* __restrict__ fp0,
                                  const double* __restrict__ fp1, const double* __restrict__ add, double* __restrict__ out) {
   const int n = c.n, ne = c.ne, ld = c.ld;
   constexpr bool AS = MODE != 0, CS = MODE == 1;
@@ -963,7 +1018,7 @@ __device__ void response_charges(Ctx& c, const RespBuf& rb, const double* __rest
 
 // A <- Z_w (or ZW_w) in the AO basis: Z = C Zt C^T
 template <int MODE, bool WMAT>
-__device__ void response_density(Ctx& c, const RespBuf& rb, const double* __restrict__ w, const double* __restrict__ fp0,
+XTB_CTX_FN void response_density(Ctx& c, const RespBuf& rb, const double* __restrict__ w, const double* __restrict__ fp0,
                                  const double* __restrict__ fp1) {
   const int ne = c.ne, ld = c.ld;
   constexpr bool AS = MODE != 0, CS = MODE == 1;
@@ -978,7 +1033,7 @@ __device__ void response_density(Ctx& c, const RespBuf& rb, const double* __rest
 // from an empty history (re-using the SCF's own Anderson history as search directions was measured SLOWER: 12 instead of 8
 // applications of chi to 1e-9, its differences carry the non-linearity of the early SCF iterations).
 template <int MODE>
-__device__ void scf_response(Ctx& c, const xtb_scf_opts& o, const RespBuf& rb, const double* __restrict__ v_out_g,
+XTB_CTX_FN void scf_response(Ctx& c, const xtb_scf_opts& o, const RespBuf& rb, const double* __restrict__ v_out_g,
                              const double* __restrict__ qat_final, double* __restrict__ Pm, double* __restrict__ Wm,
                              double* __restrict__ v_grad, double* __restrict__ y_sh, double* sm_theta) {
   const int n = c.n, ne = c.ne, ld = c.ld;
@@ -1075,7 +1130,7 @@ __device__ void scf_response(Ctx& c, const xtb_scf_opts& o, const RespBuf& rb, c
 }
 
 // Per-molecule results of the converged SCF: charges, potential, orbital energies / occupations, atom-resolved energies.
-__device__ void emit_results(Ctx& c, const xtb_batch& b, int m, double g, int iters, double* __restrict__ q_orb, double* __restrict__ q_sh,
+XTB_CTX_FN void emit_results(Ctx& c, const xtb_batch& b, int m, double g, int iters, double* __restrict__ q_orb, double* __restrict__ q_sh,
                              double* __restrict__ q_at, double* __restrict__ v_orb, double* __restrict__ e_atom,
                              double* __restrict__ fenergy, double* __restrict__ emo, double* __restrict__ occ,
                              int32_t* __restrict__ iterations, int32_t* __restrict__ status) {

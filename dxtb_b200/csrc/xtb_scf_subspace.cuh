@@ -89,33 +89,39 @@ __device__ __forceinline__ void block_max2(double& a, double& b, double* red) {
   b = __shfl_sync(0xffffffffu, r, 16);
 }
 
-// Ranks of the diagonal of A (-> c.occl, diagonal -> c.eps) and the certified gap between the `no` lowest diagonal entries
-// and the rest (header comment).  needs_perm: the occupied class is not the first `no` columns.
-__device__ double subspace_certify(Ctx& c, const double* __restrict__ A, bool& needs_perm) {
+// Certified gap between the occupied and the virtual class of the diagonal of A (header comment; diagonal -> c.eps).
+// RANKED = false: classes by position (first `no` columns occupied) -- valid for ANY partition, cheap, used once the basis is
+// in occupied-first order.  RANKED = true: classes by the ranks of the diagonal (-> c.occl); needs_perm tells the caller
+// that the occupied class is not the first `no` columns.
+template <bool RANKED>
+XTB_CTX_FN double subspace_certify(Ctx& c, const double* __restrict__ A, bool& needs_perm) {
   const int n = c.n, ld = c.ld, no = c.sub.no;
   int* rank = c.occl;
   for (int k = threadIdx.x; k < n; k += NT) c.eps[k] = A[(size_t)k * ld + k];
   __syncthreads();
-  int bad = 0;
-  for (int k = threadIdx.x; k < n; k += NT) {
-    const double e = c.eps[k];
-    int rk = 0;
-    for (int j = 0; j < n; ++j) {
-      const double ej = c.eps[j];
-      rk += (ej < e) || (ej == e && j < k);
+  needs_perm = false;
+  if (RANKED) {
+    int bad = 0;
+    for (int k = threadIdx.x; k < n; k += NT) {
+      const double e = c.eps[k];
+      int rk = 0;
+      for (int j = 0; j < n; ++j) {
+        const double ej = c.eps[j];
+        rk += (ej < e) || (ej == e && j < k);
+      }
+      rank[k] = rk;
+      bad |= (rk < no) != (k < no);
     }
-    rank[k] = rk;
-    bad |= (rk < no) != (k < no);
+    needs_perm = __syncthreads_or(bad) != 0;
   }
-  needs_perm = __syncthreads_or(bad) != 0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double hi = -1.0e300, nlo = -1.0e300;  // max over occupied rows of d + r;  max over virtual rows of -(d - r)
   for (int i = warp; i < n; i += NT / 32) {
     const double* row = A + (size_t)i * ld;
-    const bool oi = rank[i] < no;
+    const bool oi = (RANKED ? rank[i] : i) < no;
     double s = 0.0;
     for (int j = lane; j < n; j += 32)
-      if (j != i && (rank[j] < no) == oi) s += fabs(row[j]);
+      if (j != i && ((RANKED ? rank[j] : j) < no) == oi) s += fabs(row[j]);
     s = warp_sum(s);
     if (oi) hi = fmax(hi, c.eps[i] + s);
     else nlo = fmax(nlo, s - c.eps[i]);
@@ -126,7 +132,7 @@ __device__ double subspace_certify(Ctx& c, const double* __restrict__ A, bool& n
 
 // Sort the basis by the ranks in c.occl: column k of C -> column rank[k], A permuted on both sides, c.eps alike.
 // Uses the X buffer as the copy target.
-__device__ void subspace_permute(Ctx& c) {
+XTB_CTX_FN void subspace_permute(Ctx& c) {
   const int n = c.n, ne = c.ne, ld = c.ld;
   const int* rank = c.occl;
   for (int t = threadIdx.x; t < ne * ne; t += NT) {
@@ -156,7 +162,7 @@ __device__ void subspace_permute(Ctx& c) {
 // Fixed-point iteration of the Riccati equation in the occupied-first basis (A in the A buffer, its diagonal in c.eps,
 // T = A(:, v) X with Lambda = Aoo + Aov X in its first `no` rows in the X buffer).  Returns true when max |R| <= tol.
 template <int MODE>
-__device__ bool subspace_riccati(Ctx& c, const xtb_scf_opts& o) {
+XTB_CTX_FN bool subspace_riccati(Ctx& c, const xtb_scf_opts& o) {
   const int n = c.n, ld = c.ld, no = c.sub.no, nv = c.sub.nv, lds = c.sub.lds;
   const double* __restrict__ A = c.A;
   double* __restrict__ T = c.X;
@@ -200,7 +206,10 @@ __device__ bool subspace_riccati(Ctx& c, const xtb_scf_opts& o) {
     if (threadIdx.x == 0 && blockIdx.x == 0) printf("    riccati it %d: max|R| %.3e max|X| %.3e\n", it, rmax, xmax);
 #endif
     if (!(xmax < 1.0) || !(rmax < 1.0e300)) return false;  // large rotation / NaN: not the regime of this path
-    if (rmax <= o.subspace_tol) return true;
+    // X already carries the update computed from this residual: its own residual is ~ (contraction rate) x rmax.  Stop when
+    // that prediction (observed rate of the last step, at most 1/2, safety factor 2) meets the tolerance.
+    const double rate = it > 0 ? fmin(0.5, 2.0 * rmax / rprev) : 1.0;
+    if (rmax * rate <= o.subspace_tol) return true;
     if (it >= 2 && rmax > 2.0 * rprev) return false;  // diverging
     rprev = rmax;
   }
@@ -214,7 +223,7 @@ __device__ bool subspace_riccati(Ctx& c, const xtb_scf_opts& o) {
 // No XTB_ASSUME_SHARED hints in here: with them on G / E / Z nvcc 12.9 treated the whole function as unreachable for the
 // shared-memory variants (and dropped the `return true` of subspace_riccati with it) -- found in the PTX, not understood.
 template <int MODE>
-__device__ double* subspace_density(Ctx& c) {
+XTB_CTX_FN double* subspace_density(Ctx& c) {
   const int n = c.n, ld = c.ld, no = c.sub.no, nv = c.sub.nv, lds = c.sub.lds;
   const double* __restrict__ C = c.C;
   const double* __restrict__ X = c.sub.X;
@@ -260,6 +269,7 @@ __device__ double* subspace_density(Ctx& c) {
     __syncthreads();
     double* t = Zc; Zc = Zn; Zn = t;
     ++c.sub.nnewt;
+    if ((double)no * emax * emax <= 1e-13) { ok = true; break; }  // the new residual is E^2: no need to form it
   }
   if (!ok) {
     c.sub.zvalid = false;
