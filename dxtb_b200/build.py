@@ -13,8 +13,12 @@ ROOT = Path(__file__).resolve().parent
 CSRC = ROOT / "csrc"
 INCLUDE = ROOT.parent / "include"
 SO_PATH = ROOT / "_C.so"
+# secondary build of the SCF kernel (two CTAs per SM, developer knob DXTB_B200_2CTA).  Also tried: two CTAs of 256 threads
+# (-DXTB_NT=256 -DXTB_NGRP=8, 128 registers each, no spills) -- hybrid variant for caffeine 21.4 ms against 14.5 ms for the
+# shared-memory variant at 1 CTA/SM (energy only, 1024 conformers), capsaicin 61.9 against 56.1 ms.
+SECONDARY_FLAGS = ["-DXTB_SECONDARY", "-DXTB_MINB=2", "-DXTB_JACOBI_SMALL_SIN=0.0"]
 # (source, object suffix, extra flags): xtb_scf.cu is built twice, see the comment at its top
-SOURCES = [("xtb_geometry.cu", "", []), ("xtb_integrals.cu", "", []), ("xtb_scf.cu", "", []), ("xtb_scf_large.cu", "", []), ("xtb_scf.cu", ".2cta", ["-DXTB_SECONDARY", "-DXTB_MINB=2", "-DXTB_JACOBI_SMALL_SIN=0.0"])]
+SOURCES = [("xtb_geometry.cu", "", []), ("xtb_integrals.cu", "", []), ("xtb_scf.cu", "", []), ("xtb_scf_large.cu", "", []), ("xtb_scf.cu", ".2cta", SECONDARY_FLAGS)]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "-diag-suppress", "177",

@@ -76,10 +76,24 @@ def _stream_ptr(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+def _scratch_buffer(scratch: "dict | None", name: str, numel: int, dev: torch.device) -> torch.Tensor:
+    """fp64 scratch that only lives inside one C call sequence on the current stream; reused across calls of a calculator
+    (keyed by the stream, so that single points enqueued on different streams never share it)."""
+    if scratch is None:
+        return torch.empty(numel, dtype=torch.float64, device=dev)
+    key = (name, torch.cuda.current_stream(dev).cuda_stream)
+    buf = scratch.get(key)
+    if buf is None or buf.numel() < numel or buf.device != dev:
+        buf = torch.empty(numel, dtype=torch.float64, device=dev)
+        scratch[key] = buf
+    return buf
+
+
 class _Workspace:
     """Per-call device buffers (all torch-owned; the C side never allocates)."""
 
-    def __init__(self, d: BatchDescriptor, want_density: bool, scf_opts: _abi.XtbScfOpts, need_global: bool = True):
+    def __init__(self, d: BatchDescriptor, want_density: bool, scf_opts: _abi.XtbScfOpts, need_global: bool = True,
+                 scratch: "dict | None" = None):
         dev, f64 = d.device, torch.float64
         # all zero-initialised fp64 outputs are views of ONE buffer (one fill launch instead of fourteen)
         sizes = [d.nat_tot] * 3 + [d.nat_tot if d.has_d3 else 0, d.nat_tot, int(d.struct.gam_total)] + [d.nao_tot] * 4 + \
@@ -95,7 +109,10 @@ class _Workspace:
         self.iterations, self.status = ints[: d.nb], ints[d.nb:]
         scf_opts.use_smem = 0 if need_global else 1  # sizes the matrix workspace of variants 0 and 2
         nbytes = _abi.lib().xtb_scf_workspace_bytes(d.ptr, _abi.C.addressof(scf_opts))
-        self.work = torch.empty(int(nbytes) // 8 + 1, dtype=f64, device=dev)
+        # pure scratch of xtb_scf_run (nothing in it outlives the call): kept on the calculator between single points.  A fresh
+        # several-hundred-MB torch.empty per call made the caching allocator split and re-malloc its large blocks for the
+        # first ~5 steps of a run (measured: 38 instead of 20 ms per 1024-caffeine step with --steps 5 --warmup 3).
+        self.work = _scratch_buffer(scratch, "scf_work", int(nbytes) // 8 + 1, dev)
         if want_density:
             self.P = torch.empty(d.struct.mat_total, dtype=f64, device=dev)
             self.W = torch.empty(d.struct.mat_total, dtype=f64, device=dev)
@@ -119,7 +136,7 @@ class _SinglePoint(torch.autograd.Function):
         if response:
             o.want_density = 2  # sizes the workspace for the response solver
         need_global = calc._use_smem_override in (0, 2) or any(bk["use_smem"] in (0, 2) for bk in calc._buckets)
-        ws = _Workspace(d, need_grad, o, need_global)
+        ws = _Workspace(d, need_grad, o, need_global, calc._scratch)
         excl = calc._exclude
         if response:
             ws.resp = torch.zeros(d.nao_tot + d.nsh_tot, dtype=torch.float64, device=d.device)
@@ -128,7 +145,7 @@ class _SinglePoint(torch.autograd.Function):
         if d.has_d3:
             _abi.check(lib.xtb_d3_fwd(d.ptr, pos.data_ptr(), ws.cn.data_ptr(), ws.d3w.data_ptr(), ws.e_disp.data_ptr(), st), "xtb_d3_fwd")
         if calc.opts["guess"] == "eeq":
-            eeq_work = torch.empty(int(d.struct.eeq_total) + 2 * (d.nat_tot + d.nb), dtype=torch.float64, device=d.device)
+            eeq_work = _scratch_buffer(calc._scratch, "eeq_work", int(d.struct.eeq_total) + 2 * (d.nat_tot + d.nb), d.device)
             _abi.check(lib.xtb_eeq_guess(d.ptr, pos.data_ptr(), chrg.data_ptr(), eeq_work.data_ptr(), ws.q0_at.data_ptr(), st), "xtb_eeq_guess")
             for m in d.eeq_large:  # molecules the batched one-CTA LU skips (XTB_EEQ_LARGE_NAT)
                 _abi.check(lib.xtb_eeq_guess_large(d.ptr, m, int(d.nat[m]), int(d.at_off[m]), int(d.eeq_off[m]), pos.data_ptr(),
@@ -302,6 +319,7 @@ class GFN1Calculator:
         self.scf_events: list | None = None
         self.scf_event_pool: list = []
         self._use_smem_override: int | None = None  # tests: force the global-memory variant
+        self._scratch: dict = {}  # call-local device scratch kept between single points (_scratch_buffer)
         self._prefer_hybrid = os.environ.get("DXTB_B200_PREFER_HYBRID", "0") != "0"
         self._large_min_nao = int(os.environ.get("DXTB_B200_LARGE_MIN_NAO", "1000000"))
         # up to this many molecules with nao >= 256 take the large-system path (several at a time, _run_large): measured on a

@@ -250,7 +250,7 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
   c.sweeps = 0;
   c.tp1 = c.tp2 = c.tjac = c.tsub = 0;
 #ifdef XTB_PROFILE_PHASES
-  c.tcert = c.tric = c.tden = c.tfock = c.tmull = 0;
+  c.tcert = c.tric = c.tden = c.tfock = c.tmull = c.tr1 = c.tr2 = c.tr3 = 0;
 #endif
 #ifdef XTB_PROFILE_PHASES
   const long long tk0 = clock64();
@@ -327,9 +327,9 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
                   2 * sb.no <= c.ne && c.ne >= 48;
     sb.Zg = persist;  // [no][lds]
     // X [nv][lds]: in the shared-memory variant the Jacobi scratch (free between sweeps), else the workspace
-    // ((no + nv) lds <= n (n + 19)).  MODE 1 must never see the workspace pointer here: XTB_ASSUME_SHARED(X) in
-    // subspace_riccati propagates the address space to EVERY source of the pointer (a select between the two made nvcc
-    // treat the whole workspace region, Zg included, as shared memory: memcheck "invalid __shared__ write").
+    // ((no + nv) lds <= n (n + 19)).  MODE 1 must never see the workspace pointer here: an address-space hint on X
+    // propagates to EVERY source of the pointer (with a select between the two nvcc treated the whole workspace region, Zg
+    // included, as shared memory: memcheck "invalid __shared__ write").
     if (MODE == 1) {
       sb.X = c.jq;
       if (sb.nv * sb.lds > jcap) sb.eligible = false;
@@ -404,8 +404,8 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
     printf("k_scf phases (cycles): total %lld  jacobi %lld  sub-problems %lld  pass %lld  sweeps %d  subspace %lld (%d map evaluations of %d, %d fixed-point, %d Newton iterations)\n",
            clock64() - tk0, c.tjac, c.tp1, c.tp2, c.sweeps, c.tsub, c.sub.nfast, iters, c.sub.nric, c.sub.nnewt);
   if (threadIdx.x == 0 && blockIdx.x == 0)
-    printf("   certify %lld  fixed point %lld  density %lld  | projected Fock (all map evaluations) %lld  Mulliken + potential %lld\n", c.tcert, c.tric, c.tden,
-           c.tfock, c.tmull);
+    printf("   certify %lld  fixed point %lld (T GEMM %lld, residual GEMM %lld, reduction + copy %lld)  density %lld  | projected Fock (all map evaluations) %lld  Mulliken + potential %lld\n",
+           c.tcert, c.tric, c.tr1, c.tr2, c.tr3, c.tden, c.tfock, c.tmull);
 #endif
   if (o.want_density) {
     double* Pm = Pout + b.mat_off[m];

@@ -52,7 +52,7 @@ struct Ctx {
   int ng;                        // Jacobi: number of 16x16 sub-problem copies = warps that solve sub-problems concurrently
   bool defer;                    // Jacobi: Q double buffered, V pass deferred into the next round's sub-problem phase
 #ifdef XTB_PROFILE_PHASES
-  long long tcert, tric, tden, tfock, tmull;
+  long long tcert, tric, tden, tfock, tmull, tr1, tr2, tr3;
 #endif
   long long tp1, tp2, tjac, tsub;  // XTB_PROFILE_PHASES: cycles in the sub-problem phase / rotation pass / whole eigensolver / subspace solve
   const int *ao_sh, *sh_atom, *at_sh0, *at_nsh, *sh_ao, *sh_l;

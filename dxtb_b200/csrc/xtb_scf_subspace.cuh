@@ -35,30 +35,38 @@ __device__ __forceinline__ void gemm_small(int M, int N, int K, LA la, RB rb, ST
   for (int t = warp; t < mt * nt; t += NT / 32) {
     const int ti = t / nt, tj = t - ti * nt;
     const int i0 = ti * 8 * TM, j0 = tj * 8 * TN;
-    double d[TM][TN][2];
+    // two accumulator sets (even / odd k steps): twice as many independent DMMA chains per warp -- these GEMMs are small
+    // (K = 40: ten dependent DMMAs per chain otherwise) and latency-bound, in the second tile round most schedulers hold
+    // one or two warps only
+    double d[2][TM][TN][2];
 #pragma unroll
-    for (int x = 0; x < TM; ++x)
-#pragma unroll
-      for (int y = 0; y < TN; ++y) d[x][y][0] = d[x][y][1] = 0.0;
-#pragma unroll 4
-    for (int k0 = 0; k0 < K; k0 += 4) {  // unrolled: the operand loads of four steps are in flight together (L2 latency in MODE 0 / 2)
-      const int k = k0 + tg;
-      const bool kv = k < K;
-      double a[TM], b[TN];
-#pragma unroll
-      for (int x = 0; x < TM; ++x) {
-        const int i = i0 + 8 * x + g;
-        a[x] = (kv && i < M) ? la(i, k) : 0.0;
-      }
-#pragma unroll
-      for (int y = 0; y < TN; ++y) {
-        const int j = j0 + 8 * y + g;
-        b[y] = (kv && j < N) ? rb(k, j) : 0.0;
-      }
+    for (int h = 0; h < 2; ++h)
 #pragma unroll
       for (int x = 0; x < TM; ++x)
 #pragma unroll
-        for (int y = 0; y < TN; ++y) dmma884(d[x][y][0], d[x][y][1], a[x], b[y]);
+        for (int y = 0; y < TN; ++y) d[h][x][y][0] = d[h][x][y][1] = 0.0;
+#pragma unroll 2
+    for (int k0 = 0; k0 < K; k0 += 8) {  // unrolled: the operand loads of four k steps are in flight together
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = k0 + 4 * h + tg;
+        const bool kv = k < K;
+        double a[TM], b[TN];
+#pragma unroll
+        for (int x = 0; x < TM; ++x) {
+          const int i = i0 + 8 * x + g;
+          a[x] = (kv && i < M) ? la(i, k) : 0.0;
+        }
+#pragma unroll
+        for (int y = 0; y < TN; ++y) {
+          const int j = j0 + 8 * y + g;
+          b[y] = (kv && j < N) ? rb(k, j) : 0.0;
+        }
+#pragma unroll
+        for (int x = 0; x < TM; ++x)
+#pragma unroll
+          for (int y = 0; y < TN; ++y) dmma884(d[h][x][y][0], d[h][x][y][1], a[x], b[y]);
+      }
     }
 #pragma unroll
     for (int x = 0; x < TM; ++x)
@@ -66,23 +74,32 @@ __device__ __forceinline__ void gemm_small(int M, int N, int K, LA la, RB rb, ST
       for (int y = 0; y < TN; ++y) {
         const int i = i0 + 8 * x + g, j = j0 + 8 * y + 2 * tg;
         if (i < M) {
-          if (j < N) st(i, j, d[x][y][0]);
-          if (j + 1 < N) st(i, j + 1, d[x][y][1]);
+          if (j < N) st(i, j, d[0][x][y][0] + d[1][x][y][0]);
+          if (j + 1 < N) st(i, j + 1, d[0][x][y][1] + d[1][x][y][1]);
         }
       }
   }
 }
 
-// Block-wide maxima of two values with one pair of barriers (NT = 512: 16 warps; `red` holds 32 doubles).
+// p, marked as a shared-memory pointer when SH (address-space conversion round trip: a definition, not an assumption --
+// XTB_ASSUME_SHARED on the pointers of subspace_density made nvcc 12.9 drop the function as unreachable).
+template <bool SH, class T>
+__device__ __forceinline__ T* in_shared(T* p) {
+  if (SH) return (T*)__cvta_shared_to_generic(__cvta_generic_to_shared(p));
+  return p;
+}
+
+// Block-wide maxima of two values with one pair of barriers (`red` holds 32 doubles; at most 16 warps).
 __device__ __forceinline__ void block_max2(double& a, double& b, double* red) {
-  static_assert(NT == 512, "block_max2 assumes 16 warps");
+  static_assert(NT <= 512, "block_max2 assumes at most 16 warps");
+  constexpr int NW = NT / 32;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   a = warp_max(a);
   b = warp_max(b);
   __syncthreads();
   if (lane == 0) { red[w] = a; red[16 + w] = b; }
   __syncthreads();
-  double r = red[lane];  // lanes 0-15: a of the 16 warps, lanes 16-31: b
+  double r = ((lane & 15) < NW) ? red[lane] : -1.0e300;  // lanes 0-15: a of the warps, lanes 16-31: b
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) r = fmax(r, __shfl_xor_sync(0xffffffffu, r, o));
   a = __shfl_sync(0xffffffffu, r, 0);
@@ -164,13 +181,10 @@ XTB_CTX_FN void subspace_permute(Ctx& c) {
 template <int MODE>
 XTB_CTX_FN bool subspace_riccati(Ctx& c, const xtb_scf_opts& o) {
   const int n = c.n, ld = c.ld, no = c.sub.no, nv = c.sub.nv, lds = c.sub.lds;
-  const double* __restrict__ A = c.A;
-  double* __restrict__ T = c.X;
-  double* __restrict__ X = c.sub.X;
-  const double* __restrict__ dg = c.eps;
-  if (MODE != 0) XTB_ASSUME_SHARED(A);
-  if (MODE == 1) { XTB_ASSUME_SHARED(T); XTB_ASSUME_SHARED(X); }
-  XTB_ASSUME_SHARED(dg);
+  const double* __restrict__ A = in_shared<MODE != 0>(c.A);
+  double* __restrict__ T = in_shared<MODE == 1>(c.X);
+  double* __restrict__ X = in_shared<MODE == 1>(c.sub.X);
+  const double* __restrict__ dg = in_shared<true>(c.eps);
   if (!c.sub.xvalid) {
     for (int t = threadIdx.x; t < nv * lds; t += NT) X[t] = 0.0;
     c.sub.xvalid = true;
@@ -179,11 +193,17 @@ XTB_CTX_FN bool subspace_riccati(Ctx& c, const xtb_scf_opts& o) {
   }
   double rprev = 1.0e300;
   for (int it = 0; it < o.subspace_maxiter; ++it) {
+#ifdef XTB_PROFILE_PHASES
+    const long long tq0 = clock64();
+#endif
     // T[r][i] = sum_b A[no + b][r] X[b][i]  (A symmetric);  rows r < no: + Aoo -> Lambda
     gemm_small<2, 1>(
         n, no, nv, [&](int r, int b) { return A[(size_t)(no + b) * ld + r]; }, [&](int b, int i) { return X[b * lds + i]; },
         [&](int r, int i, double v) { T[r * lds + i] = (r < no) ? v + A[(size_t)r * ld + i] : v; });
     __syncthreads();
+#ifdef XTB_PROFILE_PHASES
+    const long long tq1 = clock64();
+#endif
     // R = Avo + T1 - X Lambda;  X_new = X - R / (d_a - d_i) -> written over T1 (every element has one owner)
     double rmax = 0.0, xmax = 0.0;
     gemm_small<1, 1>(
@@ -195,6 +215,9 @@ XTB_CTX_FN bool subspace_riccati(Ctx& c, const xtb_scf_opts& o) {
           rmax = fmax(rmax, fabs(r));
           xmax = fmax(xmax, fabs(xn));
         });
+#ifdef XTB_PROFILE_PHASES
+    const long long tq2 = clock64();
+#endif
     block_max2(rmax, xmax, c.red);  // its barriers also order the X_new stores before the copy
     for (int t = threadIdx.x; t < nv * no; t += NT) {
       const int a = t / no, i = t - a * no;
@@ -202,6 +225,9 @@ XTB_CTX_FN bool subspace_riccati(Ctx& c, const xtb_scf_opts& o) {
     }
     __syncthreads();
     ++c.sub.nric;
+#ifdef XTB_PROFILE_PHASES
+    c.tr1 += tq1 - tq0; c.tr2 += tq2 - tq1; c.tr3 += clock64() - tq2;
+#endif
 #ifdef XTB_DEBUG_SUBSPACE
     if (threadIdx.x == 0 && blockIdx.x == 0) printf("    riccati it %d: max|R| %.3e max|X| %.3e\n", it, rmax, xmax);
 #endif
@@ -220,17 +246,19 @@ XTB_CTX_FN bool subspace_riccati(Ctx& c, const xtb_scf_opts& o) {
 // holds P (row stride ld), or nullptr if the Newton iteration for Z failed (A is lost then: the caller rebuilds it).
 //   A buffer: G, E (no x lds each) during the Newton iteration, then Y^T and W^T = (Y Z)^T ([k][mu], no x ld each);
 //   X buffer: Z, Z' (ping-pong), then P.
-// No XTB_ASSUME_SHARED hints in here: with them on G / E / Z nvcc 12.9 treated the whole function as unreachable for the
-// shared-memory variants (and dropped the `return true` of subspace_riccati with it) -- found in the PTX, not understood.
+// Shared-memory pointers are marked with in_shared<>, not XTB_ASSUME_SHARED: with assumptions on G / E / Z nvcc 12.9 treated
+// the whole function as unreachable for the shared-memory variants (and dropped the `return true` of subspace_riccati with
+// it) -- found in the PTX.
 template <int MODE>
 XTB_CTX_FN double* subspace_density(Ctx& c) {
   const int n = c.n, ld = c.ld, no = c.sub.no, nv = c.sub.nv, lds = c.sub.lds;
-  const double* __restrict__ C = c.C;
-  const double* __restrict__ X = c.sub.X;
-  double* G = c.A;
-  double* E = c.A + (size_t)no * lds;
-  double* Zc = c.X;
-  double* Zn = c.X + (size_t)no * lds;
+  constexpr bool AS = MODE != 0, CS = MODE == 1;
+  const double* __restrict__ C = in_shared<CS>(c.C);
+  const double* __restrict__ X = in_shared<CS>(c.sub.X);
+  double* G = in_shared<AS>(c.A);
+  double* E = G + (size_t)no * lds;
+  double* Zc = in_shared<CS>(c.X);
+  double* Zn = Zc + (size_t)no * lds;
   // G = 1 + X^T X
   gemm_small<1, 1>(
       no, no, nv, [&](int i, int b) { return X[b * lds + i]; }, [&](int b, int j) { return X[b * lds + j]; },
@@ -280,8 +308,8 @@ XTB_CTX_FN double* subspace_density(Ctx& c) {
     c.sub.Zg[i * lds + j] = Zc[i * lds + j];
   }
   // Yt[k][mu] = C[mu][k] + sum_b X[b][k] C[mu][no + b]
-  double* Yt = c.A;
-  double* Wt = c.A + (size_t)no * ld;
+  double* Yt = G;
+  double* Wt = G + (size_t)no * ld;
   gemm_small<1, 2>(
       no, n, nv, [&](int k, int b) { return X[b * lds + k]; }, [&](int b, int mu) { return C[(size_t)mu * ld + no + b]; },
       [&](int k, int mu, double v) { Yt[(size_t)k * ld + mu] = v + C[(size_t)mu * ld + k]; });
@@ -292,7 +320,7 @@ XTB_CTX_FN double* subspace_density(Ctx& c) {
       [&](int k, int mu, double v) { Wt[(size_t)k * ld + mu] = v; });
   __syncthreads();
   // P[mu][nu] = 2 sum_k Wt[k][mu] Yt[k][nu]  -> X buffer (Z is dead)
-  double* Pb = c.X;
+  double* Pb = in_shared<CS>(c.X);
   gemm_small<2, 2>(
       n, n, no, [&](int mu, int k) { return Wt[(size_t)k * ld + mu]; }, [&](int k, int nu) { return Yt[(size_t)k * ld + nu]; },
       [&](int mu, int nu, double v) { Pb[(size_t)mu * ld + nu] = 2.0 * v; });
