@@ -14,6 +14,7 @@
 // eigendecomposition S = U s U^T (any S-orthonormal basis gives the same SCF trajectory up to round-off).
 #include "xtb_scf_core.cuh"
 
+#include <cstdio>
 #include <mutex>
 #include <vector>
 
@@ -35,12 +36,17 @@ struct LargeState {  // device-resident scalars of one large-molecule SCF
   double ef[2];      // Fermi levels of the last solve (SCF response)
   double abar[2];    // Fermi-level shifts of the current response density
   int spin_on[2];
-  int pad[2];
+  int sub_bad, pad;  // occupied-subspace solve: the occupied class is not the first `no` columns
+  // maxima of the subspace kernels, stored biased by kSubBias and compared as raw bits: max over occupied rows of d + r,
+  // max over virtual rows of r - d (Gershgorin), max |Riccati residual|, max |X|, max |1 - G Z|
+  double sub_hi, sub_nlo, sub_rmax, sub_xmax, sub_emax;
 };
 
 struct Layout {  // workspace offsets in doubles
   size_t C, A, X, Q, vec, hist, bij, state, total;
-  int ne, nbp;
+  // occupied-subspace solve (xtb_scf_subspace.cuh, grid-wide): nh = ne/2 rounded up to the GEMM tile bounds the occupied count
+  size_t sX, sXt, sT, sT3, sG, sE, sZ, sCt, sYt, sWt;
+  int ne, nbp, nh;
 };
 
 __host__ __device__ inline Layout layout(int n, int ns, int na, int gen) {
@@ -60,6 +66,19 @@ __host__ __device__ inline Layout layout(int n, int ns, int na, int gen) {
   l.bij = p; p += l.nbp + 1;
   p += p & 1;
   l.state = p; p += sizeof(LargeState) / 8 + 1;
+  p += p & 1;
+  l.nh = (l.ne / 2 + LPAD - 1) / LPAD * LPAD;
+  const size_t mh = (size_t)l.ne * l.nh, hh = (size_t)l.nh * l.nh;
+  l.sX = p; p += mh;    // X  [nv][no]  (ld nh)
+  l.sXt = p; p += mh;   // X^T [no][nv] (ld ne)
+  l.sT = p; p += mh;    // A(:, v) X, Lambda in its first no rows (ld nh); Newton: Z E
+  l.sT3 = p; p += mh;   // X Lambda (ld nh)
+  l.sG = p; p += hh;
+  l.sE = p; p += hh;
+  l.sZ = p; p += hh;
+  l.sCt = p; p += m;    // C^T
+  l.sYt = p; p += mh;   // Y^T [no][n] (ld ne)
+  l.sWt = p; p += mh;   // (Y Z)^T
   l.total = p;
   return l;
 }
@@ -712,6 +731,218 @@ kl_vec(int phase, const xtb_batch b, const xtb_scf_opts o, int m, const double* 
   }
 }
 
+
+// ---- occupied-subspace solve of the intermediate map evaluations, grid-wide (algorithm and safeguards: xtb_scf_subspace.cuh) ----
+// All operands are zero padded to the GEMM tile (128 columns, K multiple of 16), so that the GEMMs need no predicates: rows /
+// columns of X, X^T beyond (nv, no) stay exactly zero (the update kernel only writes the valid block).
+constexpr double kSubBias = 4096.0;  // maxima of possibly negative values are kept as raw bits of (value + bias) >= 0
+
+__device__ __forceinline__ void atomic_max_biased(double* addr, double v) {
+  atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v + kSubBias));
+}
+
+// Out[i][j] = sum_{k < K} L[k][i] R[k][j] with separate leading dimensions: grid (N / 128, M / 128), K % 16 == 0.
+__global__ void __launch_bounds__(NT, 1)
+kl_gemm_tn2(const double* __restrict__ L, int ldl, const double* __restrict__ R, int ldr, double* __restrict__ Out, int ldo, int K) {
+  extern __shared__ double gsm[];
+  double* Ls = gsm;                  // [2][GK][GLD]
+  double* Rs = gsm + 2 * GK * GLD;   // [2][GK][GLD]
+  const int i0 = blockIdx.y * GT, j0 = blockIdx.x * GT;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, tg = lane & 3;
+  const int wi = (warp >> 2) * 32, wj = (warp & 3) * 32;
+  const int srow = threadIdx.x >> 5, scol = (threadIdx.x & 31) * 4;
+  double d[4][4][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) d[a][b][0] = d[a][b][1] = 0.0;
+  double2 l0, l1, r0, r1;
+  auto gload = [&](int k0) {
+    const double* lp = L + (size_t)(k0 + srow) * ldl + i0 + scol;
+    const double* rp = R + (size_t)(k0 + srow) * ldr + j0 + scol;
+    l0 = *reinterpret_cast<const double2*>(lp); l1 = *reinterpret_cast<const double2*>(lp + 2);
+    r0 = *reinterpret_cast<const double2*>(rp); r1 = *reinterpret_cast<const double2*>(rp + 2);
+  };
+  auto sstore = [&](int buf) {
+    double* lp = Ls + (buf * GK + srow) * GLD + scol;
+    double* rp = Rs + (buf * GK + srow) * GLD + scol;
+    *reinterpret_cast<double2*>(lp) = l0; *reinterpret_cast<double2*>(lp + 2) = l1;
+    *reinterpret_cast<double2*>(rp) = r0; *reinterpret_cast<double2*>(rp + 2) = r1;
+  };
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  const int nchunk = K / GK;
+  for (int ch = 0; ch < nchunk; ++ch) {
+    const int buf = ch & 1;
+    if (ch + 1 < nchunk) gload((ch + 1) * GK);
+    const double* lb = Ls + buf * GK * GLD;
+    const double* rb = Rs + buf * GK * GLD;
+#pragma unroll
+    for (int k4 = 0; k4 < GK / 4; ++k4) {
+      double a[4], b[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        a[t] = lb[(4 * k4 + tg) * GLD + wi + 8 * t + g];
+        b[t] = rb[(4 * k4 + tg) * GLD + wj + 8 * t + g];
+      }
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) dmma884(d[mt][nt][0], d[mt][nt][1], a[mt], b[nt]);
+    }
+    if (ch + 1 < nchunk) sstore(buf ^ 1);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      double* o = Out + (size_t)(i0 + wi + 8 * mt + g) * ldo + j0 + wj + 8 * nt + 2 * tg;
+      *reinterpret_cast<double2*>(o) = make_double2(d[mt][nt][0], d[mt][nt][1]);
+    }
+}
+
+__global__ void kl_sub_diag(const double* __restrict__ A, double* __restrict__ eps, int n, int ne) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) eps[k] = A[(size_t)k * ne + k];
+}
+
+// ranks of the diagonal (ascending, ties by index); sub_bad: the `no` lowest are not the first `no` positions
+__global__ void kl_sub_rank(const double* __restrict__ eps, int* __restrict__ rank, int n, int no, LargeState* st) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const double e = eps[k];
+  int rk = 0;
+  for (int j = 0; j < n; ++j) {
+    const double ej = eps[j];
+    rk += (ej < e) || (ej == e && j < k);
+  }
+  rank[k] = rk;
+  if ((rk < no) != (k < no)) atomicOr(&st->sub_bad, 1);
+}
+
+// Gershgorin bounds inside the two classes (rank == nullptr: classes by position), one warp per row
+__global__ void kl_sub_gersh(const double* __restrict__ A, const double* __restrict__ eps, const int* __restrict__ rank, int n, int ne, int no,
+                             LargeState* st) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const double* row = A + (size_t)i * ne;
+  const bool oi = (rank ? rank[i] : i) < no;
+  double s = 0.0;
+  for (int j = lane; j < n; j += 32)
+    if (j != i && ((rank ? rank[j] : j) < no) == oi) s += fabs(row[j]);
+  s = warp_sum(s);
+  if (lane == 0) {
+    if (oi) atomic_max_biased(&st->sub_hi, eps[i] + s);
+    else atomic_max_biased(&st->sub_nlo, s - eps[i]);
+  }
+}
+
+// dst[mu][rank[k]] = src[mu][k] (columns k >= n stay in place)
+__global__ void kl_sub_perm_cols(double* __restrict__ dst, const double* __restrict__ src, const int* __restrict__ rank, int n, int ne) {
+  const size_t tot = (size_t)ne * ne;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x) {
+    const int mu = (int)(t / ne), k = (int)(t - (size_t)mu * ne);
+    dst[(size_t)mu * ne + (k < n ? rank[k] : k)] = src[t];
+  }
+}
+
+// dst[rank[i]][rank[j]] = src[i][j]
+__global__ void kl_sub_perm_sym(double* __restrict__ dst, const double* __restrict__ src, const int* __restrict__ rank, int n, int ne) {
+  const size_t tot = (size_t)ne * ne;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(t / ne), j = (int)(t - (size_t)i * ne);
+    dst[(size_t)(i < n ? rank[i] : i) * ne + (j < n ? rank[j] : j)] = src[t];
+  }
+}
+
+__global__ void kl_sub_perm_vec(double* __restrict__ dst, const double* __restrict__ src, const int* __restrict__ rank, int n) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) dst[rank[k]] = src[k];
+}
+
+// Lambda = Aoo + Aov X: T[r][i] += A[r][i] for r, i < no
+__global__ void kl_sub_lambda(double* __restrict__ T, const double* __restrict__ A, int no, int ne, int ldt) {
+  const size_t tot = (size_t)no * no;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(t / no), i = (int)(t - (size_t)r * no);
+    T[(size_t)r * ldt + i] += A[(size_t)r * ne + i];
+  }
+}
+
+// R = Avo + T1 - X Lambda;  X <- X - R / (d_a - d_i)  (X and X^T);  maxima of |R| and |X_new|
+__global__ void kl_sub_update(double* __restrict__ X, double* __restrict__ Xt, const double* __restrict__ A, const double* __restrict__ T,
+                              const double* __restrict__ T3, const double* __restrict__ eps, int no, int nv, int ne, int ldx, LargeState* st) {
+  __shared__ double red[32];
+  const size_t tot = (size_t)nv * no;
+  double rmax = 0.0, xmax = 0.0;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x) {
+    const int a = (int)(t / no), i = (int)(t - (size_t)a * no);
+    const double r = A[(size_t)(no + a) * ne + i] + T[(size_t)(no + a) * ldx + i] - T3[(size_t)a * ldx + i];
+    const double xn = X[(size_t)a * ldx + i] - r / (eps[no + a] - eps[i]);
+    X[(size_t)a * ldx + i] = xn;
+    Xt[(size_t)i * ne + a] = xn;
+    rmax = fmax(rmax, fabs(r));
+    xmax = fmax(xmax, fabs(xn));
+  }
+  rmax = block_max(rmax, red);
+  xmax = block_max(xmax, red);
+  if (threadIdx.x == 0) {
+    // NaN compares false everywhere: map it to a huge value so that the host sees the failure
+    atomic_max_biased(&st->sub_rmax, rmax == rmax ? rmax : 1.0e300);
+    atomic_max_biased(&st->sub_xmax, xmax == xmax ? xmax : 1.0e300);
+  }
+}
+
+// G <- G + 1 on the whole padded diagonal (the pad block of G, and with it of Z, is the identity)
+__global__ void kl_sub_addone(double* __restrict__ G, int np, int ld) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < np; i += gridDim.x * blockDim.x) G[(size_t)i * ld + i] += 1.0;
+}
+
+// Z0 = 2 - G
+__global__ void kl_sub_zinit(double* __restrict__ Z, const double* __restrict__ G, int np, int ld) {
+  const size_t tot = (size_t)np * np;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(t / np), j = (int)(t - (size_t)i * np);
+    Z[(size_t)i * ld + j] = (i == j ? 2.0 : 0.0) - G[(size_t)i * ld + j];
+  }
+}
+
+// E <- 1 - E (E held G Z); max |E|
+__global__ void kl_sub_eres(double* __restrict__ E, int np, int ld, LargeState* st) {
+  __shared__ double red[32];
+  const size_t tot = (size_t)np * np;
+  double emax = 0.0;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(t / np), j = (int)(t - (size_t)i * np);
+    const double e = (i == j ? 1.0 : 0.0) - E[(size_t)i * ld + j];
+    E[(size_t)i * ld + j] = e;
+    emax = fmax(emax, fabs(e));
+  }
+  emax = block_max(emax, red);
+  if (threadIdx.x == 0) atomic_max_biased(&st->sub_emax, emax == emax ? emax : 1.0e300);
+}
+
+// Z <- Z + D on the np x np block
+__global__ void kl_sub_add(double* __restrict__ Z, const double* __restrict__ D, int np, int ld) {
+  const size_t tot = (size_t)np * np;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(t / np), j = (int)(t - (size_t)i * np);
+    Z[(size_t)i * ld + j] += D[(size_t)i * ld + j];
+  }
+}
+
+// Y^T[k][mu] += C^T[k][mu] for the occupied rows k < no
+__global__ void kl_sub_addrows(double* __restrict__ Yt, const double* __restrict__ Ct, int no, int ne) {
+  const size_t tot = (size_t)no * ne;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x) Yt[t] += Ct[t];
+}
+
+__global__ void kl_sub_scale(double* __restrict__ p, size_t count, double f) {
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < count; t += (size_t)gridDim.x * blockDim.x) p[t] *= f;
+}
+
 struct SideStream {
   int dev;
   cudaStream_t main, side;
@@ -787,6 +1018,7 @@ extern "C" int xtb_scf_run_large(const xtb_batch* b, const xtb_scf_opts* o, int3
     if (dev < 0 || dev >= 64) return -5;
     if (!configured[dev]) {
       int e = set_smem(kl_gemm_tn, 4 * GK * GLD * 8);
+      if (!e) e = set_smem(kl_gemm_tn2, 4 * GK * GLD * 8);
       if (!e) e = set_smem(kl_jacobi_sub, SUB_SMEM);
       if (!e) e = set_smem(kl_jacobi_pass, PASS_SMEM);
       if (e) return e;
@@ -825,14 +1057,22 @@ extern "C" int xtb_scf_run_large(const xtb_batch* b, const xtb_scf_opts* o, int3
   };
   int total_sweeps = 0, hstatus = 0;
   // Jacobi on (Am, Vm) until max |off-diagonal| <= tol
-  auto jacobi_large = [&](double* Am, double* Vm, double tol, int maxsweeps) -> int {
+  // (diagonal: set when the off-diagonal test passed; with a null pointer running out of sweeps is an error status)
+  auto jacobi_large = [&](double* Am, double* Vm, double tol, int maxsweeps, bool* diagonal = nullptr) -> int {
     const int npass = nbp * (nbp + 1) / 2 + (ne / OP) * nbp;
+    if (diagonal) *diagonal = false;
     for (int sweep = 0;; ++sweep) {
       cudaMemsetAsync(&dst->off, 0, sizeof(double), st);
       kl_offmax<<<ew_grid, 256, 0, st>>>(Am, ne, dst);
       if (int e = read_state()) return e;
-      if (hs.off <= tol) return 0;
-      if (sweep >= maxsweeps) { hstatus |= XTB_STATUS_JACOBI_NOT_CONVERGED; return 0; }
+      if (hs.off <= tol) {
+        if (diagonal) *diagonal = true;
+        return 0;
+      }
+      if (sweep >= maxsweeps) {
+        if (!diagonal) hstatus |= XTB_STATUS_JACOBI_NOT_CONVERGED;
+        return 0;
+      }
       ++total_sweeps;
       // Round r: sub-problems -> Q (buffer r & 1), then the rotation pass.  The pass first updates the few tiles the
       // sub-problems of round r + 1 read (phase 1); those sub-problems (nbp CTAs, a third of the SMs) then run on a second,
@@ -855,21 +1095,174 @@ extern "C" int xtb_scf_run_large(const xtb_batch* b, const xtb_scf_opts* o, int3
       }
     }
   };
-  // one SCF map evaluation v -> q -> vnew
-  auto fcn = [&](double jtol) -> int {
+  // ---- occupied-subspace solve of the intermediate map evaluations (host-driven; see xtb_scf_subspace.cuh) ----------------
+  struct {
+    bool eligible, layout, xvalid, zvalid, ctvalid;
+    int no, nv, nop, nvp, ko, kv;
+    double gapmin;
+  } sb{};
+  double *sX = work + l.sX, *sXt = work + l.sXt, *sT = work + l.sT, *sT3 = work + l.sT3, *sG = work + l.sG, *sE = work + l.sE, *sZ = work + l.sZ,
+         *sCt = work + l.sCt, *sYt = work + l.sYt, *sWt = work + l.sWt;
+  const int nh = l.nh;
+  int* rank = const_cast<int*>(occl);  // the occupation list of the Fermi stage is only needed after the final solve
+  {
+    double nelh[2] = {0.0, 1.0};
+    if (cudaMemcpyAsync(nelh, nel_ab + 2 * (size_t)mol, 2 * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -6;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return -6;
+    sb.no = (int)rint(nelh[0]);
+    sb.nv = n - sb.no;
+    sb.eligible = o->subspace != 0 && o->maxiter > 0 && nelh[0] == nelh[1] && fabs(nelh[0] - (double)sb.no) < 1e-9 && sb.no >= 1 && sb.nv >= 1 &&
+                  2 * sb.no <= ne;
+    sb.nop = (sb.no + GT - 1) / GT * GT;
+    sb.nvp = (sb.nv + GT - 1) / GT * GT;
+    sb.ko = (sb.no + GK - 1) / GK * GK;
+    sb.kv = (sb.nv + GK - 1) / GK * GK;
+    sb.gapmin = fmax(o->subspace_gap * o->kt, 0.02);
+    if (sb.nop > nh || sb.nvp > ne || sb.no + sb.kv > ne) sb.eligible = false;
+  }
+  auto gemm2 = [&](const double* L, int ldl, const double* R, int ldr, double* Out, int ldo, int M, int N, int K) {
+    kl_gemm_tn2<<<dim3(N / GT, M / GT), NT, 4 * GK * GLD * 8, st>>>(L, ldl, R, ldr, Out, ldo, K);
+  };
+  // certified gap between the classes (rank: by the ranks of the diagonal, else by position)
+  auto certify = [&](bool ranked, double* gapc, bool* needs_perm) -> int {
+    cudaMemsetAsync(&dst->sub_bad, 0, 2 * sizeof(int) + 2 * sizeof(double), st);  // sub_bad, pad, sub_hi, sub_nlo
+    kl_sub_diag<<<(n + 255) / 256, 256, 0, st>>>(A, eps, n, ne);
+    if (ranked) kl_sub_rank<<<(n + 255) / 256, 256, 0, st>>>(eps, rank, n, sb.no, dst);
+    kl_sub_gersh<<<(n + 7) / 8, 256, 0, st>>>(A, eps, ranked ? rank : nullptr, n, ne, sb.no, dst);
+    if (int e = read_state()) return e;
+    *gapc = -(hs.sub_nlo - kSubBias) - (hs.sub_hi - kSubBias);
+    *needs_perm = ranked && hs.sub_bad != 0;
+    return 0;
+  };
+  auto permute = [&]() {
+    kl_sub_perm_cols<<<ew_grid, 256, 0, st>>>(X, C, rank, n, ne);
+    cudaMemcpyAsync(C, X, (size_t)ne * ne * 8, cudaMemcpyDeviceToDevice, st);
+    kl_sub_perm_sym<<<ew_grid, 256, 0, st>>>(X, A, rank, n, ne);
+    cudaMemcpyAsync(A, X, (size_t)ne * ne * 8, cudaMemcpyDeviceToDevice, st);
+    kl_sub_perm_vec<<<(n + 255) / 256, 256, 0, st>>>(srt, eps, rank, n);
+    cudaMemcpyAsync(eps, srt, (size_t)n * 8, cudaMemcpyDeviceToDevice, st);
+  };
+  // Riccati fixed point; *ok = converged
+  auto riccati = [&](bool* ok) -> int {
+    *ok = false;
+    if (!sb.xvalid) {
+      cudaMemsetAsync(sX, 0, (size_t)ne * nh * 8, st);
+      cudaMemsetAsync(sXt, 0, (size_t)ne * nh * 8, st);
+      sb.xvalid = true;
+      sb.zvalid = false;
+    }
+    double rprev = 1.0e300;
+    for (int it = 0; it < o->subspace_maxiter; ++it) {
+      gemm2(A + (size_t)sb.no * ne, ne, sX, nh, sT, nh, ne, sb.nop, sb.kv);  // T[r][i] = sum_b A[no + b][r] X[b][i]
+      kl_sub_lambda<<<ew_grid, 256, 0, st>>>(sT, A, sb.no, ne, nh);             // rows r < no: + Aoo -> Lambda
+      gemm2(sXt, ne, sT, nh, sT3, nh, sb.nvp, sb.nop, sb.ko);                  // T3[a][i] = sum_j X[a][j] Lambda[j][i]
+      cudaMemsetAsync(&dst->sub_rmax, 0, 2 * sizeof(double), st);              // sub_rmax, sub_xmax
+      kl_sub_update<<<ew_grid, 256, 0, st>>>(sX, sXt, A, sT, sT3, eps, sb.no, sb.nv, ne, nh, dst);
+      if (int e = read_state()) return e;
+      const double rmax = hs.sub_rmax - kSubBias, xmax = hs.sub_xmax - kSubBias;
+      if (!(xmax < 1.0) || !(rmax < 1.0e200)) return 0;
+      const double rate = it > 0 ? fmin(0.5, 2.0 * rmax / rprev) : 1.0;
+      if (getenv("DXTB_B200_DEBUG_LARGE")) fprintf(stderr, "    riccati it %d: max|R| %.3e max|X| %.3e\n", it, rmax, xmax);
+      if (rmax * rate <= o->subspace_tol) { *ok = true; return 0; }
+      if (it >= 2 && rmax > 2.0 * rprev) return 0;
+      rprev = rmax;
+    }
+    return 0;
+  };
+  // P = 2 Y Z Y^T -> A; *ok = false if the Newton iteration for Z failed (A untouched then)
+  auto density = [&](bool* ok) -> int {
+    *ok = false;
+    const int np = sb.nop;
+    gemm2(sX, nh, sX, nh, sG, nh, np, np, sb.kv);  // X^T X
+    kl_sub_addone<<<(np + 255) / 256, 256, 0, st>>>(sG, np, nh);
+    for (int it = 0; it < 12; ++it) {
+      if (!sb.zvalid) {
+        kl_sub_zinit<<<ew_grid, 256, 0, st>>>(sZ, sG, np, nh);
+        sb.zvalid = true;
+      }
+      gemm2(sG, nh, sZ, nh, sE, nh, np, np, np);  // G Z (G symmetric)
+      cudaMemsetAsync(&dst->sub_emax, 0, sizeof(double), st);
+      kl_sub_eres<<<ew_grid, 256, 0, st>>>(sE, np, nh, dst);
+      if (int e = read_state()) return e;
+      const double emax = hs.sub_emax - kSubBias;
+      if (emax <= 1e-12) { *ok = true; break; }
+      if (!(emax < 0.5)) {
+        if (it > 0) break;
+        sb.zvalid = false;
+        continue;
+      }
+      gemm2(sZ, nh, sE, nh, sT, nh, np, np, np);  // Z E (Z symmetric up to the Newton residual)
+      kl_sub_add<<<ew_grid, 256, 0, st>>>(sZ, sT, np, nh);
+      if ((double)sb.no * emax * emax <= 1e-13) { *ok = true; break; }
+    }
+    if (!*ok) {
+      sb.zvalid = false;
+      return 0;
+    }
+    if (!sb.ctvalid) {
+      kl_transpose<<<dim3(ne / 32, ne / 32), 256, 0, st>>>(sCt, C, ne);
+      sb.ctvalid = true;
+    }
+    gemm2(sX, nh, sCt + (size_t)sb.no * ne, ne, sYt, ne, np, ne, sb.kv);  // Yt[k][mu] = sum_b X[b][k] C[mu][no + b]
+    kl_sub_addrows<<<ew_grid, 256, 0, st>>>(sYt, sCt, sb.no, ne);           // + C[mu][k]
+    gemm2(sZ, nh, sYt, ne, sWt, ne, np, ne, np);                           // Wt[k][mu] = sum_j Z[j][k] Yt[j][mu]
+    kl_sub_scale<<<ew_grid, 256, 0, st>>>(sWt, (size_t)np * ne, 2.0);
+    gemm2(sWt, ne, sYt, ne, A, ne, ne, ne, np);                            // P = 2 Wt^T Yt
+    return 0;
+  };
+
+  // one SCF map evaluation v -> q -> vnew; final_solve: always the full eigendecomposition
+  auto fcn = [&](double jtol, bool final_solve) -> int {
     kl_fock<<<ew_grid, 256, 0, st>>>(A, Hm, Sm, v, n, ne);
     gemm(A, C, X, ne);  // X = F C (F symmetric)
     gemm(C, X, A, ne);  // A = C^T X
     kl_symmetrize<<<ew_grid, 256, 0, st>>>(A, n, ne);
-    if (int e = jacobi_large(A, C, jtol, o->jacobi_max_sweeps)) return e;
-    vec(PH_FERMI, 0);
-    if (int e = read_state()) return e;
-    const int nocc = hs.nocc, kocc = (nocc + GK - 1) / GK * GK;
-    if (kocc > 0) {
-      kl_build_y<<<dim3(ne / 32, (kocc + 31) / 32), 256, 0, st>>>(X, nullptr, C, focc, eps, occl, n, ne, nocc, kocc, 0);
-      gemm(X, X, A, kocc);  // P = Y^T Y
-    } else {
-      cudaMemsetAsync(A, 0, (size_t)ne * ne * 8, st);
+    bool fast = false, diagonal = false;
+    static const bool debug = getenv("DXTB_B200_DEBUG_LARGE") != nullptr;  // developer printout
+    if (!final_solve && sb.eligible) {
+      // Jacobi sweeps only until the gap between the diagonal blocks is certified, then the Riccati fixed point
+      for (int sweeps_here = 0;;) {
+        double gapc = -1.0;
+        bool needs_perm = false;
+        if (sb.layout)
+          if (int e = certify(false, &gapc, &needs_perm)) return e;
+        if (gapc < sb.gapmin)
+          if (int e = certify(true, &gapc, &needs_perm)) return e;
+        if (debug) fprintf(stderr, "  large: certified gap %.5f (need %.5f) after %d sweeps of this solve (%d in total)\n", gapc, sb.gapmin, sweeps_here, total_sweeps);
+        if (gapc >= sb.gapmin) {
+          if (needs_perm) {
+            permute();
+            sb.xvalid = sb.ctvalid = false;
+          }
+          sb.layout = true;
+          bool ok = false;
+          if (int e = riccati(&ok)) return e;
+          if (ok) {
+            if (int e = density(&ok)) return e;
+            if (ok) { fast = true; break; }
+          }
+        }
+        if (sweeps_here >= o->jacobi_max_sweeps) break;
+        sb.xvalid = sb.ctvalid = false;
+        if (int e = jacobi_large(A, C, jtol, 1, &diagonal)) return e;
+        ++sweeps_here;
+        if (diagonal) break;
+      }
+    }
+    if (!fast) {
+      if (!diagonal) {
+        sb.xvalid = sb.ctvalid = false;
+        if (int e = jacobi_large(A, C, jtol, o->jacobi_max_sweeps)) return e;
+      }
+      vec(PH_FERMI, 0);
+      if (int e = read_state()) return e;
+      const int nocc = hs.nocc, kocc = (nocc + GK - 1) / GK * GK;
+      if (kocc > 0) {
+        kl_build_y<<<dim3(ne / 32, (kocc + 31) / 32), 256, 0, st>>>(X, nullptr, C, focc, eps, occl, n, ne, nocc, kocc, 0);
+        gemm(X, X, A, kocc);  // P = Y^T Y
+      } else {
+        cudaMemsetAsync(A, 0, (size_t)ne * ne * 8, st);
+      }
     }
     kl_mulliken<<<(n + 7) / 8, 256, 0, st>>>(A, Sm, Hm, n0, q, eorb, n, ne);
     vec(PH_POT, 0);
@@ -896,12 +1289,12 @@ extern "C" int xtb_scf_run_large(const xtb_batch* b, const xtb_scf_opts* o, int3
 
   int iters = 1;
   bool converged = true;
-  if (int e = fcn(o->maxiter > 0 ? o->jacobi_tol_iter : o->jacobi_tol)) return e;
+  if (int e = fcn(o->maxiter > 0 ? o->jacobi_tol_iter : o->jacobi_tol, o->maxiter <= 0)) return e;
   if (o->maxiter > 0) {
     converged = false;
     vec(PH_MIX, 0);  // mix_guess (unrolling/default.py:93-94); convergence is not tested here
     for (int it = 0; it < o->maxiter; ++it) {
-      if (int e = fcn(o->jacobi_tol_iter)) return e;
+      if (int e = fcn(o->jacobi_tol_iter, false)) return e;
       ++iters;
       vec(PH_MIX, 0);
       if (int e = read_state()) return e;
@@ -909,7 +1302,7 @@ extern "C" int xtb_scf_run_large(const xtb_batch* b, const xtb_scf_opts* o, int3
     }
     vec(PH_COPYV, 0);  // converged_to_charges: one more solve with the un-mixed potential
     reorthonormalize();
-    if (int e = fcn(o->jacobi_tol)) return e;
+    if (int e = fcn(o->jacobi_tol, true)) return e;
   }
   if (!converged) hstatus |= XTB_STATUS_SCF_NOT_CONVERGED;
   // fold the host-side status / sweep count into the device state, then emit

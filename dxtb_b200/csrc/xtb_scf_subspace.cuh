@@ -24,49 +24,78 @@
 
 namespace {
 
-// Out(i, j) = sum_{k < K} la(i, k) rb(k, j) for i < M, j < N on the fp64 tensor cores: one warp per (8 TM) x (8 TN) tile,
-// out-of-range operand elements are zero, results are handed to st(i, j, value).  With leading dimensions == 4 (mod 16)
-// row-major operands are bank-conflict free in both orientations ([k][i] and [i][k]).  No trailing barrier.
-template <int TM, int TN, class LA, class RB, class ST>
-__device__ __forceinline__ void gemm_small(int M, int N, int K, LA la, RB rb, ST st) {
+// Operand of gemm_small: element (k, m) at p[k * sk + m * sm] (either orientation of a row-major matrix, any offset).
+struct Operand {
+  const double* p;
+  int sk, sm;
+};
+
+// Out(i, j) = sum_{k < K} L(k, i) R(k, j) for i < M, j < N on the fp64 tensor cores: one warp per (8 TM) x (8 TN) tile,
+// out-of-range operand elements are zero, results are handed to st(i, j, value).  With leading dimensions == 4 (mod 8)
+// row-major operands are bank-conflict free in both orientations.  Operands are (pointer, strides) so that a k step is a
+// pointer increment and the row / column predicates are loop invariant: the first version took element lambdas and spent
+// ~29 instructions per k step (index arithmetic rematerialised at the 128-register cap) for 2 DMMAs.  No trailing barrier.
+template <int TM, int TN, class ST>
+__device__ __forceinline__ void gemm_small(int M, int N, int K, Operand L, Operand R, ST st) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, tg = lane & 3;
   const int mt = (M + 8 * TM - 1) / (8 * TM), nt = (N + 8 * TN - 1) / (8 * TN);
+  const int stepl = 4 * L.sk, stepr = 4 * R.sk;
+  const int kmain = K & ~3;
   for (int t = warp; t < mt * nt; t += NT / 32) {
     const int ti = t / nt, tj = t - ti * nt;
     const int i0 = ti * 8 * TM, j0 = tj * 8 * TN;
-    // two accumulator sets (even / odd k steps): twice as many independent DMMA chains per warp -- these GEMMs are small
-    // (K = 40: ten dependent DMMAs per chain otherwise) and latency-bound, in the second tile round most schedulers hold
-    // one or two warps only
-    double d[2][TM][TN][2];
+    const double* pa[TM];
+    const double* pb[TN];
+    bool va[TM], vb[TN];
 #pragma unroll
-    for (int h = 0; h < 2; ++h)
+    for (int x = 0; x < TM; ++x) {
+      const int i = i0 + 8 * x + g;
+      va[x] = i < M;
+      pa[x] = L.p + (va[x] ? i : 0) * L.sm + tg * L.sk;
+    }
+#pragma unroll
+    for (int y = 0; y < TN; ++y) {
+      const int j = j0 + 8 * y + g;
+      vb[y] = j < N;
+      pb[y] = R.p + (vb[y] ? j : 0) * R.sm + tg * R.sk;
+    }
+    double d[TM][TN][2];
+#pragma unroll
+    for (int x = 0; x < TM; ++x)
+#pragma unroll
+      for (int y = 0; y < TN; ++y) d[x][y][0] = d[x][y][1] = 0.0;
+#pragma unroll 4
+    for (int k0 = 0; k0 < kmain; k0 += 4) {  // unrolled: the operand loads of four k steps are in flight together
+      double a[TM], b[TN];
+#pragma unroll
+      for (int x = 0; x < TM; ++x) {
+        const double v = *pa[x];
+        a[x] = va[x] ? v : 0.0;
+        pa[x] += stepl;
+      }
+#pragma unroll
+      for (int y = 0; y < TN; ++y) {
+        const double v = *pb[y];
+        b[y] = vb[y] ? v : 0.0;
+        pb[y] += stepr;
+      }
 #pragma unroll
       for (int x = 0; x < TM; ++x)
 #pragma unroll
-        for (int y = 0; y < TN; ++y) d[h][x][y][0] = d[h][x][y][1] = 0.0;
-#pragma unroll 2
-    for (int k0 = 0; k0 < K; k0 += 8) {  // unrolled: the operand loads of four k steps are in flight together
+        for (int y = 0; y < TN; ++y) dmma884(d[x][y][0], d[x][y][1], a[x], b[y]);
+    }
+    if (kmain < K) {  // last, partial k step
+      const bool kv = kmain + tg < K;
+      double a[TM], b[TN];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int k = k0 + 4 * h + tg;
-        const bool kv = k < K;
-        double a[TM], b[TN];
+      for (int x = 0; x < TM; ++x) a[x] = (kv && va[x]) ? *pa[x] : 0.0;
 #pragma unroll
-        for (int x = 0; x < TM; ++x) {
-          const int i = i0 + 8 * x + g;
-          a[x] = (kv && i < M) ? la(i, k) : 0.0;
-        }
+      for (int y = 0; y < TN; ++y) b[y] = (kv && vb[y]) ? *pb[y] : 0.0;
 #pragma unroll
-        for (int y = 0; y < TN; ++y) {
-          const int j = j0 + 8 * y + g;
-          b[y] = (kv && j < N) ? rb(k, j) : 0.0;
-        }
+      for (int x = 0; x < TM; ++x)
 #pragma unroll
-        for (int x = 0; x < TM; ++x)
-#pragma unroll
-          for (int y = 0; y < TN; ++y) dmma884(d[h][x][y][0], d[h][x][y][1], a[x], b[y]);
-      }
+        for (int y = 0; y < TN; ++y) dmma884(d[x][y][0], d[x][y][1], a[x], b[y]);
     }
 #pragma unroll
     for (int x = 0; x < TM; ++x)
@@ -74,8 +103,8 @@ __device__ __forceinline__ void gemm_small(int M, int N, int K, LA la, RB rb, ST
       for (int y = 0; y < TN; ++y) {
         const int i = i0 + 8 * x + g, j = j0 + 8 * y + 2 * tg;
         if (i < M) {
-          if (j < N) st(i, j, d[0][x][y][0] + d[1][x][y][0]);
-          if (j + 1 < N) st(i, j + 1, d[0][x][y][1] + d[1][x][y][1]);
+          if (j < N) st(i, j, d[x][y][0]);
+          if (j + 1 < N) st(i, j + 1, d[x][y][1]);
         }
       }
   }
@@ -197,9 +226,8 @@ XTB_CTX_FN bool subspace_riccati(Ctx& c, const xtb_scf_opts& o) {
     const long long tq0 = clock64();
 #endif
     // T[r][i] = sum_b A[no + b][r] X[b][i]  (A symmetric);  rows r < no: + Aoo -> Lambda
-    gemm_small<2, 1>(
-        n, no, nv, [&](int r, int b) { return A[(size_t)(no + b) * ld + r]; }, [&](int b, int i) { return X[b * lds + i]; },
-        [&](int r, int i, double v) { T[r * lds + i] = (r < no) ? v + A[(size_t)r * ld + i] : v; });
+    gemm_small<2, 1>(n, no, nv, Operand{A + (size_t)no * ld, ld, 1}, Operand{X, lds, 1},
+                     [&](int r, int i, double v) { T[r * lds + i] = (r < no) ? v + A[(size_t)r * ld + i] : v; });
     __syncthreads();
 #ifdef XTB_PROFILE_PHASES
     const long long tq1 = clock64();
@@ -207,7 +235,7 @@ XTB_CTX_FN bool subspace_riccati(Ctx& c, const xtb_scf_opts& o) {
     // R = Avo + T1 - X Lambda;  X_new = X - R / (d_a - d_i) -> written over T1 (every element has one owner)
     double rmax = 0.0, xmax = 0.0;
     gemm_small<1, 1>(
-        nv, no, no, [&](int a, int j) { return X[a * lds + j]; }, [&](int j, int i) { return T[j * lds + i]; },
+        nv, no, no, Operand{X, 1, lds}, Operand{T, lds, 1},
         [&](int a, int i, double t3) {
           const double r = A[(size_t)(no + a) * ld + i] + T[(no + a) * lds + i] - t3;
           const double xn = X[a * lds + i] - r / (dg[no + a] - dg[i]);
@@ -260,9 +288,8 @@ XTB_CTX_FN double* subspace_density(Ctx& c) {
   double* Zc = in_shared<CS>(c.X);
   double* Zn = Zc + (size_t)no * lds;
   // G = 1 + X^T X
-  gemm_small<1, 1>(
-      no, no, nv, [&](int i, int b) { return X[b * lds + i]; }, [&](int b, int j) { return X[b * lds + j]; },
-      [&](int i, int j, double v) { G[i * lds + j] = (i == j) ? 1.0 + v : v; });
+  gemm_small<1, 1>(no, no, nv, Operand{X, lds, 1}, Operand{X, lds, 1},
+                   [&](int i, int j, double v) { G[i * lds + j] = (i == j) ? 1.0 + v : v; });
   if (c.sub.zvalid)
     for (int t = threadIdx.x; t < no * lds; t += NT) Zc[t] = c.sub.Zg[t];
   __syncthreads();
@@ -278,7 +305,7 @@ XTB_CTX_FN double* subspace_density(Ctx& c) {
     }
     double emax = 0.0;
     gemm_small<1, 1>(
-        no, no, no, [&](int i, int k) { return G[i * lds + k]; }, [&](int k, int j) { return Zc[k * lds + j]; },
+        no, no, no, Operand{G, 1, lds}, Operand{Zc, lds, 1},
         [&](int i, int j, double v) {
           const double e = (i == j ? 1.0 : 0.0) - v;
           E[i * lds + j] = e;
@@ -291,9 +318,8 @@ XTB_CTX_FN double* subspace_density(Ctx& c) {
       c.sub.zvalid = false;    // warm start too far off: restart from Z0
       continue;
     }
-    gemm_small<1, 1>(
-        no, no, no, [&](int i, int k) { return Zc[i * lds + k]; }, [&](int k, int j) { return E[k * lds + j]; },
-        [&](int i, int j, double v) { Zn[i * lds + j] = Zc[i * lds + j] + v; });
+    gemm_small<1, 1>(no, no, no, Operand{Zc, 1, lds}, Operand{E, lds, 1},
+                     [&](int i, int j, double v) { Zn[i * lds + j] = Zc[i * lds + j] + v; });
     __syncthreads();
     double* t = Zc; Zc = Zn; Zn = t;
     ++c.sub.nnewt;
@@ -310,20 +336,15 @@ XTB_CTX_FN double* subspace_density(Ctx& c) {
   // Yt[k][mu] = C[mu][k] + sum_b X[b][k] C[mu][no + b]
   double* Yt = G;
   double* Wt = G + (size_t)no * ld;
-  gemm_small<1, 2>(
-      no, n, nv, [&](int k, int b) { return X[b * lds + k]; }, [&](int b, int mu) { return C[(size_t)mu * ld + no + b]; },
-      [&](int k, int mu, double v) { Yt[(size_t)k * ld + mu] = v + C[(size_t)mu * ld + k]; });
+  gemm_small<1, 2>(no, n, nv, Operand{X, lds, 1}, Operand{C + no, 1, ld},
+                   [&](int k, int mu, double v) { Yt[(size_t)k * ld + mu] = v + C[(size_t)mu * ld + k]; });
   __syncthreads();
   // Wt[k][mu] = sum_j Z[j][k] Yt[j][mu]
-  gemm_small<1, 2>(
-      no, n, no, [&](int k, int j) { return Zc[j * lds + k]; }, [&](int j, int mu) { return Yt[(size_t)j * ld + mu]; },
-      [&](int k, int mu, double v) { Wt[(size_t)k * ld + mu] = v; });
+  gemm_small<1, 2>(no, n, no, Operand{Zc, lds, 1}, Operand{Yt, ld, 1}, [&](int k, int mu, double v) { Wt[(size_t)k * ld + mu] = v; });
   __syncthreads();
   // P[mu][nu] = 2 sum_k Wt[k][mu] Yt[k][nu]  -> X buffer (Z is dead)
   double* Pb = in_shared<CS>(c.X);
-  gemm_small<2, 2>(
-      n, n, no, [&](int mu, int k) { return Wt[(size_t)k * ld + mu]; }, [&](int k, int nu) { return Yt[(size_t)k * ld + nu]; },
-      [&](int mu, int nu, double v) { Pb[(size_t)mu * ld + nu] = 2.0 * v; });
+  gemm_small<2, 2>(n, n, no, Operand{Wt, ld, 1}, Operand{Yt, ld, 1}, [&](int mu, int nu, double v) { Pb[(size_t)mu * ld + nu] = 2.0 * v; });
   __syncthreads();
   return Pb;
 }
