@@ -72,3 +72,22 @@ def test_subspace_path_refused_for_fractional_occupations(mols):
         b = _run(numbers, pos, chrg, {"exclude": ["disp"], "scf_subspace": False, **opts}, dev)
         assert np.array_equal(a["e"], b["e"]) and np.array_equal(a["g"], b["g"]) and np.array_equal(a["it"], b["it"])
         assert np.array_equal(a["sweeps"], b["sweeps"])
+
+
+def test_subspace_path_on_the_large_system_path(mols, monkeypatch):
+    """Grid-wide version (xtb_scf_large.cu): caffeine and LYS_xao forced onto the large-system path, subspace solve on against
+    off -- same iteration counts, energies 1e-10, forces 1e-8, and fewer sweeps."""
+    dev = _dev()
+    monkeypatch.setenv("DXTB_B200_LARGE_MIN_NAO", "1")
+    for name in ("caffeine", "LYS_xao"):
+        m = mols[name]
+        numbers = torch.tensor(m["numbers"])[None].expand(2, -1).contiguous().to(dev)
+        chrg = torch.full((2,), float(m["charge"]), dtype=torch.float64, device=dev)
+        pos = torch.from_numpy(_conformers(np.array(m["positions"]), 2, 5)).to(dev)
+        a = _run(numbers, pos, chrg, {"exclude": ["disp"], "scf_subspace": True}, dev)
+        b = _run(numbers, pos, chrg, {"exclude": ["disp"], "scf_subspace": False}, dev)
+        assert (a["status"] == 0).all() and (b["status"] == 0).all()
+        assert np.array_equal(a["it"], b["it"])
+        assert np.abs(a["e"] - b["e"]).max() < 1e-10
+        assert np.abs(a["g"] - b["g"]).max() < 1e-8
+        assert a["sweeps"].mean() < 0.6 * b["sweeps"].mean(), (a["sweeps"].mean(), b["sweeps"].mean())
