@@ -3,7 +3,7 @@
 #   gpurun --gpus 8 -- 'bash tools/run_scaling.sh 8'      -> gpurun_out/scale_r2_n8.jsonl
 #   gpurun          -- 'bash tools/run_scaling.sh 1'      -> gpurun_out/scale_r2_n1.jsonl
 N=${1:-1}
-OUT=gpurun_out/scale_r2_n${N}.jsonl
+OUT=gpurun_out/scale_${2:-r2}_n${N}.jsonl
 : > $OUT
 run() {
   if [ "$N" -gt 1 ]; then
