@@ -54,7 +54,7 @@ DEFAULT_OPTS: dict[str, Any] = {
     # B200 path only: add the first-order response of the SCF residual to the analytic gradient, so that forces equal the
     # reference's autograd-through-the-unrolled-SCF forces at ANY convergence threshold (xtb_scf_core.cuh:scf_response)
     "grad_response": True,
-    # B200 path only: intermediate SCF iterations of closed-shell molecules with a certified gap >= 60 kT solve for the
+    # B200 path only: intermediate SCF iterations of closed-shell molecules with a certified gap >= 50 kT solve for the
     # occupied subspace (Riccati fixed point, xtb_scf_subspace.cuh) instead of diagonalising; the final solve is always the
     # full eigendecomposition.  False: every iteration diagonalises (as the reference does).
     "scf_subspace": True,
@@ -478,7 +478,7 @@ class GFN1Calculator:
         s.subspace = 1 if o["scf_subspace"] and os.environ.get("DXTB_B200_SUBSPACE", "1") != "0" else 0
         s.subspace_maxiter = 16
         s.subspace_tol = min(1e-10, 0.05 * s.jacobi_tol_iter)
-        s.subspace_gap = 60.0
+        s.subspace_gap = float(os.environ.get("DXTB_B200_SUBSPACE_GAP", "50"))  # in kT (developer knob)
         return s
 
     def _electrons(self, chrg: torch.Tensor, spin: torch.Tensor | None) -> torch.Tensor:

@@ -15,7 +15,7 @@
 // Safeguards (each falls back to a Jacobi sweep, i.e. to the path that was there before):
 //  * integer occupations are CERTIFIED per map evaluation: with Gershgorin discs inside the two diagonal blocks and Cauchy
 //    interlacing, gap(A) >= min_a (d_a - sum_{b != a} |A_ab|) - max_i (d_i + sum_{j != i} |A_ij|); the path is taken only if
-//    that bound is >= subspace_gap * kT (60 kT: occupation error exp(-30) ~ 1e-13);
+//    that bound is >= subspace_gap * kT (50 kT: occupation error exp(-25) ~ 1.4e-11);
 //  * the o / v classification follows the ranks of the current diagonal; a change permutes C and restarts X;
 //  * a stalled, diverging or large (|X| >= 1) fixed point, or a failed Newton iteration, triggers a sweep.
 // The final solve that defines energies, charges, P, W and the orbital energies is always the full Jacobi solve.

@@ -105,7 +105,7 @@ typedef struct xtb_scf_opts {
   double jacobi_tol;        /* 1e-13: max |off-diagonal| of the final solve */
   double jacobi_tol_iter;   /* 2e-9: the same for intermediate SCF map evaluations */
   double subspace_tol;      /* 1e-10: max |Riccati residual| (Eh) of the occupied-subspace solve */
-  double subspace_gap;      /* 60: certified HOMO-LUMO gap in units of kT below which occupations are not taken as integer */
+  double subspace_gap;      /* 50: certified HOMO-LUMO gap in units of kT below which occupations are not taken as integer */
   /* optional size bucket: this launch handles molecules mol_list[0..list_len) only (device pointer; NULL = all).
    * list_*_max are the maxima over the bucket (they size the shared-memory layout). */
   const int32_t* mol_list;

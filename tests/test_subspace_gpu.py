@@ -55,12 +55,12 @@ def test_subspace_path_reproduces_full_diagonalisation(mols, name, nb, override)
     assert np.abs(a["q"] - b["q"]).max() < 1e-8
     assert np.abs(a["g"] - b["g"]).max() < 1e-8
     # the path is taken: most intermediate solves need no Jacobi sweep at all (AD7en+: the certified gap of the cation is
-    # below 60 kT in part of its iterations, which then diagonalise)
+    # below 50 kT in part of its iterations, which then diagonalise)
     assert a["sweeps"].mean() < (0.9 if name == "AD7en+" else 0.4) * b["sweeps"].mean(), (a["sweeps"].mean(), b["sweeps"].mean())
 
 
 def test_subspace_path_refused_for_fractional_occupations(mols):
-    """Open shells, hot electrons (gap < 60 kT) and molecules below 33 AOs must take the full eigendecomposition:
+    """Open shells, hot electrons (gap < 50 kT) and molecules below 33 AOs must take the full eigendecomposition:
     bit-identical results."""
     dev = _dev()
     for name, opts in (("NO2", {}), ("caffeine", {"fermi_etemp": 5000.0}), ("H", {}), ("H2O", {}), ("LiH", {})):
