@@ -266,7 +266,9 @@ class GFN1Calculator:
                 continue
             else:
                 raise KeyError(f"unknown option '{k}'")
-        if str(o["scf_mode"]).lower() not in ("full", "full_tracking", "2"):
+        # labels/scf.py:75-79: SCF_MODE_FULL = 0, strings "full" / "full_tracking" / "unrolling" (defaults.py also lists
+        # "full-tracking"); the implicit (xitorch) and single-shot modes are not implemented
+        if str(o["scf_mode"]).lower() not in ("full", "full_tracking", "full-tracking", "unrolling", "0"):
             raise NotImplementedError("only scf_mode='full' (the reference default) is implemented")
         if str(o["scp_mode"]).lower() not in ("potential", "1"):
             raise NotImplementedError("only scp_mode='potential' (the reference default) is implemented")
