@@ -29,7 +29,7 @@ class XtbBatch(C.Structure):
     _fields_ = [
         ("nb", C.c_int32), ("nat_tot", C.c_int32), ("nsh_tot", C.c_int32), ("nao_tot", C.c_int32),
         ("nat_max", C.c_int32), ("nsh_max", C.c_int32), ("nao_max", C.c_int32),
-        ("nspecies", C.c_int32), ("ncgto", C.c_int32), ("has_xb", C.c_int32),
+        ("nspecies", C.c_int32), ("ncgto", C.c_int32), ("has_xb", C.c_int32), ("nsh_l_max", C.c_int32 * 4),
         ("mat_total", C.c_int64), ("gam_total", C.c_int64), ("eeq_total", C.c_int64),
         ("at_off", _vp), ("sh_off", _vp), ("ao_off", _vp), ("mat_off", _vp), ("gam_off", _vp), ("eeq_off", _vp),
         ("at_z", _vp), ("at_species", _vp), ("at_sh0", _vp), ("at_nsh", _vp), ("at_par", _vp),

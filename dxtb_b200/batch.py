@@ -165,6 +165,7 @@ class BatchDescriptor:
         s.nat_max, s.nsh_max, s.nao_max = int(nat.max()), int(nsh.max()), int(nao.max())
         s.nspecies, s.ncgto = int(species.size), int(ukey.size)
         s.has_xb = int(bool((at_par[:, _abi.AT_XBOND] != 0.0).any()))
+        s.nsh_l_max = (C.c_int32 * 4)(*[int(x) for x in nsh_l.max(axis=0)], 0)
         s.mat_total, s.gam_total, s.eeq_total = int(self.mat_off[-1]), int(self.gam_off[-1]), int(self.eeq_off[-1])
         for name, t in self._t.items():
             setattr(s, name, t.data_ptr())

@@ -353,7 +353,8 @@ __global__ void __launch_bounds__(128) k_grad_pair(const xtb_batch b, const doub
 
 template <int LI, int LJ> int launch_overlap(const xtb_batch* b, const double* pos, const double* cn, double* S, double* H0, cudaStream_t st) {
   const int nt = 128;
-  const int npair = b->nsh_max * b->nsh_max;  // upper bound on n_I * n_J
+  const int npair = b->nsh_l_max[LI] * b->nsh_l_max[LJ];  // upper bound on n_I * n_J of this class over the shard
+  if (npair == 0) return 0;                               // e.g. no d shells anywhere in the shard
   for (int m0 = 0; m0 < b->nb; m0 += kMaxGridY) {  // gridDim.y is capped at 65535
     dim3 grid((npair + nt - 1) / nt, b->nb - m0 < kMaxGridY ? b->nb - m0 : kMaxGridY);
     k_overlap_h0<LI, LJ><<<grid, nt, 0, st>>>(*b, pos, cn, S, H0, m0);
@@ -364,7 +365,8 @@ template <int LI, int LJ>
 int launch_grad_pair(const xtb_batch* b, const double* pos, const double* cn, const double* P, const double* W, const double* v,
                      double* pairbuf, cudaStream_t st) {
   const int nt = 128;
-  const int npair = b->nsh_max * b->nsh_max;
+  const int npair = b->nsh_l_max[LI] * b->nsh_l_max[LJ];
+  if (npair == 0) return 0;
   for (int m0 = 0; m0 < b->nb; m0 += kMaxGridY) {
     dim3 grid((npair + nt - 1) / nt, b->nb - m0 < kMaxGridY ? b->nb - m0 : kMaxGridY);
     k_grad_pair<LI, LJ><<<grid, nt, 0, st>>>(*b, pos, cn, P, W, v, pairbuf, m0);

@@ -45,6 +45,8 @@ typedef struct xtb_batch {
   int32_t nspecies;                   /* unique elements in the shard */
   int32_t ncgto;                      /* rows of the cgto table */
   int32_t has_xb;                     /* 1: some atom has a non-zero halogen-bond strength (Br, I, At with "hal" not excluded) */
+  int32_t nsh_l_max[4];               /* maxima over the shard of the number of s / p / d shells of a molecule ([3] unused): size the
+                                         (l_i, l_j) class launches of the integral / gradient pair kernels, empty classes are skipped */
   int64_t mat_total, gam_total, eeq_total; /* host copies of mat_off[nb], gam_off[nb], eeq_off[nb] */
   const int32_t* at_off;  /* [nb+1] */
   const int32_t* sh_off;  /* [nb+1] */
