@@ -177,6 +177,100 @@ __device__ void gemm_tn_sym(int ne, int n, const double* __restrict__ L, const d
   __syncthreads();
 }
 
+// Operand of gemm_small: element (k, m) at p[k * sk + m * sm] (either orientation of a row-major matrix, any offset).
+struct Operand {
+  const double* p;
+  int sk, sm;
+};
+
+// Out(i, j) = sum_{k < K} L(k, i) R(k, j) for i < M, j < N on the fp64 tensor cores: one warp per (8 TM) x (8 TN) tile,
+// out-of-range operand elements are zero, results are handed to st(i, j, value).  With leading dimensions == 4 (mod 8)
+// row-major operands are bank-conflict free in both orientations.  Operands are (pointer, strides) so that a k step is a
+// pointer increment and the row / column predicates are loop invariant: the first version took element lambdas and spent
+// ~29 instructions per k step (index arithmetic rematerialised at the 128-register cap) for 2 DMMAs.  No trailing barrier.
+template <int TM, int TN, class ST>
+__device__ __forceinline__ void gemm_small(int M, int N, int K, Operand L, Operand R, ST st) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, tg = lane & 3;
+  const int mt = (M + 8 * TM - 1) / (8 * TM), nt = (N + 8 * TN - 1) / (8 * TN);
+  const int stepl = 4 * L.sk, stepr = 4 * R.sk;
+  const int kmain = K & ~3;
+  for (int t = warp; t < mt * nt; t += NT / 32) {
+    const int ti = t / nt, tj = t - ti * nt;
+    const int i0 = ti * 8 * TM, j0 = tj * 8 * TN;
+    const double* pa[TM];
+    const double* pb[TN];
+    bool va[TM], vb[TN];
+#pragma unroll
+    for (int x = 0; x < TM; ++x) {
+      const int i = i0 + 8 * x + g;
+      va[x] = i < M;
+      pa[x] = L.p + (va[x] ? i : 0) * L.sm + tg * L.sk;
+    }
+#pragma unroll
+    for (int y = 0; y < TN; ++y) {
+      const int j = j0 + 8 * y + g;
+      vb[y] = j < N;
+      pb[y] = R.p + (vb[y] ? j : 0) * R.sm + tg * R.sk;
+    }
+    double d[TM][TN][2];
+#pragma unroll
+    for (int x = 0; x < TM; ++x)
+#pragma unroll
+      for (int y = 0; y < TN; ++y) d[x][y][0] = d[x][y][1] = 0.0;
+#pragma unroll 4
+    for (int k0 = 0; k0 < kmain; k0 += 4) {  // unrolled: the operand loads of four k steps are in flight together
+      double a[TM], b[TN];
+#pragma unroll
+      for (int x = 0; x < TM; ++x) {
+        const double v = *pa[x];
+        a[x] = va[x] ? v : 0.0;
+        pa[x] += stepl;
+      }
+#pragma unroll
+      for (int y = 0; y < TN; ++y) {
+        const double v = *pb[y];
+        b[y] = vb[y] ? v : 0.0;
+        pb[y] += stepr;
+      }
+#pragma unroll
+      for (int x = 0; x < TM; ++x)
+#pragma unroll
+        for (int y = 0; y < TN; ++y) dmma884(d[x][y][0], d[x][y][1], a[x], b[y]);
+    }
+    if (kmain < K) {  // last, partial k step
+      const bool kv = kmain + tg < K;
+      double a[TM], b[TN];
+#pragma unroll
+      for (int x = 0; x < TM; ++x) a[x] = (kv && va[x]) ? *pa[x] : 0.0;
+#pragma unroll
+      for (int y = 0; y < TN; ++y) b[y] = (kv && vb[y]) ? *pb[y] : 0.0;
+#pragma unroll
+      for (int x = 0; x < TM; ++x)
+#pragma unroll
+        for (int y = 0; y < TN; ++y) dmma884(d[x][y][0], d[x][y][1], a[x], b[y]);
+    }
+#pragma unroll
+    for (int x = 0; x < TM; ++x)
+#pragma unroll
+      for (int y = 0; y < TN; ++y) {
+        const int i = i0 + 8 * x + g, j = j0 + 8 * y + 2 * tg;
+        if (i < M) {
+          if (j < N) st(i, j, d[x][y][0]);
+          if (j + 1 < N) st(i, j + 1, d[x][y][1]);
+        }
+      }
+  }
+}
+
+// p, marked as a shared-memory pointer when SH (address-space conversion round trip: a definition, not an assumption --
+// XTB_ASSUME_SHARED on the pointers of subspace_density made nvcc 12.9 drop the function as unreachable).
+template <bool SH, class T>
+__device__ __forceinline__ T* in_shared(T* p) {
+  if (SH) return (T*)__cvta_shared_to_generic(__cvta_generic_to_shared(p));
+  return p;
+}
+
 #ifndef XTB_DEFER_NBP_MAX
 #define XTB_DEFER_NBP_MAX 16
 #endif
@@ -939,15 +1033,17 @@ XTB_CTX_FN void potential_lin(Ctx& c, const double* __restrict__ y, const double
   __syncthreads();
 }
 
-// Buffers of the response solver: C (eigenvectors, untouched), X = C^T (set up once), A (work), and two matrices in the
-// global workspace: SC = S C (set up once) and G2 (GEMM output).  With A_w = -1/2 (diag(w) S + S diag(w)):
+// Buffers of the response solver: C (eigenvectors, untouched), X = S C (set up once; the operand of both contractions of an
+// application, so it lives next to C -- in shared memory in the shared-memory variant), A (work), and one matrix in the global
+// workspace (G2: temporary of the two back-transformations at the end).  With A_w = -1/2 (diag(w) S + S diag(w)):
 //     At = C^T A_w C = -1/2 (M + M^T),   M = C^T diag(w) (S C)                       -- ONE weighted GEMM
-//     chi w = -diag(Z S) = -rowdot(C Zt, S C)                                         -- ONE GEMM (X^T-contraction) + row dots
+//     chi w = -diag(Z S) = -rowdot(C Zt, S C)                                         -- ONE GEMM with the row dots in its epilogue
 // i.e. 2 GEMMs per application of chi instead of 4 GEMMs + 2 transposes; the full Z / ZW matrices (2 more GEMMs each) are
-// only formed once at the end.
+// only formed once at the end.  (Until round 2b S C and the product C Zt lived in the global workspace and X held C^T: an
+// application cost ~100 k cycles, most of it L2 latency of the GEMM operand S C and of the C Zt round trip.)
 struct RespBuf {
-  double* SC;  // [mu][q]  (global workspace)
-  double* G2;  // GEMM output (global workspace)
+  double* SC;  // unused since round 2b (S C is kept in the X buffer); the workspace region stays reserved
+  double* G2;  // GEMM temporary / row-dot partial sums (global workspace)
 };
 
 // A <- Zt (WMAT = false) or ZWt (WMAT = true) of the perturbation w, in the eigenvector basis
@@ -956,7 +1052,7 @@ XTB_CTX_FN void response_zt(Ctx& c, const RespBuf& rb, const double* __restrict_
                             const double* __restrict__ fp1) {
   const int n = c.n, ne = c.ne, ld = c.ld;
   constexpr bool AS = MODE != 0, CS = MODE == 1;
-  gemm_tn<CS, false, true>(ne, n, c.C, rb.SC, ld, c.A, ld, ne, w);  // M[i][j] = sum_{mu < n} w_mu C[mu][i] SC[mu][j]
+  gemm_tn<CS, CS, true>(ne, n, c.C, c.X, ld, c.A, ld, ne, w);  // M[i][j] = sum_{mu < n} w_mu C[mu][i] SC[mu][j]   (X = S C)
   // Fermi-level shift per spin channel: abar_s = sum_k f'_s(k) At_kk / sum_k f'_s(k),  At_kk = -M_kk
   double s0 = 0.0, s1 = 0.0, n0 = 0.0, n1 = 0.0;
   for (int k = threadIdx.x; k < n; k += NT) {
@@ -996,35 +1092,94 @@ XTB_CTX_FN void response_zt(Ctx& c, const RespBuf& rb, const double* __restrict_
   (void)AS;
 }
 
-// out[mu] = add[mu] + chi w = add[mu] - sum_q (C Zt)[mu][q] SC[mu][q]
+// out[mu] = add[mu] + chi w = add[mu] - sum_q (C Zt)[mu][q] SC[mu][q]: the product C Zt is never stored -- every 16 x 16 tile
+// is multiplied with its tile of S C in registers and reduced along q (two shuffles over the four lanes of a row); the
+// per-tile-column partial sums are added in a fixed order (deterministic: get_forces and autograd.grad stay bit-equal).
 template <int MODE>
 XTB_CTX_FN void response_charges(Ctx& c, const RespBuf& rb, const double* __restrict__ w, const double* __restrict__ fp0,
                                  const double* __restrict__ fp1, const double* __restrict__ add, double* __restrict__ out) {
-  const int n = c.n, ne = c.ne, ld = c.ld;
+  const int n = c.n, ld = c.ld;
   constexpr bool AS = MODE != 0, CS = MODE == 1;
   response_zt<MODE, false>(c, rb, w, fp0, fp1);
-  gemm_tn<CS, AS>(ne, ne, c.X, c.A, ld, rb.G2, ld, ne);  // G2[mu][q] = sum_p C^T[p][mu] Zt[p][q]
-  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-  for (int mu = wp; mu < n; mu += NT / 32) {
-    const double* gr = rb.G2 + (size_t)mu * ld;
-    const double* sr = rb.SC + (size_t)mu * ld;
+  const double* __restrict__ C = in_shared<CS>(c.C);
+  const double* __restrict__ Zt = in_shared<AS>(c.A);
+  const double* __restrict__ SC = in_shared<CS>(c.X);
+  double* part = MODE == 1 ? in_shared<true>(c.jq) : rb.G2;  // [tile column][mu]; MODE 1: ne^2 / 16 <= 20 ne doubles of Jacobi scratch
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, tg = lane & 3;
+  const int nt = (n + 15) >> 4, kmain = n & ~3;
+  for (int t = warp; t < nt * nt; t += NT / 32) {
+    const int ti = t / nt, tj = t - ti * nt;
+    const int i0 = ti << 4, j0 = tj << 4;
+    // (C Zt)[mu][q] = sum_p C[mu][p] Zt[p][q]: A operand C[mu][p] (row major in mu), B operand Zt[p][q]
+    const bool va0 = i0 + g < n, va1 = i0 + 8 + g < n, vb0 = j0 + g < n, vb1 = j0 + 8 + g < n;
+    const double* pa0 = C + (size_t)(va0 ? i0 + g : 0) * ld + tg;
+    const double* pa1 = C + (size_t)(va1 ? i0 + 8 + g : 0) * ld + tg;
+    const double* pb0 = Zt + (size_t)tg * ld + (vb0 ? j0 + g : 0);
+    const double* pb1 = Zt + (size_t)tg * ld + (vb1 ? j0 + 8 + g : 0);
+    double d[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+#pragma unroll 4
+    for (int k0 = 0; k0 < kmain; k0 += 4) {
+      const double x0 = *pa0, x1 = *pa1, y0 = *pb0, y1 = *pb1;
+      const double a0 = va0 ? x0 : 0.0, a1 = va1 ? x1 : 0.0, b0 = vb0 ? y0 : 0.0, b1 = vb1 ? y1 : 0.0;
+      pa0 += 4; pa1 += 4; pb0 += 4 * ld; pb1 += 4 * ld;
+      dmma884(d[0][0][0], d[0][0][1], a0, b0);
+      dmma884(d[0][1][0], d[0][1][1], a0, b1);
+      dmma884(d[1][0][0], d[1][0][1], a1, b0);
+      dmma884(d[1][1][0], d[1][1][1], a1, b1);
+    }
+    if (kmain < n) {
+      const bool kv = kmain + tg < n;
+      const double a0 = (kv && va0) ? *pa0 : 0.0, a1 = (kv && va1) ? *pa1 : 0.0;
+      const double b0 = (kv && vb0) ? *pb0 : 0.0, b1 = (kv && vb1) ? *pb1 : 0.0;
+      dmma884(d[0][0][0], d[0][0][1], a0, b0);
+      dmma884(d[0][1][0], d[0][1][1], a0, b1);
+      dmma884(d[1][0][0], d[1][0][1], a1, b0);
+      dmma884(d[1][1][0], d[1][1][1], a1, b1);
+    }
+#pragma unroll
+    for (int x = 0; x < 2; ++x) {
+      const int mu = i0 + 8 * x + g;
+      double sacc = 0.0;
+      if (mu < n) {
+#pragma unroll
+        for (int y = 0; y < 2; ++y) {
+          const int q = j0 + 8 * y + 2 * tg;
+          const double* sr = SC + (size_t)mu * ld + q;
+          if (q < n) sacc = fma(d[x][y][0], sr[0], sacc);
+          if (q + 1 < n) sacc = fma(d[x][y][1], sr[1], sacc);
+        }
+      }
+      sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+      sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+      if (tg == 0 && mu < n) part[(size_t)tj * c.ne + mu] = sacc;
+    }
+  }
+  __syncthreads();
+  for (int mu = threadIdx.x; mu < n; mu += NT) {
     double acc = 0.0;
-    for (int q = lane; q < n; q += 32) acc = fma(gr[q], sr[q], acc);
-    acc = warp_sum(acc);
-    if (lane == 0) out[mu] = (add ? add[mu] : 0.0) - acc;
+    for (int tj = 0; tj < nt; ++tj) acc += part[(size_t)tj * c.ne + mu];
+    out[mu] = (add ? add[mu] : 0.0) - acc;
   }
   __syncthreads();
 }
 
-// A <- Z_w (or ZW_w) in the AO basis: Z = C Zt C^T
+// A <- Z_w (or ZW_w) in the AO basis: Z = C Zt C^T (temporary in the global workspace; twice per single point)
 template <int MODE, bool WMAT>
 XTB_CTX_FN void response_density(Ctx& c, const RespBuf& rb, const double* __restrict__ w, const double* __restrict__ fp0,
                                  const double* __restrict__ fp1) {
-  const int ne = c.ne, ld = c.ld;
+  const int n = c.n, ld = c.ld;
   constexpr bool AS = MODE != 0, CS = MODE == 1;
   response_zt<MODE, WMAT>(c, rb, w, fp0, fp1);
-  gemm_tn<AS, CS>(ne, ne, c.A, c.X, ld, rb.G2, ld, ne);     // G2[q][mu] = sum_p Zt[p][q] C^T[p][mu]
-  gemm_tn<false, CS>(ne, ne, rb.G2, c.X, ld, c.A, ld, ne);  // Z[mu][nu] = sum_q G2[q][mu] C^T[q][nu]
+  const double* C = in_shared<CS>(c.C);
+  double* A = in_shared<AS>(c.A);
+  double* G2 = rb.G2;
+  // G2[q][mu] = sum_p Zt[p][q] C[mu][p]
+  gemm_small<2, 2>(n, n, n, Operand{A, ld, 1}, Operand{C, 1, ld}, [&](int q, int mu, double v) { G2[(size_t)q * ld + mu] = v; });
+  __syncthreads();
+  // Z[mu][nu] = sum_q G2[q][mu] C[nu][q]
+  gemm_small<2, 2>(n, n, n, Operand{G2, ld, 1}, Operand{C, 1, ld}, [&](int mu, int nu, double v) { A[(size_t)mu * ld + nu] = v; });
+  __syncthreads();
 }
 
 // Runs after the final solve and after P, W were written: adds Z_u, ZW_u to Pm, Wm and writes v_out + K y / y_sh.
@@ -1065,18 +1220,15 @@ XTB_CTX_FN void scf_response(Ctx& c, const xtb_scf_opts& o, const RespBuf& rb, c
 #ifdef XTB_PROFILE_PHASES
   const long long tr0 = clock64();
   int nit = 0;
+  c.tr1 = c.tr2 = c.tr3 = 0;  // (re-used: the subspace split was printed before)
 #endif
-  // set-up: SC = S C (global), X = C^T
+  // set-up: X = S C
   for (int t = threadIdx.x; t < ne * ld; t += NT) {
     const int i = t / ld, j = t - i * ld;
     c.A[t] = (i < n && j < n) ? c.S[(size_t)i * n + j] : 0.0;
   }
-  for (int t = threadIdx.x; t < ne * ne; t += NT) {
-    const int k = t / ne, i = t - k * ne;
-    c.X[(size_t)k * ld + i] = c.C[(size_t)i * ld + k];
-  }
   __syncthreads();
-  gemm_tn<AS, CS>(ne, ne, c.A, c.C, ld, rb.SC, ld, ne);  // SC[mu][q] = sum_nu S[nu][mu] C[nu][q]
+  gemm_tn<AS, CS>(ne, ne, c.A, c.C, ld, c.X, ld, ne);  // SC[mu][q] = sum_nu S[nu][mu] C[nu][q]
 
   response_charges<MODE>(c, rb, dv, fp0, fp1, nullptr, z0);
   potential_lin(c, z0, qat_final, c.v);  // w0 = K z0
@@ -1086,25 +1238,45 @@ XTB_CTX_FN void scf_response(Ctx& c, const xtb_scf_opts& o, const RespBuf& rb, c
   Mixer mx;
   mx.step = 0; mx.head = 0;
   for (int it = 0; it < kResponseMaxIter; ++it) {
+#ifdef XTB_PROFILE_PHASES
+    const long long ta0 = clock64();
+#endif
     response_charges<MODE>(c, rb, c.v, fp0, fp1, z0, y);  // y = z0 + chi w
+#ifdef XTB_PROFILE_PHASES
+    const long long ta1 = clock64();
+#endif
     potential_lin(c, y, qat_final, c.vnew);               // g(w) = K y; leaves y_sh in c.qsh
+#ifdef XTB_PROFILE_PHASES
+    const long long ta2 = clock64();
+    c.tr1 += ta1 - ta0; c.tr2 += ta2 - ta1;
+#endif
     double res = 0.0;
     for (int k = threadIdx.x; k < n; k += NT) res = fmax(res, fabs(c.vnew[k] - c.v[k]));
     res = block_max(res, c.red);
     __syncthreads();
 #ifdef XTB_PROFILE_PHASES
     ++nit;
+#ifdef XTB_DEBUG_SUBSPACE
     if (threadIdx.x == 0 && blockIdx.x == 0) printf("  response it %d: residual %.3e\n", it, res);
+#endif
 #endif
     if (res < kResponseTol) {
       for (int k = threadIdx.x; k < n; k += NT) c.v[k] = c.vnew[k];
       __syncthreads();
       break;
     }
+#ifdef XTB_PROFILE_PHASES
+    const long long ta3 = clock64();
+#endif
     mix(c, mx, o2, sm_theta);
+#ifdef XTB_PROFILE_PHASES
+    c.tr3 += clock64() - ta3;
+#endif
   }
 #ifdef XTB_PROFILE_PHASES
-  if (threadIdx.x == 0 && blockIdx.x == 0) printf("  response: %d applications in the loop, %lld cycles so far\n", nit, clock64() - tr0);
+  if (threadIdx.x == 0 && blockIdx.x == 0)
+    printf("  response: %d applications in the loop, %lld cycles so far (in the loop: chi w %lld, K y %lld, mixer %lld)\n", nit, clock64() - tr0, c.tr1,
+           c.tr2, c.tr3);
 #endif
   for (int k = threadIdx.x; k < c.ns; k += NT) y_sh[k] = c.qsh[k];
   for (int k = threadIdx.x; k < n; k += NT) {

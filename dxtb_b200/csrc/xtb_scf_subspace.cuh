@@ -24,100 +24,6 @@
 
 namespace {
 
-// Operand of gemm_small: element (k, m) at p[k * sk + m * sm] (either orientation of a row-major matrix, any offset).
-struct Operand {
-  const double* p;
-  int sk, sm;
-};
-
-// Out(i, j) = sum_{k < K} L(k, i) R(k, j) for i < M, j < N on the fp64 tensor cores: one warp per (8 TM) x (8 TN) tile,
-// out-of-range operand elements are zero, results are handed to st(i, j, value).  With leading dimensions == 4 (mod 8)
-// row-major operands are bank-conflict free in both orientations.  Operands are (pointer, strides) so that a k step is a
-// pointer increment and the row / column predicates are loop invariant: the first version took element lambdas and spent
-// ~29 instructions per k step (index arithmetic rematerialised at the 128-register cap) for 2 DMMAs.  No trailing barrier.
-template <int TM, int TN, class ST>
-__device__ __forceinline__ void gemm_small(int M, int N, int K, Operand L, Operand R, ST st) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int g = lane >> 2, tg = lane & 3;
-  const int mt = (M + 8 * TM - 1) / (8 * TM), nt = (N + 8 * TN - 1) / (8 * TN);
-  const int stepl = 4 * L.sk, stepr = 4 * R.sk;
-  const int kmain = K & ~3;
-  for (int t = warp; t < mt * nt; t += NT / 32) {
-    const int ti = t / nt, tj = t - ti * nt;
-    const int i0 = ti * 8 * TM, j0 = tj * 8 * TN;
-    const double* pa[TM];
-    const double* pb[TN];
-    bool va[TM], vb[TN];
-#pragma unroll
-    for (int x = 0; x < TM; ++x) {
-      const int i = i0 + 8 * x + g;
-      va[x] = i < M;
-      pa[x] = L.p + (va[x] ? i : 0) * L.sm + tg * L.sk;
-    }
-#pragma unroll
-    for (int y = 0; y < TN; ++y) {
-      const int j = j0 + 8 * y + g;
-      vb[y] = j < N;
-      pb[y] = R.p + (vb[y] ? j : 0) * R.sm + tg * R.sk;
-    }
-    double d[TM][TN][2];
-#pragma unroll
-    for (int x = 0; x < TM; ++x)
-#pragma unroll
-      for (int y = 0; y < TN; ++y) d[x][y][0] = d[x][y][1] = 0.0;
-#pragma unroll 4
-    for (int k0 = 0; k0 < kmain; k0 += 4) {  // unrolled: the operand loads of four k steps are in flight together
-      double a[TM], b[TN];
-#pragma unroll
-      for (int x = 0; x < TM; ++x) {
-        const double v = *pa[x];
-        a[x] = va[x] ? v : 0.0;
-        pa[x] += stepl;
-      }
-#pragma unroll
-      for (int y = 0; y < TN; ++y) {
-        const double v = *pb[y];
-        b[y] = vb[y] ? v : 0.0;
-        pb[y] += stepr;
-      }
-#pragma unroll
-      for (int x = 0; x < TM; ++x)
-#pragma unroll
-        for (int y = 0; y < TN; ++y) dmma884(d[x][y][0], d[x][y][1], a[x], b[y]);
-    }
-    if (kmain < K) {  // last, partial k step
-      const bool kv = kmain + tg < K;
-      double a[TM], b[TN];
-#pragma unroll
-      for (int x = 0; x < TM; ++x) a[x] = (kv && va[x]) ? *pa[x] : 0.0;
-#pragma unroll
-      for (int y = 0; y < TN; ++y) b[y] = (kv && vb[y]) ? *pb[y] : 0.0;
-#pragma unroll
-      for (int x = 0; x < TM; ++x)
-#pragma unroll
-        for (int y = 0; y < TN; ++y) dmma884(d[x][y][0], d[x][y][1], a[x], b[y]);
-    }
-#pragma unroll
-    for (int x = 0; x < TM; ++x)
-#pragma unroll
-      for (int y = 0; y < TN; ++y) {
-        const int i = i0 + 8 * x + g, j = j0 + 8 * y + 2 * tg;
-        if (i < M) {
-          if (j < N) st(i, j, d[x][y][0]);
-          if (j + 1 < N) st(i, j + 1, d[x][y][1]);
-        }
-      }
-  }
-}
-
-// p, marked as a shared-memory pointer when SH (address-space conversion round trip: a definition, not an assumption --
-// XTB_ASSUME_SHARED on the pointers of subspace_density made nvcc 12.9 drop the function as unreachable).
-template <bool SH, class T>
-__device__ __forceinline__ T* in_shared(T* p) {
-  if (SH) return (T*)__cvta_shared_to_generic(__cvta_generic_to_shared(p));
-  return p;
-}
-
 // Block-wide maxima of two values with one pair of barriers (`red` holds 32 doubles; at most 16 warps).
 __device__ __forceinline__ void block_max2(double& a, double& b, double* red) {
   static_assert(NT <= 512, "block_max2 assumes at most 16 warps");
