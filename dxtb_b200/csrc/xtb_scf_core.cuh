@@ -1049,10 +1049,11 @@ struct RespBuf {
 // A <- Zt (WMAT = false) or ZWt (WMAT = true) of the perturbation w, in the eigenvector basis
 template <int MODE, bool WMAT>
 XTB_CTX_FN void response_zt(Ctx& c, const RespBuf& rb, const double* __restrict__ w, const double* __restrict__ fp0,
-                            const double* __restrict__ fp1) {
+                            const double* __restrict__ fp1, bool have_m = false) {
   const int n = c.n, ne = c.ne, ld = c.ld;
   constexpr bool AS = MODE != 0, CS = MODE == 1;
-  gemm_tn<CS, CS, true>(ne, n, c.C, c.X, ld, c.A, ld, ne, w);  // M[i][j] = sum_{mu < n} w_mu C[mu][i] SC[mu][j]   (X = S C)
+  // M[i][j] = sum_{mu < n} w_mu C[mu][i] SC[mu][j]   (X = S C); have_m: the caller has put M into the A buffer already
+  if (!have_m) gemm_tn<CS, CS, true>(ne, n, c.C, c.X, ld, c.A, ld, ne, w);
   // Fermi-level shift per spin channel: abar_s = sum_k f'_s(k) At_kk / sum_k f'_s(k),  At_kk = -M_kk
   double s0 = 0.0, s1 = 0.0, n0 = 0.0, n1 = 0.0;
   for (int k = threadIdx.x; k < n; k += NT) {
@@ -1164,21 +1165,31 @@ XTB_CTX_FN void response_charges(Ctx& c, const RespBuf& rb, const double* __rest
   __syncthreads();
 }
 
-// A <- Z_w (or ZW_w) in the AO basis: Z = C Zt C^T (temporary in the global workspace; twice per single point)
+// A <- Z_w (or ZW_w) in the AO basis, Z = C Zt C^T.  Called twice at the end with the SAME perturbation (Z, then ZW): the
+// two only differ in the occupation factors applied to M, so M is computed once (first call: saved to the global G2; second
+// call: reloaded) and the X buffer, whose S C is no longer needed once M exists, is the temporary of the back-transformation.
 template <int MODE, bool WMAT>
 XTB_CTX_FN void response_density(Ctx& c, const RespBuf& rb, const double* __restrict__ w, const double* __restrict__ fp0,
                                  const double* __restrict__ fp1) {
-  const int n = c.n, ld = c.ld;
+  const int n = c.n, ne = c.ne, ld = c.ld;
   constexpr bool AS = MODE != 0, CS = MODE == 1;
-  response_zt<MODE, WMAT>(c, rb, w, fp0, fp1);
+  if (!WMAT) {
+    gemm_tn<CS, CS, true>(ne, n, c.C, c.X, ld, c.A, ld, ne, w);
+    for (int t = threadIdx.x; t < ne * ld; t += NT) rb.G2[t] = c.A[t];
+  } else {
+    __syncthreads();
+    for (int t = threadIdx.x; t < ne * ld; t += NT) c.A[t] = rb.G2[t];
+    __syncthreads();
+  }
+  response_zt<MODE, WMAT>(c, rb, w, fp0, fp1, true);
   const double* C = in_shared<CS>(c.C);
   double* A = in_shared<AS>(c.A);
-  double* G2 = rb.G2;
-  // G2[q][mu] = sum_p Zt[p][q] C[mu][p]
-  gemm_small<2, 2>(n, n, n, Operand{A, ld, 1}, Operand{C, 1, ld}, [&](int q, int mu, double v) { G2[(size_t)q * ld + mu] = v; });
+  double* T = in_shared<CS>(c.X);
+  // T[q][mu] = sum_p Zt[p][q] C[mu][p]
+  gemm_small<2, 2>(n, n, n, Operand{A, ld, 1}, Operand{C, 1, ld}, [&](int q, int mu, double v) { T[(size_t)q * ld + mu] = v; });
   __syncthreads();
-  // Z[mu][nu] = sum_q G2[q][mu] C[nu][q]
-  gemm_small<2, 2>(n, n, n, Operand{G2, ld, 1}, Operand{C, 1, ld}, [&](int mu, int nu, double v) { A[(size_t)mu * ld + nu] = v; });
+  // Z[mu][nu] = sum_q T[q][mu] C[nu][q]
+  gemm_small<2, 2>(n, n, n, Operand{T, ld, 1}, Operand{C, 1, ld}, [&](int mu, int nu, double v) { A[(size_t)mu * ld + nu] = v; });
   __syncthreads();
 }
 
