@@ -1096,6 +1096,7 @@ extern "C" int xtb_scf_run_large(const xtb_batch* b, const xtb_scf_opts* o, int3
     }
   };
   // ---- occupied-subspace solve of the intermediate map evaluations (host-driven; see xtb_scf_subspace.cuh) ----------------
+  static const bool debug = getenv("DXTB_B200_DEBUG_LARGE") != nullptr;  // developer printout of the certificate / fixed point
   struct {
     bool eligible, layout, xvalid, zvalid, ctvalid;
     int no, nv, nop, nvp, ko, kv;
@@ -1162,7 +1163,7 @@ extern "C" int xtb_scf_run_large(const xtb_batch* b, const xtb_scf_opts* o, int3
       const double rmax = hs.sub_rmax - kSubBias, xmax = hs.sub_xmax - kSubBias;
       if (!(xmax < 1.0) || !(rmax < 1.0e200)) return 0;
       const double rate = it > 0 ? fmin(0.5, 2.0 * rmax / rprev) : 1.0;
-      if (getenv("DXTB_B200_DEBUG_LARGE")) fprintf(stderr, "    riccati it %d: max|R| %.3e max|X| %.3e\n", it, rmax, xmax);
+      if (debug) fprintf(stderr, "    riccati it %d: max|R| %.3e max|X| %.3e\n", it, rmax, xmax);
       if (rmax * rate <= o->subspace_tol) { *ok = true; return 0; }
       if (it >= 2 && rmax > 2.0 * rprev) return 0;
       rprev = rmax;
@@ -1218,7 +1219,6 @@ extern "C" int xtb_scf_run_large(const xtb_batch* b, const xtb_scf_opts* o, int3
     gemm(C, X, A, ne);  // A = C^T X
     kl_symmetrize<<<ew_grid, 256, 0, st>>>(A, n, ne);
     bool fast = false, diagonal = false;
-    static const bool debug = getenv("DXTB_B200_DEBUG_LARGE") != nullptr;  // developer printout
     if (!final_solve && sb.eligible) {
       // Jacobi sweeps only until the gap between the diagonal blocks is certified, then the Riccati fixed point
       for (int sweeps_here = 0;;) {

@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""Developer tool: one caffeine conformer pair through a -DXTB_PROFILE_PHASES build (DXTB_B200_LIB=...), kernel variant forced by argv[1]."""
+"""Developer tool: two conformers of a molecule (argv[2], default caffeine) through a developer build of the library
+(DXTB_B200_LIB=..., built with DXTB_B200_NVCC_FLAGS="-DXTB_PROFILE_PHASES -DXTB_DEBUG_SUBSPACE": cycle split, certified gap per
+sweep, residual of every fixed-point / response iteration for block 0); kernel variant forced by argv[1] (-1: default)."""
 import sys
 from pathlib import Path
 import numpy as np, torch
