@@ -219,8 +219,9 @@ class _SinglePoint(torch.autograd.Function):
         if ge.numel() != d.nb:
             ge = ge.expand(d.nb).contiguous()
         grad = torch.empty((d.nat_tot, 3), dtype=torch.float64, device=d.device)
-        dedcn = torch.empty(d.nat_tot, dtype=torch.float64, device=d.device)
-        pairbuf = torch.empty(4 * int(d.struct.gam_total), dtype=torch.float64, device=d.device)
+        # pure scratch of xtb_grad_bwd (per-pair slots, dE/dCN): kept on the calculator like the SCF workspace
+        dedcn = _scratch_buffer(calc._scratch, "dedcn", d.nat_tot, d.device)
+        pairbuf = _scratch_buffer(calc._scratch, "pairbuf", 4 * int(d.struct.gam_total), d.device)
         resp = ctx.resp
         v_ptr = resp.data_ptr() if resp is not None else v_orb.data_ptr()
         y_ptr = resp.data_ptr() + 8 * d.nao_tot if resp is not None else None
