@@ -226,6 +226,39 @@ XTB_CTX_FN double fcn(Ctx& c, const double* __restrict__ v, const xtb_scf_opts& 
   return g;
 }
 
+__host__ __device__ inline int64_t vec_smem_bytes(int64_t nao_max, int64_t nsx, int64_t nax, bool v_global) {
+  const int64_t nmx = nao_max + 2;
+  int64_t d = 2 * (nmx + (nmx & 1)) + 8 * nmx + 2 * nsx + nax + 32 + 36 + (nmx + 2) / 2 + 1;
+  d += d & 1;
+  const int64_t nbpx = (nao_max + 15) / 16;
+  d += (v_global && nbpx <= XTB_DEFER_NBP ? 2 : 1) * nbpx * JB2 * QLD + (nbpx < NGRP ? nbpx : NGRP) * JB2 * MLD;  // block-Jacobi scratch
+  d += d & 1;
+  return d * 8;
+}
+
+// vectors + Jacobi scratch + the matrices the mode keeps in shared memory
+__host__ __device__ inline int64_t mode_smem_base(int mode, int64_t nao_max, int64_t nsx, int64_t nax) {
+  const int64_t nex = (nao_max + 15) & ~15;
+  const int64_t nmat = mode == 1 ? 3 : mode == 2 ? 1 : 0;
+  return vec_smem_bytes(nao_max, nsx, nax, mode != 1) + nmat * nex * (nex + 4) * 8;
+}
+
+// Hybrid / global-memory variants: scratch of the occupied-subspace solve (T = A(:, v) X, n x lds with no <= ne / 2; afterwards
+// the Newton iterates) in shared memory behind everything else, when it fits -- the operands of the small GEMMs then come from
+// shared memory instead of L2 (the fixed point was 27 % of the capsaicin single point with T and X in the workspace).
+__host__ __device__ inline int64_t sub_scratch_bytes(int mode, int64_t nao_max, int64_t nsx, int64_t nax) {
+  if (mode == 1) return 0;
+  const int64_t nex = (nao_max + 15) & ~15;
+  const int64_t ldsx = ((nex / 2 + 15) & ~15) + 4;
+  const int64_t ext = nex * ldsx * 8;
+  return mode_smem_base(mode, nao_max, nsx, nax) + ext <= XTB_SMEM_LIMIT ? ext : 0;
+}
+
+// dynamic shared memory of a launch
+__host__ __device__ inline int64_t mode_smem_bytes(int mode, int64_t nao_max, int64_t nsx, int64_t nax) {
+  return mode_smem_base(mode, nao_max, nsx, nax) + sub_scratch_bytes(mode, nao_max, nsx, nax);
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(NT, XTB_MINB)
 k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, const double* __restrict__ H0,
@@ -330,11 +363,15 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
     // ((no + nv) lds <= n (n + 19)).  MODE 1 must never see the workspace pointer here: an address-space hint on X
     // propagates to EVERY source of the pointer (with a select between the two nvcc treated the whole workspace region, Zg
     // included, as shared memory: memcheck "invalid __shared__ write").
+    sb.T = c.X;
     if (MODE == 1) {
       sb.X = c.jq;
       if (sb.nv * sb.lds > jcap) sb.eligible = false;
     } else {
-      sb.X = persist + (size_t)sb.no * sb.lds;
+      // hybrid / global-memory variants: X in the Jacobi scratch when it fits (no address-space hints on it in these
+      // variants), T behind the carve-up when the launch reserved it (sub_scratch_bytes)
+      sb.X = sb.nv * sb.lds <= jcap ? c.jq : persist + (size_t)sb.no * sb.lds;
+      if (sub_scratch_bytes(MODE, lnao, lnsh, lnat) > 0) sb.T = sm + mode_smem_base(MODE, lnao, lnsh, lnat) / 8;
     }
   }
 
@@ -434,23 +471,6 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
       scf_response<MODE>(c, o, rb, v_orb + c.o0, q_at + c.a0, Pm, Wm, resp + c.o0, resp + b.nao_tot + c.s0, sm_theta);
     }
   }
-}
-
-int64_t vec_smem_bytes(int64_t nao_max, int64_t nsx, int64_t nax, bool v_global) {
-  const int64_t nmx = nao_max + 2;
-  int64_t d = 2 * (nmx + (nmx & 1)) + 8 * nmx + 2 * nsx + nax + 32 + 36 + (nmx + 2) / 2 + 1;
-  d += d & 1;
-  const int64_t nbpx = (nao_max + 15) / 16;
-  d += (v_global && nbpx <= XTB_DEFER_NBP ? 2 : 1) * nbpx * JB2 * QLD + (nbpx < NGRP ? nbpx : NGRP) * JB2 * MLD;  // block-Jacobi scratch
-  d += d & 1;
-  return d * 8;
-}
-
-// dynamic shared memory of a launch: vectors + Jacobi scratch + the matrices the mode keeps in shared memory
-int64_t mode_smem_bytes(int mode, int64_t nao_max, int64_t nsx, int64_t nax) {
-  const int64_t nex = (nao_max + 15) & ~15;
-  const int64_t nmat = mode == 1 ? 3 : mode == 2 ? 1 : 0;
-  return vec_smem_bytes(nao_max, nsx, nax, mode != 1) + nmat * nex * (nex + 4) * 8;
 }
 
 #define XTB_SCF_ARGS                                                                                                              \

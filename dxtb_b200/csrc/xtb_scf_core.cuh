@@ -35,6 +35,7 @@ struct Subspace {
   int no, nv, lds; // occupied / virtual orbitals, leading dimension of the no-column matrices (== 4 mod 16)
   double gapmin;   // certified HOMO-LUMO gap required for integer occupations
   double* X;       // [nv][lds] graph of the occupied subspace in the basis C (shared Jacobi scratch or workspace)
+  double* T;       // scratch of the fixed point / Newton iterates: the X buffer, or shared memory behind the carve-up (MODE 0 / 2)
   double* Zg;      // [no][lds] workspace copy of Z
   int nfast, nric, nnewt;  // diagnostics: map evaluations on this path, fixed-point / Newton iterations
 };

@@ -117,7 +117,7 @@ template <int MODE>
 XTB_CTX_FN bool subspace_riccati(Ctx& c, const xtb_scf_opts& o) {
   const int n = c.n, ld = c.ld, no = c.sub.no, nv = c.sub.nv, lds = c.sub.lds;
   const double* __restrict__ A = in_shared<MODE != 0>(c.A);
-  double* __restrict__ T = in_shared<MODE == 1>(c.X);
+  double* __restrict__ T = in_shared<MODE == 1>(MODE == 1 ? c.X : c.sub.T);
   double* __restrict__ X = in_shared<MODE == 1>(c.sub.X);
   const double* __restrict__ dg = in_shared<true>(c.eps);
   if (!c.sub.xvalid) {
@@ -191,7 +191,7 @@ XTB_CTX_FN double* subspace_density(Ctx& c) {
   const double* __restrict__ X = in_shared<CS>(c.sub.X);
   double* G = in_shared<AS>(c.A);
   double* E = G + (size_t)no * lds;
-  double* Zc = in_shared<CS>(c.X);
+  double* Zc = in_shared<CS>(MODE == 1 ? c.X : c.sub.T);  // (T is free once the fixed point has converged)
   double* Zn = Zc + (size_t)no * lds;
   // G = 1 + X^T X
   gemm_small<1, 1>(no, no, nv, Operand{X, lds, 1}, Operand{X, lds, 1},

@@ -175,6 +175,7 @@ int64_t xtb_scf_smem_bytes_for(int32_t nao_max, int32_t nsh_max, int32_t nat_max
    launch has at least 1.5 molecules per SM and this is at most XTB_SMEM_2CTA (measured slower in round 2; off by default). */
 int64_t xtb_scf_smem_bytes_mode(int32_t mode, int32_t nao_max, int32_t nsh_max, int32_t nat_max);
 #define XTB_SMEM_2CTA (113 * 1024)
+#define XTB_SMEM_LIMIT (227 * 1024) /* per-CTA opt-in shared memory on sm_100 */
 
 /* The whole SCF (scf/iterator.py:51-144, scf/unrolling/default.py:71-136, scf/base.py:651-907,
  * mixer/anderson.py:163-317, wavefunction/filling.py:201-366): one CTA per molecule, no host round-trips.
