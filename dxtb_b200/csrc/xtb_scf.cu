@@ -417,9 +417,10 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
       for (int k = threadIdx.x; k < n; k += NT) c.v[k] = c.vnew[k];
       __syncthreads();
     }
-    // one Newton-Schulz step on the Cholesky start basis, and again before the solve that defines the results (removes the
-    // drift of the accumulated rotations)
-    if (stage != 1) reorthonormalize<MODE>(c);
+    // one Newton-Schulz step before the solve that defines the results: the Cholesky start basis is S-orthonormal only to
+    // cond(S) eps and the accumulated rotations drift (defect 1e-13 .. 1e-10: irrelevant for the intermediate charges, squared
+    // by the step)
+    if (stage == 2 || o.maxiter <= 0) reorthonormalize<MODE>(c);
     g = fcn<MODE>(c, c.v, o, nel_a, nel_b, final_solve ? o.jacobi_tol : o.jacobi_tol_iter, final_solve);
     if (stage != 2) ++iters;
     if (final_solve) break;

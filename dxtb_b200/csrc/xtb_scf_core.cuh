@@ -189,15 +189,26 @@ struct Operand {
 // row-major operands are bank-conflict free in both orientations.  Operands are (pointer, strides) so that a k step is a
 // pointer increment and the row / column predicates are loop invariant: the first version took element lambdas and spent
 // ~29 instructions per k step (index arithmetic rematerialised at the 128-register cap) for 2 DMMAs.  No trailing barrier.
-template <int TM, int TN, class ST>
+// SYM (M == N, TM == TN, symmetric result): only the tiles on and below the diagonal are computed; st decides what to mirror.
+template <int TM, int TN, bool SYM = false, class ST>
 __device__ __forceinline__ void gemm_small(int M, int N, int K, Operand L, Operand R, ST st) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, tg = lane & 3;
   const int mt = (M + 8 * TM - 1) / (8 * TM), nt = (N + 8 * TN - 1) / (8 * TN);
   const int stepl = 4 * L.sk, stepr = 4 * R.sk;
   const int kmain = K & ~3;
-  for (int t = warp; t < mt * nt; t += NT / 32) {
-    const int ti = t / nt, tj = t - ti * nt;
+  const int ntile = SYM ? mt * (mt + 1) / 2 : mt * nt;
+  for (int t = warp; t < ntile; t += NT / 32) {
+    int ti, tj;
+    if (SYM) {
+      ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+      while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+      while (ti * (ti + 1) / 2 > t) --ti;
+      tj = t - ti * (ti + 1) / 2;
+    } else {
+      ti = t / nt;
+      tj = t - ti * nt;
+    }
     const int i0 = ti * 8 * TM, j0 = tj * 8 * TN;
     const double* pa[TM];
     const double* pb[TN];

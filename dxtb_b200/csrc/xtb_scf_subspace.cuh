@@ -250,7 +250,12 @@ XTB_CTX_FN double* subspace_density(Ctx& c) {
   __syncthreads();
   // P[mu][nu] = 2 sum_k Wt[k][mu] Yt[k][nu]  -> X buffer (Z is dead)
   double* Pb = in_shared<CS>(c.X);
-  gemm_small<2, 2>(n, n, no, Operand{Wt, ld, 1}, Operand{Yt, ld, 1}, [&](int mu, int nu, double v) { Pb[(size_t)mu * ld + nu] = 2.0 * v; });
+  gemm_small<2, 2, true>(n, n, no, Operand{Wt, ld, 1}, Operand{Yt, ld, 1}, [&](int mu, int nu, double v) {
+    if (mu >= nu) {  // lower tiles computed, mirrored: P exactly symmetric
+      Pb[(size_t)mu * ld + nu] = 2.0 * v;
+      Pb[(size_t)nu * ld + mu] = 2.0 * v;
+    }
+  });
   __syncthreads();
   return Pb;
 }
