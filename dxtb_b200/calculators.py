@@ -474,7 +474,7 @@ class GFN1Calculator:
         s.x_atol, s.x_atol_max = float(o["x_atol"]), float(o["x_atol_max"])
         s.kt = float(o["fermi_etemp"]) * self.par.KELVIN2AU  # scf/base.py:291
         s.fermi_thresh = math.sqrt(torch.finfo(torch.float64).eps) if o["fermi_thresh"] is None else float(o["fermi_thresh"])
-        s.jacobi_tol = 1e-13
+        s.jacobi_tol = float(os.environ.get("DXTB_B200_JACOBI_TOL", "1e-13"))  # final solve: max |off-diagonal| (developer knob)
         # intermediate map evaluations: eigensolver residual 4 orders below the SCF convergence threshold
         s.jacobi_tol_iter = min(2e-9, max(s.jacobi_tol, 1e-4 * min(s.x_atol, s.x_atol_max)))
         # occupied-subspace solve of the intermediate iterations (DXTB_B200_SUBSPACE=0: developer A/B switch)
