@@ -614,7 +614,7 @@ def run_ours(args) -> None:
             "scf_iterations_mean": float(it.mean()),
             "eigensolver": {"jacobi_sweeps_mean": float((calc.cache["status"] >> 8).double().mean()),
                             "occupied_subspace_path": bool(calc.opts["scf_subspace"]),
-                            "note": "intermediate iterations of closed-shell molecules with a certified gap >= 60 kT solve for the occupied "
+                            "note": "intermediate iterations of closed-shell molecules with a certified gap >= 50 kT solve for the occupied "
                                     "subspace (Riccati fixed point) instead of diagonalising; the roofline convention still counts the "
                                     "reference's 10 n^3 per map evaluation, so `achieved` is algorithmic, not executed, flops"},
             "per_rank_ms": {"step_and_scf_kernel": per_rank, "systems": [len(p) for p in parts]},
