@@ -55,7 +55,7 @@ class XtbScfOpts(C.Structure):
         ("x_atol", C.c_double), ("x_atol_max", C.c_double), ("kt", C.c_double), ("fermi_thresh", C.c_double),
         ("jacobi_tol", C.c_double), ("jacobi_tol_iter", C.c_double), ("subspace_tol", C.c_double), ("subspace_gap", C.c_double),
         ("mol_list", _vp), ("list_len", C.c_int32), ("list_nao_max", C.c_int32), ("list_nsh_max", C.c_int32),
-        ("list_nat_max", C.c_int32),
+        ("list_nat_max", C.c_int32), ("persistent", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 

@@ -174,6 +174,7 @@ class _SinglePoint(torch.autograd.Function):
             o.use_smem = bk["use_smem"] if calc._use_smem_override is None else calc._use_smem_override
             o.mol_list, o.list_len = bk["list"].data_ptr(), bk["len"]
             o.list_nao_max, o.list_nsh_max, o.list_nat_max = bk["nao"], bk["nsh"], bk["nat"]
+            o.persistent = 1 if bk["uniform"] and calc._warm_start else 0
             _abi.check(
                 lib.xtb_scf_run(
                     d.ptr, _abi.C.addressof(o), ws.S.data_ptr(), ws.H0.data_ptr(), ws.gamma.data_ptr(), nel_ab.data_ptr(),
@@ -323,6 +324,7 @@ class GFN1Calculator:
         self.scf_event_pool: list = []
         self._use_smem_override: int | None = None  # tests: force the global-memory variant
         self._scratch: dict = {}  # call-local device scratch kept between single points (_scratch_buffer)
+        self._warm_start = os.environ.get("DXTB_B200_WARM_START", "1") != "0"  # developer A/B switch (xtb_scf_opts.persistent)
         self._prefer_hybrid = os.environ.get("DXTB_B200_PREFER_HYBRID", "0") != "0"
         self._large_min_nao = int(os.environ.get("DXTB_B200_LARGE_MIN_NAO", "1000000"))
         # up to this many molecules with nao >= 256 take the large-system path (several at a time, _run_large): measured on a
@@ -394,6 +396,9 @@ class GFN1Calculator:
                 "use_smem": use_smem,
                 "list": torch.from_numpy(idx.astype(np.int32)).to(self.device),
                 "len": int(idx.size), "nao": int(d.nao[idx].max()), "nsh": int(d.nsh[idx].max()), "nat": int(d.nat[idx].max()),
+                # equally sized molecules (conformer batches): persistent CTAs with the eigenvector warm start between molecules
+                "uniform": bool(d.nao[idx].min() == d.nao[idx].max() and d.nsh[idx].min() == d.nsh[idx].max()
+                                and d.nat[idx].min() == d.nat[idx].max()),
                 "mols": [int(i) for i in idx] if use_smem == 3 else None,
             })
         return buckets

@@ -53,6 +53,57 @@ XTB_CTX_FN void reorthonormalize(Ctx& c) {
   gemm_tn<CS, AS>(ne, ne, c.X, c.A, ld, c.C, ld, ne);  // C = C M
 }
 
+// Start basis of a molecule from the final eigenvectors of the previous molecule of this CTA (persistent launch over a batch
+// of equally sized molecules, i.e. conformers): C_prev is S_prev-orthonormal; Newton-Schulz steps C <- C (3/2 - 1/2 C^T S C)
+// make it S-orthonormal for the new overlap (defect 0.03 for 0.05 bohr perturbations: 0.03 -> 7e-4 -> 4e-7 -> 1e-13).  In that
+// basis the first projected Fock matrix is nearly diagonal, the gap certificate holds after 1-2 Jacobi sweeps instead of 4-5.
+// Returns false (C is garbage then: the caller falls back to the Cholesky start basis) if the first defect is >= 1/2 -- a
+// different molecule with the same dimensions, or an overlap that is not positive definite -- or after 6 steps.
+template <int MODE>
+XTB_CTX_FN bool warm_start_basis(Ctx& c, const double* __restrict__ prevC) {
+  const int n = c.n, ne = c.ne, ld = c.ld;
+  constexpr bool AS = MODE != 0, CS = MODE == 1;
+  if (prevC != c.C) {  // hybrid / global variants: every molecule has its own matrices in the workspace
+    for (int t = threadIdx.x; t < ne * ld; t += NT) c.C[t] = prevC[t];
+    __syncthreads();
+  }
+  for (int it = 0; it < 6; ++it) {
+    for (int t = threadIdx.x; t < ne * ld; t += NT) {
+      const int i = t / ld, j = t - i * ld;
+      c.A[t] = (i < n && j < n) ? c.S[(size_t)i * n + j] : 0.0;
+    }
+    __syncthreads();
+    gemm_tn<AS, CS>(ne, ne, c.A, c.C, ld, c.X, ld, ne);  // X = S C
+    gemm_tn<CS, CS>(ne, ne, c.C, c.X, ld, c.A, ld, ne);  // A = C^T S C
+    double defect = 0.0;
+    for (int t = threadIdx.x; t < n * n; t += NT) {
+      const int i = t / n, j = t - i * n;
+      defect = fmax(defect, fabs(c.A[(size_t)i * ld + j] - (i == j ? 1.0 : 0.0)));
+    }
+    defect = block_max(defect, c.red);
+    __syncthreads();
+    if (!(defect < 0.5)) return false;
+    if (defect < 1e-12) return true;
+    for (int t = threadIdx.x; t < ne * ne; t += NT) {
+      const int i = t / ne, j = t - i * ne;
+      if (i <= j) {
+        const double g = 0.5 * (c.A[(size_t)i * ld + j] + c.A[(size_t)j * ld + i]);
+        const double m = (i == j ? 1.5 : 0.0) - 0.5 * g;
+        c.A[(size_t)i * ld + j] = m;
+        c.A[(size_t)j * ld + i] = m;
+      }
+    }
+    for (int t = threadIdx.x; t < ne * ne; t += NT) {
+      const int k = t / ne, i = t - k * ne;
+      c.X[(size_t)k * ld + i] = c.C[(size_t)i * ld + k];  // X = C^T
+    }
+    __syncthreads();
+    gemm_tn<CS, AS>(ne, ne, c.X, c.A, ld, c.C, ld, ne);  // C = C M
+    if (defect < 1e-6) return true;  // the step squares the defect: no need to measure it again
+  }
+  return false;
+}
+
 // A = C^T F C with F = H0 - 1/2 S o (v_i + v_j), exactly symmetric, pad rows / columns exactly zero (X buffer: F C).
 template <int MODE>
 XTB_CTX_FN void build_projected_fock(Ctx& c, const double* __restrict__ v) {
@@ -268,7 +319,13 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
       int32_t* __restrict__ iterations, int32_t* __restrict__ status, double* __restrict__ Pout, double* __restrict__ Wout,
       double* __restrict__ resp) {
   extern __shared__ double sm[];
-  const int m = o.mol_list ? o.mol_list[blockIdx.x] : (int)blockIdx.x;
+  // one molecule per CTA, or (o.persistent: equally sized molecules, gridDim.x = number of SMs) a fixed-stride walk over the
+  // list with the eigenvector warm start between consecutive molecules of the CTA (warm_start_basis)
+  const int nslot = o.mol_list ? o.list_len : b.nb;
+  int prev_n = -1;
+  const double* prev_c = nullptr;
+  for (int slot = blockIdx.x; slot < nslot; slot += gridDim.x) {
+  const int m = o.mol_list ? o.mol_list[slot] : slot;
   const int lnao = o.mol_list ? o.list_nao_max : b.nao_max, lnsh = o.mol_list ? o.list_nsh_max : b.nsh_max,
             lnat = o.mol_list ? o.list_nat_max : b.nat_max;
   Ctx c;
@@ -385,7 +442,8 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
 #ifdef XTB_PROFILE_PHASES
   const long long tc0 = clock64();
 #endif
-  if (!cholesky_start_basis<MODE>(c)) c.status |= XTB_STATUS_S_NOT_POSDEF;
+  const bool warm = o.persistent != 0 && prev_n == n && warm_start_basis<MODE>(c, prev_c);
+  if (!warm && !cholesky_start_basis<MODE>(c)) c.status |= XTB_STATUS_S_NOT_POSDEF;
 #ifdef XTB_PROFILE_PHASES
   if (threadIdx.x == 0 && blockIdx.x == 0) printf("   Cholesky start basis %lld\n", clock64() - tc0);
 #endif
@@ -472,6 +530,10 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
       scf_response<MODE>(c, o, rb, v_orb + c.o0, q_at + c.a0, Pm, Wm, resp + c.o0, resp + b.nao_tot + c.s0, sm_theta);
     }
   }
+  prev_n = n;
+  prev_c = c.C;  // the final eigenvectors (untouched by the P / W output and by the response solver)
+  __syncthreads();
+  }  // molecules of this CTA
 }
 
 #define XTB_SCF_ARGS                                                                                                              \
@@ -492,8 +554,14 @@ int launch_mode(XTB_SCF_ARGS) {
     if (e != cudaSuccess) return (int)e;
     configured[dev] = smem;
   }
-  k_scf<MODE><<<nblocks, NT, (size_t)smem, st>>>(*b, *o, S, H0, gamma, nel_ab, q0_at, work, q_orb, q_sh, q_at, v_orb, e_atom, fenergy, emo,
-                                                  occ, iterations, status, P, W, resp);
+  int grid = nblocks;
+  if (o->persistent) {  // one CTA per SM (the kernel occupies a whole SM: 512 threads x 128 registers)
+    int n_sm = 0;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sm > 0 && grid > n_sm * XTB_MINB) grid = n_sm * XTB_MINB;
+  }
+  k_scf<MODE><<<grid, NT, (size_t)smem, st>>>(*b, *o, S, H0, gamma, nel_ab, q0_at, work, q_orb, q_sh, q_at, v_orb, e_atom, fenergy, emo,
+                                               occ, iterations, status, P, W, resp);
   return launch_status();
 }
 

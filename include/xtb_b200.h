@@ -112,6 +112,11 @@ typedef struct xtb_scf_opts {
    * list_*_max are the maxima over the bucket (they size the shared-memory layout). */
   const int32_t* mol_list;
   int32_t list_len, list_nao_max, list_nsh_max, list_nat_max;
+  /* 1: the launch is a batch of equally sized molecules (conformers): one persistent CTA per SM walks the list with a fixed
+   * stride and starts every molecule after its first from the eigenvectors of the previous one, re-orthonormalised against the
+   * new overlap (Newton-Schulz), instead of the Cholesky start basis -- the first solve then needs 1-2 Jacobi sweeps, not 4-5.
+   * Results are those of the Cholesky start to solver tolerance (same iteration counts); falls back per molecule. */
+  int32_t persistent, reserved0;
 } xtb_scf_opts;
 
 /* status bits written per molecule by xtb_scf_run */
