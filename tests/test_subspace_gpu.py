@@ -91,3 +91,25 @@ def test_subspace_path_on_the_large_system_path(mols, monkeypatch):
         assert np.abs(a["e"] - b["e"]).max() < 1e-10
         assert np.abs(a["g"] - b["g"]).max() < 1e-8
         assert a["sweeps"].mean() < 0.6 * b["sweeps"].mean(), (a["sweeps"].mean(), b["sweeps"].mean())
+
+
+def test_persistent_launch_with_eigenvector_warm_start(mols, monkeypatch):
+    """More molecules than SMs in a uniform bucket: persistent CTAs start every molecule after their first from the previous
+    molecule's eigenvectors (xtb_scf_opts.persistent).  Against one CTA per molecule with the Cholesky start
+    basis: identical iteration counts, energies 1e-11 Eh, forces 1e-9, fewer sweeps; and the launch is deterministic."""
+    dev = _dev()
+    nb = 2 * torch.cuda.get_device_properties(dev).multi_processor_count + 17
+    m = mols["caffeine"]
+    numbers = torch.tensor(m["numbers"])[None].expand(nb, -1).contiguous().to(dev)
+    chrg = torch.zeros(nb, dtype=torch.float64, device=dev)
+    pos = torch.from_numpy(_conformers(np.array(m["positions"]), nb, 3)).to(dev)
+    a = _run(numbers, pos, chrg, {"exclude": ["disp"]}, dev)
+    a2 = _run(numbers, pos, chrg, {"exclude": ["disp"]}, dev)
+    monkeypatch.setenv("DXTB_B200_WARM_START", "0")
+    b = _run(numbers, pos, chrg, {"exclude": ["disp"]}, dev)
+    assert (a["status"] == 0).all() and (b["status"] == 0).all()
+    assert np.array_equal(a["it"], b["it"])
+    assert np.abs(a["e"] - b["e"]).max() < 1e-11
+    assert np.abs(a["g"] - b["g"]).max() < 1e-9
+    assert a["sweeps"].mean() < b["sweeps"].mean() - 0.5
+    assert np.array_equal(a["e"], a2["e"]) and np.array_equal(a["g"], a2["g"])  # fixed-stride walk: same bits every time
