@@ -41,6 +41,23 @@ if which in ("all", "global"):
     run(["nicotine", "H2O"], override=0)                            # variant 0 (forced)
 if which in ("all", "large"):
     run(["H2O", "caffeine"], DXTB_B200_LARGE_MIN_NAO=1)            # variant 3 (two molecules in flight on host threads)
+if which in ("all", "persistent"):
+    # more equally sized molecules than SMs: persistent CTAs + eigenvector warm start (round 2b)
+    import numpy as np
+    nsm = torch.cuda.get_device_properties(dev).multi_processor_count
+    m = mols["nicotine"]
+    nb = nsm + 12
+    rng = np.random.default_rng(0)
+    pos = torch.from_numpy(np.array(m["positions"])[None] + rng.normal(0.0, 0.05, size=(nb, len(m["numbers"]), 3))).to(dev).requires_grad_(True)
+    calc = GFN1Calculator(torch.tensor(m["numbers"])[None].expand(nb, -1).contiguous().to(dev),
+                          opts={"exclude": ["disp"], "maxiter": int(os.environ.get("SAN_MAXITER", "3"))}, device=dev, dtype=torch.float64)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        e = calc.get_energy(p := pos, torch.zeros(nb, dtype=torch.float64, device=dev))
+    (g,) = torch.autograd.grad(e.sum(), p)
+    torch.cuda.synchronize()
+    print("nicotine x", nb, calc._variants, round(float(e.sum()), 6), "sweeps", float((calc.cache["status"] >> 8).float().mean()))
 if which in ("all", "halogen"):
     # halogen-bond energy + gradient, SCF response on a converged-enough state (round 2)
     sys.path.insert(0, str(ROOT / "tests"))
