@@ -445,7 +445,7 @@ k_scf(const xtb_batch b, const xtb_scf_opts o, const double* __restrict__ S, con
   const bool warm = o.persistent != 0 && prev_n == n && warm_start_basis<MODE>(c, prev_c);
   if (!warm && !cholesky_start_basis<MODE>(c)) c.status |= XTB_STATUS_S_NOT_POSDEF;
 #ifdef XTB_PROFILE_PHASES
-  if (threadIdx.x == 0 && blockIdx.x == 0) printf("   Cholesky start basis %lld\n", clock64() - tc0);
+  if (threadIdx.x == 0 && blockIdx.x == 0) printf("   start basis (%s) %lld\n", warm ? "warm start: Newton-Schulz on the previous eigenvectors" : "Cholesky", clock64() - tc0);
 #endif
 
   // guess: atomic charges spread equally over shells, then over the AOs of a shell (scf/guess.py:122-182)
